@@ -1,0 +1,257 @@
+"""ctypes view of ``libfqd_b200.so`` (``include/fqd_b200.h``): the one place the Python
+host code meets the C ABI.  No torch, no numpy-side arithmetic: arrays are only handed
+over as pointers.
+
+The library is loaded from this directory (in-tree build, ``fastqdedup_b200/build.py``).
+There is no CPU fallback: if the library is missing ``load()`` raises, and if no CUDA
+device is usable every compute call raises ``FqdCudaError``.
+"""
+import ctypes
+import os
+from ctypes import (POINTER, Structure, byref, c_char_p, c_double, c_float, c_int, c_int32,
+                    c_size_t, c_uint8, c_uint32, c_uint64, c_void_p)
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libfqd_b200.so")
+
+FQD_OK = 0
+ERR_ARG, ERR_PHRED, ERR_CUDA, ERR_NOMEM, ERR_LOOKUP, ERR_UNSUPPORTED, ERR_NCCL = range(1, 8)
+MEM_HOST, MEM_DEVICE = 0, 1
+METHODS = {"highest_count": 0, "adjacency": 1, "directional": 2}
+
+
+class FqdError(RuntimeError):
+    pass
+
+
+class FqdCudaError(FqdError):
+    pass
+
+
+class FqdPhredError(ValueError):
+    """Byte outside '!'..'~' in a quality string (reference _fastqmodule.c:65-70)."""
+
+    def __init__(self, msg, record=None, char=None):
+        super().__init__(msg)
+        self.record = record
+        self.char = char
+
+
+class ClusterJob(Structure):
+    _fields_ = [
+        ("n_records", c_uint64),
+        ("keys", c_void_p), ("key_offsets", c_void_p), ("key_lengths", c_void_p),
+        ("key_stride", c_uint32), ("key_length", c_uint32),
+        ("quals", c_void_p), ("qual_offsets", c_void_p), ("qual_lengths", c_void_p),
+        ("qual_stride", c_uint32), ("qual_length", c_uint32),
+        ("max_distance", c_int32), ("use_edit_distance", c_int32),
+        ("method", c_int32), ("memory_space", c_int32),
+        ("max_average_error_rate", c_double),
+        ("phred_offset", c_uint8), ("reserved", c_uint8 * 7),
+        ("alphabet", c_char_p),
+        ("record_counts", c_void_p),
+    ]
+
+
+class ClusterStats(Structure):
+    _fields_ = [
+        ("total_records", c_uint64), ("discarded_records", c_uint64),
+        ("number_of_sequences", c_uint64), ("number_of_uniques", c_uint64),
+        ("number_of_clusters", c_uint64), ("number_selected", c_uint64),
+        ("candidate_pairs", c_uint64), ("bad_record", c_uint64),
+        ("bad_char", c_uint32), ("key_bits", c_uint32), ("key_words", c_uint32),
+        ("n_passes", c_uint32),
+        ("ms_total", c_float), ("ms_ingest", c_float), ("ms_gather", c_float),
+        ("ms_neighbour", c_float), ("ms_select", c_float), ("ms_h2d", c_float),
+        ("ms_compare", c_float), ("reserved_f", c_float),
+    ]
+
+    def as_dict(self):
+        return {name: getattr(self, name) for name, _ in self._fields_ if name != "reserved_f"}
+
+
+# every symbol include/fqd_b200.h declares (tests/test_abi.py checks the library exports them)
+EXPORTS = [
+    "fqd_last_error", "fqd_device_count", "fqd_context_create", "fqd_context_destroy",
+    "fqd_default_context", "fqd_device_alloc", "fqd_device_free", "fqd_device_upload",
+    "fqd_device_download", "fqd_context_synchronize", "fqd_host_alloc", "fqd_host_free",
+    "fqd_cluster", "fqd_cluster_fetch", "fqd_cluster_fetch_selected",
+    "fqd_average_error_rate", "fqd_within_distance",
+    "fqd_trie_new", "fqd_trie_free", "fqd_trie_add_sequence", "fqd_trie_contains_sequence",
+    "fqd_trie_pop_cluster", "fqd_trie_cluster_item", "fqd_trie_number_of_sequences",
+    "fqd_trie_alphabet", "fqd_trie_memory_size", "fqd_trie_raw_stats",
+]
+
+_lib = None
+
+
+def load():
+    """Load the native library; fails loudly when it was never built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise FqdError(f"{LIB_PATH} is missing: build it with `python -m fastqdedup_b200.build` "
+                       "(the CUDA path has no Python/CPU fallback)")
+    lib = ctypes.CDLL(LIB_PATH)
+    lib.fqd_last_error.restype = c_char_p
+    lib.fqd_device_count.restype = c_int
+    lib.fqd_context_create.argtypes = [c_int, POINTER(c_void_p)]
+    lib.fqd_context_destroy.argtypes = [c_void_p]
+    lib.fqd_context_destroy.restype = None
+    lib.fqd_default_context.argtypes = [POINTER(c_void_p)]
+    lib.fqd_device_alloc.argtypes = [c_void_p, c_size_t, POINTER(c_void_p)]
+    lib.fqd_device_free.argtypes = [c_void_p, c_void_p]
+    lib.fqd_device_upload.argtypes = [c_void_p, c_void_p, c_void_p, c_size_t]
+    lib.fqd_device_download.argtypes = [c_void_p, c_void_p, c_void_p, c_size_t]
+    lib.fqd_context_synchronize.argtypes = [c_void_p]
+    lib.fqd_host_alloc.argtypes = [c_size_t, POINTER(c_void_p)]
+    lib.fqd_host_free.argtypes = [c_void_p]
+    lib.fqd_cluster.argtypes = [c_void_p, POINTER(ClusterJob), POINTER(ClusterStats), c_void_p]
+    lib.fqd_cluster_fetch.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
+    lib.fqd_cluster_fetch_selected.argtypes = [c_void_p, c_void_p]
+    lib.fqd_average_error_rate.argtypes = [c_void_p, c_void_p, c_void_p, c_uint64, c_uint8,
+                                           c_void_p, POINTER(c_uint64), POINTER(c_uint32)]
+    lib.fqd_within_distance.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                        c_uint64, c_int32, c_int32, c_void_p]
+    _lib = lib
+    return lib
+
+
+def check(rc, stats=None):
+    if rc == FQD_OK:
+        return
+    msg = load().fqd_last_error().decode("latin-1")
+    if rc == ERR_PHRED:
+        raise FqdPhredError(msg, None if stats is None else stats.bad_record,
+                            None if stats is None else stats.bad_char)
+    if rc == ERR_ARG:
+        raise ValueError(msg)
+    if rc == ERR_NOMEM:
+        raise MemoryError(msg)
+    if rc == ERR_LOOKUP:
+        raise LookupError(msg)
+    if rc == ERR_UNSUPPORTED:
+        raise NotImplementedError(msg)
+    if rc == ERR_CUDA:
+        raise FqdCudaError(msg)
+    raise FqdError(msg)
+
+
+class Context:
+    """One GPU context (stream + memory pool + last result)."""
+
+    def __init__(self, device=0):
+        self.lib = load()
+        h = c_void_p()
+        check(self.lib.fqd_context_create(int(device), byref(h)))
+        self.handle = h
+        self.device = device
+
+    def close(self):
+        if self.handle:
+            self.lib.fqd_context_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- device buffers (inputs resident in HBM) ----
+    def device_alloc(self, nbytes):
+        p = c_void_p()
+        check(self.lib.fqd_device_alloc(self.handle, nbytes, byref(p)))
+        return p.value
+
+    def device_free(self, ptr):
+        check(self.lib.fqd_device_free(self.handle, c_void_p(ptr)))
+
+    def upload(self, array):
+        array = np.ascontiguousarray(array)
+        ptr = self.device_alloc(array.nbytes)
+        check(self.lib.fqd_device_upload(self.handle, c_void_p(ptr), array.ctypes.data, array.nbytes))
+        return ptr
+
+    def download(self, ptr, nbytes, dtype=np.uint8):
+        out = np.empty(nbytes // np.dtype(dtype).itemsize, dtype=dtype)
+        check(self.lib.fqd_device_download(self.handle, out.ctypes.data, c_void_p(ptr), nbytes))
+        return out
+
+    def synchronize(self):
+        check(self.lib.fqd_context_synchronize(self.handle))
+
+    # ---- the batched job ----
+    def cluster(self, job, keep_bitmap_ptr=None):
+        stats = ClusterStats()
+        rc = self.lib.fqd_cluster(self.handle, byref(job), byref(stats),
+                                  c_void_p(keep_bitmap_ptr) if keep_bitmap_ptr else None)
+        check(rc, stats)
+        return stats
+
+    def fetch(self, n_uniques):
+        first = np.empty(n_uniques, dtype=np.uint64)
+        count = np.empty(n_uniques, dtype=np.uint32)
+        label = np.empty(n_uniques, dtype=np.uint64)
+        sel = np.empty(n_uniques, dtype=np.uint8)
+        check(self.lib.fqd_cluster_fetch(self.handle, first.ctypes.data, count.ctypes.data,
+                                         label.ctypes.data, sel.ctypes.data))
+        return first, count, label, sel
+
+    def fetch_selected(self, n_selected):
+        idx = np.empty(n_selected, dtype=np.uint64)
+        check(self.lib.fqd_cluster_fetch_selected(self.handle, idx.ctypes.data))
+        return idx
+
+    # ---- function-level entry points ----
+    def average_error_rate(self, strings, phred_offset=33):
+        flat, off = _flatten(strings)
+        out = np.empty(len(strings), dtype=np.float64)
+        bad_i, bad_c = c_uint64(), c_uint32()
+        rc = self.lib.fqd_average_error_rate(self.handle, flat.ctypes.data, off.ctypes.data,
+                                             len(strings), phred_offset, out.ctypes.data,
+                                             byref(bad_i), byref(bad_c))
+        if rc == ERR_PHRED:
+            raise FqdPhredError(self.lib.fqd_last_error().decode("latin-1"), bad_i.value, bad_c.value)
+        check(rc)
+        return out
+
+    def within_distance(self, a_strings, b_strings, max_distance, use_edit_distance=False):
+        a, ao = _flatten(a_strings)
+        b, bo = _flatten(b_strings)
+        out = np.empty(len(a_strings), dtype=np.uint8)
+        check(self.lib.fqd_within_distance(self.handle, a.ctypes.data, ao.ctypes.data,
+                                           b.ctypes.data, bo.ctypes.data, len(a_strings),
+                                           int(max_distance), int(bool(use_edit_distance)),
+                                           out.ctypes.data))
+        return out.astype(bool)
+
+
+def _flatten(strings):
+    lens = np.fromiter((len(s) for s in strings), dtype=np.uint64, count=len(strings))
+    off = np.zeros(len(strings) + 1, dtype=np.uint64)
+    np.cumsum(lens, out=off[1:])
+    joined = b"".join(strings)
+    flat = np.frombuffer(joined, dtype=np.uint8) if joined else np.zeros(1, dtype=np.uint8)
+    return flat, off
+
+
+_default = None
+
+
+def default_context():
+    """Process-wide context on the device the library picks ($FQD_DEVICE / $LOCAL_RANK / 0);
+    the same one the CPython shims use."""
+    global _default
+    if _default is None:
+        lib = load()
+        h = c_void_p()
+        check(lib.fqd_default_context(byref(h)))
+        ctx = Context.__new__(Context)
+        ctx.lib, ctx.handle, ctx.device = lib, h, None
+        ctx.close = lambda: None      # owned by the library
+        _default = ctx
+    return _default

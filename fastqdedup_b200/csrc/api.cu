@@ -1,0 +1,493 @@
+// api.cu -- C ABI entry points of libfqd_b200.so (include/fqd_b200.h): context and
+// memory plumbing, the batched clustering job and the function-level entry points that
+// mirror _fastq.average_error_rate and _distance.within_distance.
+#include <string.h>
+
+#include <stdlib.h>
+
+#include <algorithm>
+#include <mutex>
+
+#include "common.h"
+
+namespace fqd {
+
+static thread_local char g_error[512] = "";
+
+void set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_error, sizeof g_error, fmt, ap);
+    va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char *what, const char *file, int line)
+{
+    const char *base = strrchr(file, '/');
+    set_error("CUDA error %s (%s) at %s:%d in %s", cudaGetErrorName(e), cudaGetErrorString(e),
+              base ? base + 1 : file, line, what);
+    cudaGetLastError();
+    return e == cudaErrorMemoryAllocation ? FQD_ERR_NOMEM : FQD_ERR_CUDA;
+}
+
+int dev_alloc(fqd_context *ctx, size_t bytes, void **p)
+{
+    *p = nullptr;
+    FQD_CUDA(cudaMallocAsync(p, bytes, ctx->pool, ctx->stream));
+    return FQD_OK;
+}
+
+void dev_free(fqd_context *ctx, void *p)
+{
+    if (p) cudaFreeAsync(p, ctx->stream);
+}
+
+// Build the symbol coding for an alphabet (bytes in first-seen order, like the
+// reference's Alphabet, _triemodule.c:32-67).  Codes are dense; rank is ASCII order + 1
+// with PAD = 0 so that a proper prefix sorts first.
+static int make_codec(const std::vector<uint8_t> &alphabet, bool varlen, Codec *c)
+{
+    memset(c->lut, 0xFF, sizeof c->lut);
+    memset(c->rank, 0, sizeof c->rank);
+    const int n = (int)alphabet.size();
+    const int codes = n + (varlen ? 1 : 0);
+    int need = 1;
+    while ((1 << need) < codes) need++;
+    const int bits = supported_bits(need);
+    if (!bits) {
+        set_error("alphabet of %d symbols is too large for this build", n);
+        return FQD_ERR_UNSUPPORTED;
+    }
+    std::vector<uint8_t> sorted(alphabet);
+    std::sort(sorted.begin(), sorted.end());
+    for (int i = 0; i < n; i++) {
+        c->lut[alphabet[i]] = (uint8_t)i;
+        const int r = (int)(std::lower_bound(sorted.begin(), sorted.end(), alphabet[i]) - sorted.begin());
+        c->rank[i] = (uint8_t)std::min(255, r + 1);
+    }
+    c->pad_code = (uint8_t)std::min(255, n);   // only meaningful when varlen
+    c->bits = (uint8_t)bits;
+    c->n_symbols = (uint8_t)std::min(255, n);
+    c->varlen = varlen ? 1 : 0;
+    if (varlen && n >= (1 << bits)) {
+        set_error("alphabet of %d symbols plus PAD does not fit %d bits", n, bits);
+        return FQD_ERR_UNSUPPORTED;
+    }
+    return FQD_OK;
+}
+
+static int check_device(fqd_context *ctx)
+{
+    if (!ctx) { set_error("null context"); return FQD_ERR_ARG; }
+    FQD_CUDA(cudaSetDevice(ctx->device));
+    return FQD_OK;
+}
+
+}  // namespace fqd
+
+using namespace fqd;
+
+extern "C" {
+
+const char *fqd_last_error(void) { return g_error; }
+
+int fqd_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int fqd_context_create(int device_ordinal, fqd_context **out)
+{
+    if (!out) { set_error("null output pointer"); return FQD_ERR_ARG; }
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        set_error("no usable CUDA device (%s): fastqdedup_b200 has no CPU fallback",
+                  e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+        return FQD_ERR_CUDA;
+    }
+    if (device_ordinal < 0 || device_ordinal >= n) {
+        set_error("device ordinal %d out of range (0..%d)", device_ordinal, n - 1);
+        return FQD_ERR_ARG;
+    }
+    fqd_context *ctx = new fqd_context();
+    ctx->device = device_ordinal;
+    FQD_CUDA(cudaSetDevice(device_ordinal));
+    FQD_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    cudaMemPoolProps props{};
+    props.allocType = cudaMemAllocationTypePinned;
+    props.handleTypes = cudaMemHandleTypeNone;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = device_ordinal;
+    FQD_CUDA(cudaMemPoolCreate(&ctx->pool, &props));
+    uint64_t threshold = UINT64_MAX;   // keep freed blocks cached between jobs
+    FQD_CUDA(cudaMemPoolSetAttribute(ctx->pool, cudaMemPoolAttrReleaseThreshold, &threshold));
+    FQD_CUDA(cudaMalloc(&ctx->d_ctr, sizeof(DevCounters)));
+    FQD_CUDA(cudaHostAlloc(&ctx->h_ctr, sizeof(DevCounters), cudaHostAllocDefault));
+    for (auto &ev : ctx->ev) FQD_CUDA(cudaEventCreate(&ev));
+    cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device_ordinal);
+    *out = ctx;
+    return FQD_OK;
+}
+
+void fqd_context_destroy(fqd_context *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    dev_free(ctx, ctx->res.ufirst); dev_free(ctx, ctx->res.ucount);
+    dev_free(ctx, ctx->res.parent_full); dev_free(ctx, ctx->res.selected);
+    cudaStreamSynchronize(ctx->stream);
+    for (auto &ev : ctx->ev) if (ev) cudaEventDestroy(ev);
+    if (ctx->d_ctr) cudaFree(ctx->d_ctr);
+    if (ctx->h_ctr) cudaFreeHost(ctx->h_ctr);
+    if (ctx->pool) cudaMemPoolDestroy(ctx->pool);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+int fqd_default_context(fqd_context **out)
+{
+    static std::mutex mu;
+    static fqd_context *g_ctx = nullptr;
+    std::lock_guard<std::mutex> lock(mu);
+    if (!g_ctx) {
+        int dev = 0;
+        const int n = fqd_device_count();
+        const char *e = getenv("FQD_DEVICE");
+        if (e && *e) dev = atoi(e);
+        else if ((e = getenv("LOCAL_RANK")) && *e && n > 0) dev = atoi(e) % n;
+        FQD_TRY(fqd_context_create(dev, &g_ctx));
+    }
+    *out = g_ctx;
+    return FQD_OK;
+}
+
+int fqd_device_alloc(fqd_context *ctx, size_t bytes, void **dptr)
+{
+    FQD_TRY(check_device(ctx));
+    FQD_CUDA(cudaMalloc(dptr, bytes ? bytes : 16));
+    return FQD_OK;
+}
+
+int fqd_device_free(fqd_context *ctx, void *dptr)
+{
+    FQD_TRY(check_device(ctx));
+    FQD_CUDA(cudaFree(dptr));
+    return FQD_OK;
+}
+
+int fqd_device_upload(fqd_context *ctx, void *dptr, const void *host, size_t bytes)
+{
+    FQD_TRY(check_device(ctx));
+    FQD_CUDA(cudaMemcpyAsync(dptr, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    FQD_CUDA(cudaStreamSynchronize(ctx->stream));
+    return FQD_OK;
+}
+
+int fqd_device_download(fqd_context *ctx, void *host, const void *dptr, size_t bytes)
+{
+    FQD_TRY(check_device(ctx));
+    FQD_CUDA(cudaMemcpyAsync(host, dptr, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    FQD_CUDA(cudaStreamSynchronize(ctx->stream));
+    return FQD_OK;
+}
+
+int fqd_context_synchronize(fqd_context *ctx)
+{
+    FQD_TRY(check_device(ctx));
+    FQD_CUDA(cudaStreamSynchronize(ctx->stream));
+    return FQD_OK;
+}
+
+int fqd_host_alloc(size_t bytes, void **hptr)
+{
+    FQD_CUDA(cudaHostAlloc(hptr, bytes ? bytes : 16, cudaHostAllocDefault));
+    return FQD_OK;
+}
+
+int fqd_host_free(void *hptr)
+{
+    FQD_CUDA(cudaFreeHost(hptr));
+    return FQD_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// fqd_cluster
+// ------------------------------------------------------------------------------------------
+
+int fqd_cluster(fqd_context *ctx, const fqd_cluster_job *job, fqd_cluster_stats *stats,
+                uint32_t *keep_bitmap)
+{
+    FQD_TRY(check_device(ctx));
+    if (!job || !stats) { set_error("null job/stats"); return FQD_ERR_ARG; }
+    memset(stats, 0, sizeof *stats);
+    if (job->max_distance < 0) {
+        set_error("max_distance should be non-negative");   // _triemodule.c:789-793
+        return FQD_ERR_ARG;
+    }
+    if (job->method < 0 || job->method > 2) { set_error("unknown cluster dissection method %d", job->method); return FQD_ERR_ARG; }
+    if (job->memory_space != FQD_MEM_HOST && job->memory_space != FQD_MEM_DEVICE) {
+        set_error("unknown memory space %d", job->memory_space);
+        return FQD_ERR_ARG;
+    }
+    const uint64_t n = job->n_records;
+    if (n && !job->keys) { set_error("keys is NULL"); return FQD_ERR_ARG; }
+    if (n >= 0xFFFFFFF0ull) { set_error("too many records for one job (%llu)", (unsigned long long)n); return FQD_ERR_UNSUPPORTED; }
+    cudaStream_t s = ctx->stream;
+    const size_t bitmap_words = (size_t)((n + 31) / 32);
+    stats->total_records = n;
+    if (n == 0) {
+        dev_free(ctx, ctx->res.ufirst); dev_free(ctx, ctx->res.ucount);
+        dev_free(ctx, ctx->res.parent_full); dev_free(ctx, ctx->res.selected);
+        ctx->res = fqd_result{};
+        return FQD_OK;
+    }
+
+    DeviceJob dj;
+    dj.n = n;
+    dj.d = job->max_distance; dj.edit = job->use_edit_distance ? 1 : 0; dj.method = job->method;
+    dj.max_err = job->max_average_error_rate;
+    dj.filter_on = job->max_average_error_rate < 1.0 && job->quals != nullptr;   // __init__.py:235
+    dj.phred_offset = job->phred_offset;
+    dj.key_stride = job->key_stride; dj.key_len = job->key_length;
+    dj.qual_stride = job->qual_stride; dj.qual_len = job->qual_length;
+    if (!job->key_offsets && job->key_length > job->key_stride) { set_error("key_length > key_stride"); return FQD_ERR_ARG; }
+    if (dj.filter_on && !job->qual_offsets && job->qual_length > job->qual_stride) { set_error("qual_length > qual_stride"); return FQD_ERR_ARG; }
+
+    // ---- resolve inputs to device memory ----
+    DevBuf b_keys, b_koff, b_klen, b_quals, b_qoff, b_qlen, b_bitmap, b_weights;
+    cudaEvent_t h0, h1;
+    FQD_CUDA(cudaEventCreate(&h0)); FQD_CUDA(cudaEventCreate(&h1));
+    FQD_CUDA(cudaEventRecord(h0, s));
+    if (job->memory_space == FQD_MEM_HOST) {
+        auto up = [&](DevBuf &b, const void *src, size_t bytes, const void **dst) -> int {
+            FQD_TRY(b.alloc(ctx, bytes));
+            FQD_CUDA(cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, s));
+            *dst = b.p;
+            return FQD_OK;
+        };
+        size_t key_bytes;
+        if (job->key_offsets) {
+            key_bytes = (size_t)job->key_offsets[n];
+            FQD_TRY(up(b_koff, job->key_offsets, (n + 1) * 8, (const void **)&dj.key_off));
+        } else {
+            key_bytes = (size_t)n * job->key_stride;
+            if (job->key_lengths) FQD_TRY(up(b_klen, job->key_lengths, n * 4, (const void **)&dj.key_lens));
+        }
+        FQD_TRY(up(b_keys, job->keys, key_bytes, (const void **)&dj.keys));
+        if (dj.filter_on) {
+            size_t qual_bytes;
+            if (job->qual_offsets) {
+                qual_bytes = (size_t)job->qual_offsets[n];
+                FQD_TRY(up(b_qoff, job->qual_offsets, (n + 1) * 8, (const void **)&dj.qual_off));
+            } else {
+                qual_bytes = (size_t)n * job->qual_stride;
+                if (job->qual_lengths) FQD_TRY(up(b_qlen, job->qual_lengths, n * 4, (const void **)&dj.qual_lens));
+            }
+            FQD_TRY(up(b_quals, job->quals, qual_bytes, (const void **)&dj.quals));
+        }
+        if (job->record_counts) FQD_TRY(up(b_weights, job->record_counts, n * 4, (const void **)&dj.weights));
+        if (keep_bitmap) {
+            FQD_TRY(b_bitmap.alloc(ctx, bitmap_words * 4));
+            dj.bitmap = b_bitmap.as<uint32_t>();
+        }
+    } else {
+        dj.keys = job->keys; dj.key_off = job->key_offsets; dj.key_lens = job->key_offsets ? nullptr : job->key_lengths;
+        if (dj.filter_on) { dj.quals = job->quals; dj.qual_off = job->qual_offsets; dj.qual_lens = job->qual_offsets ? nullptr : job->qual_lengths; }
+        dj.bitmap = keep_bitmap;
+        dj.weights = job->record_counts;
+    }
+    FQD_CUDA(cudaEventRecord(h1, s));
+
+    // ---- key length range: PW and whether PAD is needed ----
+    if (dj.key_off || dj.key_lens) {
+        DevCounters init{};
+        init.len_min = 0xFFFFFFFFu;
+        *ctx->h_ctr = init;
+        FQD_CUDA(cudaMemcpyAsync(ctx->d_ctr, ctx->h_ctr, sizeof(DevCounters), cudaMemcpyHostToDevice, s));
+        length_range_kernel<<<std::min<uint64_t>(ctx->sm_count * 8, (n + 255) / 256), 256, 0, s>>>(
+            n, dj.key_off, dj.key_lens, ctx->d_ctr);
+        FQD_CUDA(cudaGetLastError());
+        FQD_CUDA(cudaMemcpyAsync(ctx->h_ctr, ctx->d_ctr, sizeof(DevCounters), cudaMemcpyDeviceToHost, s));
+        FQD_CUDA(cudaStreamSynchronize(s));
+        dj.max_len = ctx->h_ctr->len_max;
+        dj.varlen = ctx->h_ctr->len_min != ctx->h_ctr->len_max;
+        if (!dj.key_off && dj.max_len > job->key_stride) { set_error("a key length exceeds key_stride"); return FQD_ERR_ARG; }
+    } else {
+        dj.max_len = job->key_length;
+        dj.varlen = false;
+    }
+
+    // ---- alphabet: start from the caller's (default "ACGTN"), grow when bytes outside it show up ----
+    std::vector<uint8_t> alphabet;
+    {
+        const char *a = job->alphabet ? job->alphabet : "ACGTN";
+        bool seen[256] = {};
+        for (const char *p = a; *p; p++) {
+            const uint8_t c = (uint8_t)*p;
+            if (seen[c]) { set_error("Alphabet should consist of unique characters.Character %c was repeated. ", c); return FQD_ERR_ARG; }
+            seen[c] = true;
+            alphabet.push_back(c);
+        }
+        if (alphabet.empty()) alphabet.push_back('A');
+    }
+    int rc = FQD_OK;
+    for (int attempt = 0; attempt < 3; attempt++) {
+        Codec codec;
+        FQD_TRY(make_codec(alphabet, dj.varlen, &codec));
+        uint32_t unknown[8] = {};
+        rc = run_pipeline(ctx, dj, codec, stats, unknown);
+        if (rc != RC_RETRY_ALPHABET) break;
+        for (int c = 0; c < 256; c++)
+            if (unknown[c >> 5] & (1u << (c & 31))) alphabet.push_back((uint8_t)c);
+    }
+    if (rc == RC_RETRY_ALPHABET) { set_error("internal: alphabet did not converge"); rc = FQD_ERR_CUDA; }
+    if (rc != FQD_OK) { cudaEventDestroy(h0); cudaEventDestroy(h1); return rc; }
+
+    if (job->memory_space == FQD_MEM_HOST && keep_bitmap) {
+        FQD_CUDA(cudaMemcpyAsync(keep_bitmap, dj.bitmap, bitmap_words * 4, cudaMemcpyDeviceToHost, s));
+    }
+    FQD_CUDA(cudaStreamSynchronize(s));
+    cudaEventElapsedTime(&stats->ms_h2d, h0, h1);
+    cudaEventDestroy(h0); cudaEventDestroy(h1);
+    return FQD_OK;
+}
+
+int fqd_cluster_fetch(fqd_context *ctx, uint64_t *first, uint32_t *count, uint64_t *label,
+                      uint8_t *selected)
+{
+    FQD_TRY(check_device(ctx));
+    const uint32_t U = ctx->res.U;
+    if (!U) return FQD_OK;
+    cudaStream_t s = ctx->stream;
+    std::vector<uint32_t> tmp(U);
+    if (first || label) {
+        FQD_CUDA(cudaMemcpyAsync(tmp.data(), ctx->res.ufirst, (size_t)U * 4, cudaMemcpyDeviceToHost, s));
+        FQD_CUDA(cudaStreamSynchronize(s));
+        if (first) for (uint32_t i = 0; i < U; i++) first[i] = tmp[i];
+    }
+    if (count) {
+        FQD_CUDA(cudaMemcpyAsync(count, ctx->res.ucount, (size_t)U * 4, cudaMemcpyDeviceToHost, s));
+    }
+    if (selected) {
+        FQD_CUDA(cudaMemcpyAsync(selected, ctx->res.selected, (size_t)U, cudaMemcpyDeviceToHost, s));
+    }
+    if (label) {
+        DevBuf minfirst, root;
+        FQD_TRY(minfirst.alloc(ctx, (size_t)U * 4));
+        FQD_TRY(root.alloc(ctx, (size_t)U * 4));
+        FQD_CUDA(cudaMemsetAsync(minfirst.p, 0xFF, (size_t)U * 4, s));
+        SelectParams sp{};
+        sp.U = U; sp.ufirst = ctx->res.ufirst; sp.parent_full = ctx->res.parent_full;
+        sp.root = root.as<uint32_t>(); sp.minfirst = minfirst.as<uint32_t>();
+        label_min_kernel<<<(U + 255) / 256, 256, 0, s>>>(sp);
+        FQD_CUDA(cudaGetLastError());
+        std::vector<uint32_t> hroot(U), hmin(U);
+        FQD_CUDA(cudaMemcpyAsync(hroot.data(), root.p, (size_t)U * 4, cudaMemcpyDeviceToHost, s));
+        FQD_CUDA(cudaMemcpyAsync(hmin.data(), minfirst.p, (size_t)U * 4, cudaMemcpyDeviceToHost, s));
+        FQD_CUDA(cudaStreamSynchronize(s));
+        for (uint32_t i = 0; i < U; i++) label[i] = hmin[hroot[i]];
+    }
+    FQD_CUDA(cudaStreamSynchronize(s));
+    return FQD_OK;
+}
+
+int fqd_cluster_fetch_selected(fqd_context *ctx, uint64_t *indices)
+{
+    FQD_TRY(check_device(ctx));
+    const uint32_t U = ctx->res.U;
+    if (!U) return FQD_OK;
+    std::vector<uint32_t> f(U);
+    std::vector<uint8_t> sel(U);
+    FQD_CUDA(cudaMemcpyAsync(f.data(), ctx->res.ufirst, (size_t)U * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    FQD_CUDA(cudaMemcpyAsync(sel.data(), ctx->res.selected, (size_t)U, cudaMemcpyDeviceToHost, ctx->stream));
+    FQD_CUDA(cudaStreamSynchronize(ctx->stream));
+    size_t k = 0;
+    for (uint32_t i = 0; i < U; i++) if (sel[i]) indices[k++] = f[i];
+    std::sort(indices, indices + k);
+    return FQD_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// function-level entry points
+// ------------------------------------------------------------------------------------------
+
+int fqd_average_error_rate(fqd_context *ctx, const uint8_t *phred, const uint64_t *offsets,
+                           uint64_t n_strings, uint8_t phred_offset, double *out,
+                           uint64_t *bad_index, uint32_t *bad_char)
+{
+    FQD_TRY(check_device(ctx));
+    if (!n_strings) return FQD_OK;
+    if (!offsets || !out) { set_error("null argument"); return FQD_ERR_ARG; }
+    cudaStream_t s = ctx->stream;
+    const size_t bytes = (size_t)offsets[n_strings];
+    DevBuf d_ph, d_off, d_out;
+    FQD_TRY(d_ph.alloc(ctx, bytes)); FQD_TRY(d_off.alloc(ctx, (n_strings + 1) * 8)); FQD_TRY(d_out.alloc(ctx, n_strings * 8));
+    if (bytes) FQD_CUDA(cudaMemcpyAsync(d_ph.p, phred, bytes, cudaMemcpyHostToDevice, s));
+    FQD_CUDA(cudaMemcpyAsync(d_off.p, offsets, (n_strings + 1) * 8, cudaMemcpyHostToDevice, s));
+    DevCounters init{};
+    init.phred_err = ~0ull;
+    *ctx->h_ctr = init;
+    FQD_CUDA(cudaMemcpyAsync(ctx->d_ctr, ctx->h_ctr, sizeof(DevCounters), cudaMemcpyHostToDevice, s));
+    error_rate_kernel<<<(uint32_t)((n_strings + 127) / 128), 128, 0, s>>>(
+        d_ph.as<uint8_t>(), d_off.as<uint64_t>(), n_strings, phred_offset, d_out.as<double>(), ctx->d_ctr);
+    FQD_CUDA(cudaGetLastError());
+    FQD_CUDA(cudaMemcpyAsync(out, d_out.p, n_strings * 8, cudaMemcpyDeviceToHost, s));
+    FQD_CUDA(cudaMemcpyAsync(ctx->h_ctr, ctx->d_ctr, sizeof(DevCounters), cudaMemcpyDeviceToHost, s));
+    FQD_CUDA(cudaStreamSynchronize(s));
+    if (ctx->h_ctr->phred_err != ~0ull) {
+        const uint32_t c = (uint32_t)(ctx->h_ctr->phred_err & 0xFF);
+        if (bad_index) *bad_index = ctx->h_ctr->phred_err >> 8;
+        if (bad_char) *bad_char = c;
+        set_error("Character %c outside of valid phred range ('%c' to '%c')", (int)c, (int)phred_offset, 126);
+        return FQD_ERR_PHRED;
+    }
+    return FQD_OK;
+}
+
+int fqd_within_distance(fqd_context *ctx, const uint8_t *a, const uint64_t *a_offsets,
+                        const uint8_t *b, const uint64_t *b_offsets, uint64_t n_pairs,
+                        int32_t max_distance, int32_t use_edit_distance, uint8_t *out)
+{
+    FQD_TRY(check_device(ctx));
+    if (!n_pairs) return FQD_OK;
+    if (!a_offsets || !b_offsets || !out) { set_error("null argument"); return FQD_ERR_ARG; }
+    if (use_edit_distance && max_distance > MAX_BAND_D) {
+        // a band wider than every string is the full matrix: clamp when that is exact
+        uint64_t longest = 0;
+        for (uint64_t i = 0; i < n_pairs; i++) {
+            longest = std::max(longest, a_offsets[i + 1] - a_offsets[i]);
+            longest = std::max(longest, b_offsets[i + 1] - b_offsets[i]);
+        }
+        if (longest > (uint64_t)MAX_BAND_D) {
+            set_error("edit distances above %d are not supported for strings longer than that", MAX_BAND_D);
+            return FQD_ERR_UNSUPPORTED;
+        }
+        max_distance = MAX_BAND_D;   // >= both lengths => always within distance, like the true predicate
+    }
+    cudaStream_t s = ctx->stream;
+    const size_t ab = (size_t)a_offsets[n_pairs], bb = (size_t)b_offsets[n_pairs];
+    DevBuf d_a, d_ao, d_b, d_bo, d_out;
+    FQD_TRY(d_a.alloc(ctx, ab)); FQD_TRY(d_b.alloc(ctx, bb));
+    FQD_TRY(d_ao.alloc(ctx, (n_pairs + 1) * 8)); FQD_TRY(d_bo.alloc(ctx, (n_pairs + 1) * 8));
+    FQD_TRY(d_out.alloc(ctx, n_pairs));
+    if (ab) FQD_CUDA(cudaMemcpyAsync(d_a.p, a, ab, cudaMemcpyHostToDevice, s));
+    if (bb) FQD_CUDA(cudaMemcpyAsync(d_b.p, b, bb, cudaMemcpyHostToDevice, s));
+    FQD_CUDA(cudaMemcpyAsync(d_ao.p, a_offsets, (n_pairs + 1) * 8, cudaMemcpyHostToDevice, s));
+    FQD_CUDA(cudaMemcpyAsync(d_bo.p, b_offsets, (n_pairs + 1) * 8, cudaMemcpyHostToDevice, s));
+    within_distance_kernel<<<(uint32_t)((n_pairs + 127) / 128), 128, 0, s>>>(
+        d_a.as<uint8_t>(), d_ao.as<uint64_t>(), d_b.as<uint8_t>(), d_bo.as<uint64_t>(), n_pairs,
+        max_distance, use_edit_distance ? 1 : 0, d_out.as<uint8_t>());
+    FQD_CUDA(cudaGetLastError());
+    FQD_CUDA(cudaMemcpyAsync(out, d_out.p, n_pairs, cudaMemcpyDeviceToHost, s));
+    FQD_CUDA(cudaStreamSynchronize(s));
+    return FQD_OK;
+}
+
+}  // extern "C"

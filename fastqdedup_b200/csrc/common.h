@@ -1,0 +1,123 @@
+// common.h -- host-side plumbing shared by the translation units of libfqd_b200.so:
+// error reporting across the C ABI, the per-GPU context, stream-ordered device buffers.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/fqd_b200.h"
+#include "pipeline.cuh"
+
+namespace fqd {
+
+void set_error(const char *fmt, ...);
+int cuda_fail(cudaError_t e, const char *what, const char *file, int line);
+
+#define FQD_CUDA(call)                                                            \
+    do {                                                                          \
+        cudaError_t _e = (call);                                                  \
+        if (_e != cudaSuccess) return ::fqd::cuda_fail(_e, #call, __FILE__, __LINE__); \
+    } while (0)
+
+#define FQD_TRY(call)                \
+    do {                             \
+        int _rc = (call);            \
+        if (_rc != FQD_OK) return _rc; \
+    } while (0)
+
+}  // namespace fqd
+
+// Result of the last job, kept on the device until the next one.
+struct fqd_result {
+    uint32_t U = 0;
+    uint64_t n_records = 0;
+    uint64_t n_selected = 0;
+    uint32_t *ufirst = nullptr;
+    uint32_t *ucount = nullptr;
+    uint32_t *parent_full = nullptr;
+    uint8_t *selected = nullptr;
+};
+
+struct fqd_context {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaMemPool_t pool = nullptr;
+    fqd::DevCounters *d_ctr = nullptr;
+    fqd::DevCounters *h_ctr = nullptr;   // pinned
+    cudaEvent_t ev[8] = {};
+    fqd_result res;
+    int sm_count = 148;
+};
+
+namespace fqd {
+
+// stream-ordered allocation from the context's pool (cached across jobs)
+int dev_alloc(fqd_context *ctx, size_t bytes, void **p);
+void dev_free(fqd_context *ctx, void *p);
+
+// RAII holder for job-lifetime device buffers
+struct DevBuf {
+    fqd_context *ctx = nullptr;
+    void *p = nullptr;
+    DevBuf() = default;
+    explicit DevBuf(fqd_context *c) : ctx(c) {}
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+    ~DevBuf() { reset(); }
+    int alloc(fqd_context *c, size_t bytes)
+    {
+        reset();
+        ctx = c;
+        return dev_alloc(c, bytes ? bytes : 16, &p);
+    }
+    void reset()
+    {
+        if (p) dev_free(ctx, p);
+        p = nullptr;
+    }
+    void *release()
+    {
+        void *r = p;
+        p = nullptr;
+        return r;
+    }
+    template <typename T>
+    T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+// The job with every pointer resolved to device memory.
+struct DeviceJob {
+    uint64_t n = 0;
+    const uint8_t *keys = nullptr;
+    const uint64_t *key_off = nullptr;
+    const uint32_t *key_lens = nullptr;
+    uint32_t key_stride = 0, key_len = 0;
+    const uint8_t *quals = nullptr;
+    const uint64_t *qual_off = nullptr;
+    const uint32_t *qual_lens = nullptr;
+    uint32_t qual_stride = 0, qual_len = 0;
+    int d = 1, edit = 0, method = 2;
+    bool filter_on = false;
+    double max_err = 1.0;
+    uint32_t phred_offset = 33;
+    uint32_t max_len = 0;
+    bool varlen = false;
+    const uint32_t *weights = nullptr;
+    uint32_t *bitmap = nullptr;   // device, (n+31)/32 words, zeroed by the pipeline; may be null
+};
+
+constexpr int RC_RETRY_ALPHABET = -100;   // internal: unknown bytes were seen, grow the alphabet
+
+// pipeline.cu: runs the stages for one (K, PW) instantiation
+int run_pipeline(fqd_context *ctx, const DeviceJob &job, const Codec &codec,
+                 fqd_cluster_stats *stats, uint32_t unknown_out[8]);
+
+// largest key (in symbols) this build can pack for a given number of code bits
+uint32_t max_supported_length(int bits);
+int supported_bits(int needed_bits);
+
+}  // namespace fqd

@@ -1,0 +1,323 @@
+// key.cuh -- packed-key primitives of the B200 clustering path.
+//
+// A key (the --check-lengths slices of one read tuple, reference
+// src/fastqdedup/__init__.py:160-167, :251) is stored bit-sliced: K bit planes of PW
+// 32-bit words each, plane-major (w[p*PW + i]); bit (i%32) of word i/32 of plane p is bit
+// p of the code of symbol i.  With the default alphabet "ACGTN" (reference
+// __init__.py:240) K = 3: planes 0/1 are the classic 2-bit base code and plane 2 is the
+// N mask, which is the "2-bit packed with an N mask" layout BASELINE.json asks for,
+// generalised to any alphabet of up to 2^K - 1 symbols (one code is reserved as PAD).
+//
+// Variable-length keys (reads shorter than the check length) are padded to the job's
+// maximum length with the PAD code, which no real symbol uses; two keys are the same
+// string iff all their plane words are equal, so hashing/equality never look at a length.
+//
+// Everything here is __host__ __device__ so tests/test_key_primitives.py can exercise the
+// exact same code on the CPU (through csrc/host_probe.cu) where no GPU exists; the
+// product never calls the host instantiations.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define FQD_HD __host__ __device__ __forceinline__
+#else
+#define FQD_HD inline
+#endif
+
+namespace fqd {
+
+#if defined(__CUDA_ARCH__)
+FQD_HD int popc32(uint32_t x) { return __popc(x); }
+FQD_HD int ctz32(uint32_t x) { return __ffs((int)x) - 1; }
+#else
+FQD_HD int popc32(uint32_t x) { return __builtin_popcount(x); }
+FQD_HD int ctz32(uint32_t x) { return __builtin_ctz(x); }
+#endif
+
+// Symbol coding of one job: byte -> code (0xFF = not in the alphabet), code -> rank in
+// ASCII order (PAD ranks below everything so a proper prefix sorts first, like Python's
+// str comparison used by sorted() at reference __init__.py:68, :99, :111).
+struct Codec {
+    uint8_t lut[256];
+    uint8_t rank[256];
+    uint8_t pad_code;
+    uint8_t bits;      // K
+    uint8_t n_symbols;
+    uint8_t varlen;    // 1: keys of several lengths are present (PAD in use)
+};
+
+template <int K, int PW>
+struct Key {
+    static constexpr int NW = K * PW;
+    uint32_t w[NW];
+};
+
+FQD_HD uint64_t mix64(uint64_t h)
+{
+    h ^= h >> 33; h *= 0xff51afd7ed558ccdULL;
+    h ^= h >> 33; h *= 0xc4ceb9fe1a85ec53ULL;
+    h ^= h >> 33;
+    return h;
+}
+
+template <int K, int PW>
+FQD_HD uint64_t hash_key(const Key<K, PW> &k)
+{
+    uint64_t h = 0x243f6a8885a308d3ULL;
+#pragma unroll
+    for (int i = 0; i < K * PW; i++) {
+        h = (h ^ k.w[i]) * 0x9E3779B97F4A7C15ULL;
+        h ^= h >> 29;
+    }
+    return mix64(h);
+}
+
+template <int K, int PW>
+FQD_HD bool key_equal(const Key<K, PW> &a, const Key<K, PW> &b)
+{
+    uint32_t d = 0;
+#pragma unroll
+    for (int i = 0; i < K * PW; i++) d |= a.w[i] ^ b.w[i];
+    return d == 0;
+}
+
+// Pack `len` bytes (symbols beyond len up to padded_len become PAD).  Returns false when
+// a byte is not in the codec's alphabet; *bad receives that byte.
+template <int K, int PW>
+FQD_HD bool pack_key(const uint8_t *bytes, uint32_t len, uint32_t padded_len,
+                     const uint8_t *lut, uint32_t pad_code, Key<K, PW> &out, uint32_t *bad)
+{
+    bool ok = true;
+#pragma unroll
+    for (int wi = 0; wi < PW; wi++) {
+        uint32_t acc[K];
+#pragma unroll
+        for (int p = 0; p < K; p++) acc[p] = 0;
+        const uint32_t base = wi * 32;
+        for (uint32_t b = 0; b < 32 && base + b < padded_len; b++) {
+            uint32_t c;
+            if (base + b < len) {
+                c = lut[bytes[base + b]];
+                if (c == 0xFF) { ok = false; *bad = bytes[base + b]; c = 0; }
+            } else {
+                c = pad_code;
+            }
+#pragma unroll
+            for (int p = 0; p < K; p++) acc[p] |= ((c >> p) & 1u) << b;
+        }
+#pragma unroll
+        for (int p = 0; p < K; p++) out.w[p * PW + wi] = acc[p];
+    }
+    return ok;
+}
+
+// Bit mask (per plane word i) of the positions holding PAD.
+template <int K, int PW>
+FQD_HD uint32_t pad_mask_word(const Key<K, PW> &a, int i, uint32_t pad_code)
+{
+    uint32_t m = 0xFFFFFFFFu;
+#pragma unroll
+    for (int p = 0; p < K; p++) m &= ((pad_code >> p) & 1u) ? a.w[p * PW + i] : ~a.w[p * PW + i];
+    return m;
+}
+
+// Length of a padded key: index of its first PAD symbol, or max_len.
+template <int K, int PW>
+FQD_HD uint32_t key_length(const Key<K, PW> &a, uint32_t pad_code, uint32_t max_len)
+{
+#pragma unroll
+    for (int i = 0; i < PW; i++) {
+        uint32_t m = pad_mask_word(a, i, pad_code);
+        if (m) {
+            uint32_t pos = 32u * i + (uint32_t)ctz32(m);
+            return pos < max_len ? pos : max_len;
+        }
+    }
+    return max_len;
+}
+
+// Hamming predicate of reference distances.h:8-31 on packed keys: XOR the planes, OR them
+// into one mismatch bit per symbol, popcount, early exit once the budget is exceeded.
+// Keys of different length never match (:16-20): with PAD padding that is "the PAD
+// positions differ".
+template <int K, int PW>
+FQD_HD bool hamming_within(const Key<K, PW> &a, const Key<K, PW> &b, int max_distance,
+                           bool varlen, uint32_t pad_code)
+{
+    int dist = 0;
+#pragma unroll
+    for (int i = 0; i < PW; i++) {
+        uint32_t diff = 0;
+#pragma unroll
+        for (int p = 0; p < K; p++) diff |= a.w[p * PW + i] ^ b.w[p * PW + i];
+        dist += popc32(diff);
+        if (dist > max_distance) return false;
+        if (varlen && (pad_mask_word(a, i, pad_code) != pad_mask_word(b, i, pad_code))) return false;
+    }
+    return true;
+}
+
+// Code of symbol `pos`.
+template <int K, int PW>
+FQD_HD uint32_t symbol_at(const Key<K, PW> &a, uint32_t pos)
+{
+    uint32_t c = 0;
+    const uint32_t wi = pos >> 5, sh = pos & 31u;
+#pragma unroll
+    for (int p = 0; p < K; p++) {
+        uint32_t word = 0;
+#pragma unroll
+        for (int i = 0; i < PW; i++) word = (wi == (uint32_t)i) ? a.w[p * PW + i] : word;
+        c |= ((word >> sh) & 1u) << p;
+    }
+    return c;
+}
+
+// Strict "a < b" in Python str order (bytes lexicographic, proper prefix first).
+template <int K, int PW>
+FQD_HD bool key_less(const Key<K, PW> &a, const Key<K, PW> &b, const uint8_t *rank)
+{
+#pragma unroll
+    for (int i = 0; i < PW; i++) {
+        uint32_t diff = 0;
+#pragma unroll
+        for (int p = 0; p < K; p++) diff |= a.w[p * PW + i] ^ b.w[p * PW + i];
+        if (diff) {
+            const int sh = ctz32(diff);
+            uint32_t ca = 0, cb = 0;
+#pragma unroll
+            for (int p = 0; p < K; p++) {
+                ca |= ((a.w[p * PW + i] >> sh) & 1u) << p;
+                cb |= ((b.w[p * PW + i] >> sh) & 1u) << p;
+            }
+            return rank[ca] < rank[cb];
+        }
+    }
+    return false;
+}
+
+// (count, key) tuple order of the reference's sorted() calls.
+template <int K, int PW>
+FQD_HD bool prio_less(uint32_t ca, const Key<K, PW> &a, uint32_t cb, const Key<K, PW> &b,
+                      const uint8_t *rank)
+{
+    if (ca != cb) return ca < cb;
+    return key_less(a, b, rank);
+}
+
+// 32 plane bits starting at symbol position `pos` (bits past the end read as 0).
+template <int K, int PW>
+FQD_HD uint32_t plane_bits32(const Key<K, PW> &a, int p, uint32_t pos)
+{
+    const uint32_t wi = pos >> 5, sh = pos & 31u;
+    uint32_t lo = 0, hi = 0;
+#pragma unroll
+    for (int i = 0; i < PW; i++) {
+        lo = (wi == (uint32_t)i) ? a.w[p * PW + i] : lo;
+        hi = (wi + 1 == (uint32_t)i) ? a.w[p * PW + i] : hi;
+    }
+    return sh ? ((lo >> sh) | (hi << (32u - sh))) : lo;
+}
+
+// Hash of the symbols [start, start+len) right-aligned, so that the same substring hashes
+// equal wherever it sits in the key (needed by the shifted blocks of the Levenshtein
+// pigeonhole).  `salt` separates passes / block ids / lengths.
+template <int K, int PW>
+FQD_HD uint64_t block_hash(const Key<K, PW> &a, uint32_t start, uint32_t len, uint64_t salt)
+{
+    uint64_t h = salt * 0xD6E8FEB86659FD93ULL + 0x9E3779B97F4A7C15ULL;
+#pragma unroll
+    for (int c = 0; c < PW; c++) {
+        if ((uint32_t)(32 * c) < len) {
+            const uint32_t rem = len - 32u * c;
+            const uint32_t mask = rem >= 32u ? 0xFFFFFFFFu : ((1u << rem) - 1u);
+#pragma unroll
+            for (int p = 0; p < K; p++) {
+                uint32_t v = plane_bits32(a, p, start + 32u * c) & mask;
+                h = (h ^ v) * 0x9E3779B97F4A7C15ULL;
+                h ^= h >> 29;
+            }
+        }
+    }
+    return mix64(h);
+}
+
+// Pigeonhole block j of d+1 over a key of `len` symbols: [len*j/(d+1), len*(j+1)/(d+1)).
+FQD_HD uint32_t block_start(uint32_t len, uint32_t j, uint32_t nblocks)
+{
+    return (uint32_t)(((uint64_t)len * j) / nblocks);
+}
+
+// ---------------------------------------------------------------------------------------
+// Levenshtein predicate (reference distances.h:33-87 == "edit distance <= d") by Myers'
+// bit-vector algorithm in Hyyro's global-distance form, NW64 64-bit words per column
+// (one word for keys up to 64 symbols).  Pattern = a (length la), text = b (length lb).
+// ---------------------------------------------------------------------------------------
+template <int K, int PW>
+FQD_HD bool myers_within(const Key<K, PW> &a, uint32_t la, const Key<K, PW> &b, uint32_t lb,
+                         int max_distance)
+{
+    constexpr int NW64 = (PW + 1) / 2;
+    const uint32_t diff = la > lb ? la - lb : lb - la;
+    if (max_distance < 0 || diff > (uint32_t)max_distance) return false;
+    if (la == 0) return lb <= (uint32_t)max_distance;
+    // pattern planes as 64-bit words
+    uint64_t P[K][NW64];
+#pragma unroll
+    for (int p = 0; p < K; p++)
+#pragma unroll
+        for (int i = 0; i < NW64; i++) {
+            uint64_t lo = a.w[p * PW + 2 * i];
+            uint64_t hi = (2 * i + 1 < PW) ? a.w[p * PW + 2 * i + 1] : 0u;
+            P[p][i] = lo | (hi << 32);
+        }
+    uint64_t valid[NW64];   // bits < la
+#pragma unroll
+    for (int i = 0; i < NW64; i++) {
+        const uint32_t lo = 64u * i;
+        valid[i] = la >= lo + 64u ? ~0ULL : (la > lo ? ((1ULL << (la - lo)) - 1ULL) : 0ULL);
+    }
+    uint64_t Pv[NW64], Mv[NW64];
+#pragma unroll
+    for (int i = 0; i < NW64; i++) { Pv[i] = valid[i]; Mv[i] = 0; }
+    int score = (int)la;
+    const uint32_t top_w = (la - 1) >> 6;
+    const uint64_t top_bit = 1ULL << ((la - 1) & 63u);
+    for (uint32_t j = 0; j < lb; j++) {
+        const uint32_t c = symbol_at(b, j);
+        uint64_t carry_add = 0;      // carry of (Eq & Pv) + Pv across words
+        uint64_t ph_in = 1;          // global distance: D[0][j] - D[0][j-1] = +1
+        uint64_t mh_in = 0;
+#pragma unroll
+        for (int i = 0; i < NW64; i++) {
+            uint64_t Eq = valid[i];
+#pragma unroll
+            for (int p = 0; p < K; p++) Eq &= ((c >> p) & 1u) ? P[p][i] : ~P[p][i];
+            const uint64_t Xv = Eq | Mv[i];
+            const uint64_t x = Eq & Pv[i];
+            const uint64_t s1 = x + Pv[i];
+            const uint64_t c1 = s1 < x;
+            const uint64_t sum = s1 + carry_add;
+            const uint64_t c2 = sum < s1;
+            carry_add = c1 | c2;
+            const uint64_t Xh = (sum ^ Pv[i]) | Eq;
+            uint64_t Ph = Mv[i] | ~(Xh | Pv[i]);
+            uint64_t Mh = Pv[i] & Xh;
+            if ((uint32_t)i == top_w) {
+                if (Ph & top_bit) score++;
+                else if (Mh & top_bit) score--;
+            }
+            const uint64_t ph_out = Ph >> 63, mh_out = Mh >> 63;
+            Ph = (Ph << 1) | ph_in;
+            Mh = (Mh << 1) | mh_in;
+            ph_in = ph_out; mh_in = mh_out;
+            Pv[i] = (Mh | ~(Xv | Ph)) & valid[i];
+            Mv[i] = Ph & Xv & valid[i];
+        }
+        // the final score can still drop by at most one per remaining text symbol
+        if (score - (int)(lb - 1 - j) > max_distance) return false;
+    }
+    return score <= max_distance;
+}
+
+}  // namespace fqd

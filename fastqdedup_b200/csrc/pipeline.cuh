@@ -1,0 +1,838 @@
+// pipeline.cuh -- device kernels of the clustering path (sm_100a) and their launch plan.
+//
+// Stages (DESIGN.md has the data layout and the per-kernel roofline):
+//   ingest   : per record quality filter (bit-exact double sum), bit-plane packing and
+//              exact dedupe with counts + first index in an open-addressing table in HBM
+//              (replaces Trie.add_sequence, reference _triemodule.c:222-288, and
+//              average_error_rate, _fastqmodule.c:38-76)
+//   gather   : claimed slots -> dense unique arrays (key, count, first)
+//   passes   : pigeonhole block bucketing (counting sort of 8-byte {tag, uid} entries by
+//              block hash) + in-bucket verification with XOR/popc Hamming or Myers
+//              bit-vector Levenshtein; every verified pair is an edge
+//              (replaces TrieNode_FindNearest / Trie.pop_cluster, _triemodule.c:380-495,
+//              :778-897, and distances.h)
+//   select   : lock-free union-find components + the three dissections in closed /
+//              round-based form (replaces __init__.py:60-122)
+#pragma once
+#include <cooperative_groups.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "key.cuh"
+#define FQD_LUT_QUALIFIER static __constant__
+#include "phred_lut.h"
+
+namespace cg = cooperative_groups;
+
+namespace fqd {
+
+constexpr uint32_t SLOT_EMPTY = 0xFFFFFFFFu;
+constexpr uint32_t SLOT_LOCKED = 0xFFFFFFFEu;
+constexpr uint32_t ENT_LAST = 0x80000000u;
+constexpr uint32_t ENT_BUILD = 0x40000000u;
+constexpr uint32_t ENT_UID = 0x3FFFFFFFu;
+constexpr uint32_t RANK_INVALID = 0xFFFFFFFFu;
+
+constexpr int METHOD_HIGHEST = 0, METHOD_ADJACENCY = 1, METHOD_DIRECTIONAL = 2;
+
+__host__ __device__ constexpr int round_up4(int x) { return (x + 3) & ~3; }
+
+struct DevCounters {
+    unsigned long long phred_err;     // min over (record << 8 | byte); ~0 = none
+    unsigned long long n_candidates;
+    unsigned long long n_edges;
+    unsigned long long sum_weights;   // kept reads when records carry multiplicities
+    uint32_t n_unique;
+    uint32_t n_discarded;
+    uint32_t n_merges;
+    uint32_t n_selected;
+    uint32_t table_full;
+    uint32_t undecided;
+    uint32_t unknown[8];              // bitmap of key bytes outside the alphabet
+    uint32_t len_min, len_max;
+};
+
+// ---- small device helpers -----------------------------------------------------------
+
+__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t *p)
+{
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_u32(uint32_t *p, uint32_t v)
+{
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_relaxed_u32(const uint32_t *p)
+{
+    uint32_t v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// one atomicAdd per converged group instead of one per thread
+__device__ __forceinline__ uint32_t aggregated_inc(uint32_t *ctr)
+{
+    cg::coalesced_group g = cg::coalesced_threads();
+    uint32_t base = 0;
+    if (g.thread_rank() == 0) base = atomicAdd(ctr, g.size());
+    return g.shfl(base, 0) + g.thread_rank();
+}
+__device__ __forceinline__ unsigned long long aggregated_inc64(unsigned long long *ctr)
+{
+    cg::coalesced_group g = cg::coalesced_threads();
+    unsigned long long base = 0;
+    if (g.thread_rank() == 0) base = atomicAdd(ctr, (unsigned long long)g.size());
+    return g.shfl(base, 0) + g.thread_rank();
+}
+
+template <int K, int PW>
+__device__ __forceinline__ void load_key(const uint32_t *__restrict__ ukey, uint32_t u,
+                                         Key<K, PW> &k)
+{
+    const uint32_t *p = ukey + (size_t)u * (K * PW);
+#pragma unroll
+    for (int i = 0; i < K * PW; i++) k.w[i] = __ldg(p + i);
+}
+
+// ---- ingest: filter + pack + exact dedupe ----------------------------------------------
+
+struct IngestParams {
+    uint64_t n;
+    const uint8_t *keys;
+    const uint64_t *key_off;
+    const uint32_t *key_lens;
+    uint32_t key_stride, key_len;
+    const uint8_t *quals;
+    const uint64_t *qual_off;
+    const uint32_t *qual_lens;
+    uint32_t qual_stride, qual_len;
+    uint32_t max_len;          // padded key length
+    uint32_t stage_bytes;      // >0: fixed-stride rows are staged through shared memory
+    int filter_on;
+    int phase;                 // 0: insert kept records, 1: first-index fix-up of discarded ones
+    double max_err;
+    uint32_t phred_offset;
+    uint32_t pad_code;
+    uint32_t *table;
+    uint64_t capacity;
+    uint32_t *uslot;
+    uint32_t *keepmask;        // bit per record: passed the filter
+    const uint32_t *weights;   // optional multiplicity per record
+    DevCounters *ctr;
+    Codec codec;
+};
+
+template <int K, int PW>
+__device__ __forceinline__ void table_insert(const IngestParams &P, const Key<K, PW> &key,
+                                             uint32_t t)
+{
+    uint32_t weight = 1u;
+    if (P.weights) {
+        weight = P.weights[t];
+        atomicAdd(&P.ctr->sum_weights, (unsigned long long)weight);
+    }
+    constexpr int KW = K * PW, RW = round_up4(KW + 2);
+    const uint64_t h = hash_key(key);
+    uint64_t s = __umul64hi(h, P.capacity);
+    for (uint64_t probes = 0; probes < P.capacity;) {
+        uint32_t *rec = P.table + s * RW;
+        uint32_t st = ld_acquire_u32(rec + KW + 1);
+        if (st == SLOT_EMPTY) {
+            const uint32_t old = atomicCAS(rec + KW + 1, SLOT_EMPTY, SLOT_LOCKED);
+            if (old == SLOT_EMPTY) {
+#pragma unroll
+                for (int i = 0; i < KW; i++) rec[i] = key.w[i];
+                rec[KW] = weight;
+                __threadfence();
+                st_release_u32(rec + KW + 1, t);
+                const uint32_t pos = aggregated_inc(&P.ctr->n_unique);
+                P.uslot[pos] = (uint32_t)s;
+                return;
+            }
+            st = old;
+        }
+        if (st == SLOT_LOCKED) continue;  // another record is publishing this slot: look again
+        uint32_t diff = 0;
+        const uint4 *rv = reinterpret_cast<const uint4 *>(rec);
+#pragma unroll
+        for (int c = 0; c < (KW + 3) / 4; c++) {
+            const uint4 v = __ldcg(rv + c);
+            if (4 * c + 0 < KW) diff |= v.x ^ key.w[(4 * c + 0) < KW ? 4 * c + 0 : 0];
+            if (4 * c + 1 < KW) diff |= v.y ^ key.w[(4 * c + 1) < KW ? 4 * c + 1 : 0];
+            if (4 * c + 2 < KW) diff |= v.z ^ key.w[(4 * c + 2) < KW ? 4 * c + 2 : 0];
+            if (4 * c + 3 < KW) diff |= v.w ^ key.w[(4 * c + 3) < KW ? 4 * c + 3 : 0];
+        }
+        if (diff == 0) {
+            atomicAdd(rec + KW, weight);
+            if (t < st) atomicMin(rec + KW + 1, t);
+            return;
+        }
+        s = (s + 1 == P.capacity) ? 0 : s + 1;
+        probes++;
+    }
+    P.ctr->table_full = 1u;
+}
+
+// Records that failed the filter still define "first occurrence" (pass 2 of the reference
+// does not re-apply the filter, __init__.py:201-206): lower `first` of an existing key.
+template <int K, int PW>
+__device__ __forceinline__ void table_touch_first(const IngestParams &P, const Key<K, PW> &key,
+                                                  uint32_t t)
+{
+    constexpr int KW = K * PW, RW = round_up4(KW + 2);
+    const uint64_t h = hash_key(key);
+    uint64_t s = __umul64hi(h, P.capacity);
+    for (uint64_t probes = 0; probes < P.capacity; probes++) {
+        uint32_t *rec = P.table + s * RW;
+        const uint32_t st = ld_relaxed_u32(rec + KW + 1);
+        if (st == SLOT_EMPTY) return;
+        uint32_t diff = 0;
+#pragma unroll
+        for (int i = 0; i < KW; i++) diff |= __ldcg(rec + i) ^ key.w[i];
+        if (diff == 0) {
+            if (t < st) atomicMin(rec + KW + 1, t);
+            return;
+        }
+        s = (s + 1 == P.capacity) ? 0 : s + 1;
+    }
+}
+
+template <int K, int PW>
+static __global__ void __launch_bounds__(256) ingest_kernel(const __grid_constant__ IngestParams P)
+{
+    extern __shared__ __align__(16) uint8_t smem[];
+    double *lut_d = reinterpret_cast<double *>(smem);   // 128 doubles
+    uint8_t *lut = smem + 1024;                         // 256 bytes
+    uint8_t *stage = smem + 1280;                       // stage_bytes
+    const int tid = threadIdx.x;
+    if (tid < 128) lut_d[tid] = __longlong_as_double((long long)FQD_PHRED_LUT_BITS[tid]);
+    lut[tid] = P.codec.lut[tid];
+    const uint64_t t0 = (uint64_t)blockIdx.x * 256u;
+    const uint32_t nblk = (uint32_t)min((uint64_t)256u, P.n - t0);
+    const uint64_t t = t0 + tid;
+    const bool active = tid < (int)nblk;
+    __syncthreads();
+
+    bool keep = true;
+    if (P.phase == 1) keep = active && !((P.keepmask[t >> 5] >> (t & 31)) & 1u);
+
+    // ---- quality filter (reference _fastqmodule.c:58-75) ----
+    if (P.filter_on && P.phase == 0) {
+        const uint8_t *q = nullptr;
+        uint32_t qlen = 0;
+        if (P.qual_off) {
+            if (active) { q = P.quals + P.qual_off[t]; qlen = (uint32_t)(P.qual_off[t + 1] - P.qual_off[t]); }
+        } else {
+            if (P.stage_bytes) {
+                const uint64_t bytes = (uint64_t)nblk * P.qual_stride;
+                const uint8_t *src = P.quals + t0 * P.qual_stride;
+                if ((reinterpret_cast<uintptr_t>(src) & 15u) == 0) {
+                    const uint4 *s4 = reinterpret_cast<const uint4 *>(src);
+                    uint4 *d4 = reinterpret_cast<uint4 *>(stage);
+                    for (uint32_t i = tid; i < bytes / 16; i += 256) d4[i] = __ldg(s4 + i);
+                    for (uint32_t i = (uint32_t)(bytes & ~15ull) + tid; i < bytes; i += 256) stage[i] = __ldg(src + i);
+                } else {
+                    for (uint32_t i = tid; i < bytes; i += 256) stage[i] = __ldg(src + i);
+                }
+                __syncthreads();
+                q = stage + (size_t)tid * P.qual_stride;
+            } else {
+                q = P.quals + t * P.qual_stride;
+            }
+            if (active) qlen = P.qual_lens ? P.qual_lens[t] : P.qual_len;
+        }
+        if (active) {
+            double total = 0.0;
+            const uint32_t max_score = (126u - P.phred_offset) & 0xFFu;
+            bool bad = false;
+            for (uint32_t i = 0; i < qlen; i++) {
+                const uint32_t c = q[i];
+                const uint32_t score = (c - P.phred_offset) & 0xFFu;   // uint8 wrap (:62)
+                if (score > max_score) {
+                    atomicMin(&P.ctr->phred_err, (unsigned long long)((t << 8) | c));
+                    bad = true;
+                    break;
+                }
+                total = __dadd_rn(total, lut_d[score]);                // left to right (:72)
+            }
+            const double avg = __ddiv_rn(total, (double)qlen);         // (:74), 0/0 = NaN
+            keep = !bad && !(avg > P.max_err);                         // strict; NaN keeps
+        }
+        __syncthreads();   // stage is reused for the keys
+    }
+    if (!active) keep = false;
+
+    if (P.phase == 0) {
+        const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, keep);
+        if ((tid & 31) == 0 && t0 + tid < P.n) P.keepmask[(t0 + tid) >> 5] = ballot;
+    }
+
+    // ---- pack (bit planes) ----
+    const uint8_t *kb = nullptr;
+    uint32_t klen = 0;
+    if (P.key_off) {
+        if (active) { kb = P.keys + P.key_off[t]; klen = (uint32_t)(P.key_off[t + 1] - P.key_off[t]); }
+    } else {
+        if (P.stage_bytes) {
+            const uint64_t bytes = (uint64_t)nblk * P.key_stride;
+            const uint8_t *src = P.keys + t0 * P.key_stride;
+            if ((reinterpret_cast<uintptr_t>(src) & 15u) == 0) {
+                const uint4 *s4 = reinterpret_cast<const uint4 *>(src);
+                uint4 *d4 = reinterpret_cast<uint4 *>(stage);
+                for (uint32_t i = tid; i < bytes / 16; i += 256) d4[i] = __ldg(s4 + i);
+                for (uint32_t i = (uint32_t)(bytes & ~15ull) + tid; i < bytes; i += 256) stage[i] = __ldg(src + i);
+            } else {
+                for (uint32_t i = tid; i < bytes; i += 256) stage[i] = __ldg(src + i);
+            }
+            __syncthreads();
+            kb = stage + (size_t)tid * P.key_stride;
+        } else {
+            kb = P.keys + t * P.key_stride;
+        }
+        if (active) klen = P.key_lens ? P.key_lens[t] : P.key_len;
+    }
+    if (!active) return;
+    if (P.filter_on && P.phase == 0 && !keep) {
+        aggregated_inc(&P.ctr->n_discarded);
+    }
+    if (!keep) return;   // phase 0: filtered out; phase 1: record was kept, nothing to fix
+    if (klen > P.max_len) klen = P.max_len;
+    Key<K, PW> key;
+    uint32_t badbyte = 0;
+    if (!pack_key<K, PW>(kb, klen, P.codec.varlen ? P.max_len : klen, lut, P.pad_code, key, &badbyte)) {
+        // report every unknown byte of this key so one retry with a grown alphabet suffices
+        for (uint32_t i = 0; i < klen; i++) {
+            const uint32_t c = kb[i];
+            if (lut[c] == 0xFF) atomicOr(&P.ctr->unknown[c >> 5], 1u << (c & 31));
+        }
+        return;
+    }
+    if (P.phase == 0) table_insert<K, PW>(P, key, (uint32_t)t);
+    else table_touch_first<K, PW>(P, key, (uint32_t)t);
+}
+
+// min / max of the key lengths (decides PW and whether PAD is needed)
+static __global__ void length_range_kernel(uint64_t n, const uint64_t *off, const uint32_t *lens,
+                                    DevCounters *ctr)
+{
+    uint32_t lo = 0xFFFFFFFFu, hi = 0;
+    for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n;
+         t += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t l = off ? (uint32_t)(off[t + 1] - off[t]) : lens[t];
+        lo = min(lo, l);
+        hi = max(hi, l);
+    }
+    for (int o = 16; o; o >>= 1) {
+        lo = min(lo, __shfl_xor_sync(0xFFFFFFFFu, lo, o));
+        hi = max(hi, __shfl_xor_sync(0xFFFFFFFFu, hi, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMin(&ctr->len_min, lo);
+        atomicMax(&ctr->len_max, hi);
+    }
+}
+
+// ---- gather: claimed slots -> dense unique arrays --------------------------------------
+
+template <int K, int PW>
+static __global__ void __launch_bounds__(256) gather_kernel(uint32_t U, const uint32_t *__restrict__ table,
+                                                     const uint32_t *__restrict__ uslot,
+                                                     uint32_t *__restrict__ ukey,
+                                                     uint32_t *__restrict__ ucount,
+                                                     uint32_t *__restrict__ ufirst,
+                                                     uint32_t *__restrict__ parent_a,
+                                                     uint32_t *__restrict__ parent_b,
+                                                     uint32_t *__restrict__ best)
+{
+    constexpr int KW = K * PW, RW = round_up4(KW + 2);
+    const uint32_t u = blockIdx.x * 256u + threadIdx.x;
+    if (u >= U) return;
+    const uint4 *rec = reinterpret_cast<const uint4 *>(table + (size_t)uslot[u] * RW);
+    uint32_t w[RW];
+#pragma unroll
+    for (int c = 0; c < RW / 4; c++) {
+        const uint4 v = __ldcs(rec + c);
+        w[4 * c] = v.x; w[4 * c + 1] = v.y; w[4 * c + 2] = v.z; w[4 * c + 3] = v.w;
+    }
+#pragma unroll
+    for (int i = 0; i < KW; i++) ukey[(size_t)u * KW + i] = w[i];
+    ucount[u] = w[KW];
+    ufirst[u] = w[KW + 1];
+    parent_a[u] = u;
+    if (parent_b) parent_b[u] = u;
+    if (best) best[u] = u;
+}
+
+static __global__ void __launch_bounds__(256) iota_kernel(uint32_t *p, uint32_t n)
+{
+    const uint32_t i = blockIdx.x * 256u + threadIdx.x;
+    if (i < n) p[i] = i;
+}
+
+// ---- union-find (roots have the smallest id of their set => deterministic labels) ------
+
+__device__ __forceinline__ uint32_t uf_find(uint32_t *parent, uint32_t x)
+{
+    uint32_t p = ld_relaxed_u32(parent + x);
+    while (p != x) {
+        const uint32_t gp = ld_relaxed_u32(parent + p);
+        if (gp != p) atomicMin(parent + x, gp);   // path halving; parents only ever decrease
+        x = p;
+        p = gp;
+    }
+    return x;
+}
+
+__device__ __forceinline__ bool uf_union(uint32_t *parent, uint32_t a, uint32_t b)
+{
+    for (;;) {
+        a = uf_find(parent, a);
+        b = uf_find(parent, b);
+        if (a == b) return false;
+        if (a < b) { const uint32_t t = a; a = b; b = t; }   // hook the larger root under the smaller
+        const uint32_t old = atomicCAS(parent + a, a, b);
+        if (old == a) return true;
+    }
+}
+
+// ---- pigeonhole passes -------------------------------------------------------------------
+
+struct PassParams {
+    uint32_t U;
+    const uint32_t *ukey;
+    const uint32_t *ucount;
+    int d, edit, varlen, method;
+    uint32_t max_len, pad_code;
+    int pass_j, V;
+    uint32_t nb_mask;
+    uint32_t *cnt;          // NB+1 counters -> exclusive offsets after the scan
+    uint32_t *rank;         // U*V
+    uint2 *entries;
+    uint32_t n_entries;
+    uint32_t *parent_full;
+    uint32_t *parent_one;
+    uint8_t *dominated;
+    uint8_t *dead;
+    uint2 *edges;
+    unsigned long long edge_cap;
+    DevCounters *ctr;
+    uint8_t rank_of_code[256];
+};
+
+// Variant v of unique `key` in pass j: which substring is hashed, and whether the entry
+// is the key's own (canonical) block.  Hamming: one variant, block j of d+1.
+// Levenshtein: the probe side enumerates every build length la = len - delta and every
+// shift s the <= d edits allow: s in [-floor((d-delta)/2), floor((d+delta)/2)].
+template <int K, int PW>
+__device__ __forceinline__ bool pass_variant(const Key<K, PW> &key, uint32_t len,
+                                             const PassParams &P, int v, uint64_t &sig,
+                                             bool &build)
+{
+    const uint32_t nb = (uint32_t)P.d + 1u;
+    const uint32_t j = (uint32_t)P.pass_j;
+    if (!P.edit) {
+        const uint32_t st = block_start(len, j, nb);
+        const uint32_t bl = block_start(len, j + 1, nb) - st;
+        sig = block_hash(key, st, bl, ((uint64_t)j << 32) | len);
+        build = true;
+        return true;
+    }
+    const int li = v / (P.d + 1), si = v % (P.d + 1);
+    const int delta = P.varlen ? li - P.d : 0;
+    const int la = (int)len - delta;
+    if (la < 0 || la > (int)P.max_len) return false;
+    const int smin = -((P.d - delta) / 2), smax = (P.d + delta) / 2;
+    const int s = smin + si;
+    if (s > smax) return false;
+    const uint32_t st = block_start((uint32_t)la, j, nb);
+    const uint32_t bl = block_start((uint32_t)la, j + 1, nb) - st;
+    const int pos = (int)st + s;
+    if (pos < 0 || pos + (int)bl > (int)len) return false;
+    sig = block_hash(key, (uint32_t)pos, bl, ((uint64_t)j << 32) | (uint32_t)la);
+    build = (delta == 0 && s == 0);
+    return true;
+}
+
+template <int K, int PW>
+static __global__ void __launch_bounds__(256) sig_count_kernel(const __grid_constant__ PassParams P)
+{
+    const uint32_t u = blockIdx.x * 256u + threadIdx.x;
+    if (u >= P.U) return;
+    Key<K, PW> key;
+    load_key<K, PW>(P.ukey, u, key);
+    const uint32_t len = P.varlen ? key_length(key, P.pad_code, P.max_len) : P.max_len;
+    for (int v = 0; v < P.V; v++) {
+        uint64_t sig;
+        bool build;
+        uint32_t r = RANK_INVALID;
+        if (pass_variant<K, PW>(key, len, P, v, sig, build))
+            r = atomicAdd(P.cnt + ((uint32_t)sig & P.nb_mask), 1u);
+        P.rank[(size_t)u * P.V + v] = r;
+    }
+}
+
+template <int K, int PW>
+static __global__ void __launch_bounds__(256) scatter_kernel(const __grid_constant__ PassParams P)
+{
+    const uint32_t u = blockIdx.x * 256u + threadIdx.x;
+    if (u >= P.U) return;
+    Key<K, PW> key;
+    load_key<K, PW>(P.ukey, u, key);
+    const uint32_t len = P.varlen ? key_length(key, P.pad_code, P.max_len) : P.max_len;
+    for (int v = 0; v < P.V; v++) {
+        const uint32_t r = P.rank[(size_t)u * P.V + v];
+        if (r == RANK_INVALID) continue;
+        uint64_t sig;
+        bool build;
+        pass_variant<K, PW>(key, len, P, v, sig, build);
+        const uint32_t b = (uint32_t)sig & P.nb_mask;
+        const uint32_t lo = P.cnt[b], hi = P.cnt[b + 1];
+        const uint32_t pos = lo + r;
+        uint32_t meta = u | (build ? ENT_BUILD : 0u) | (pos + 1 == hi ? ENT_LAST : 0u);
+        P.entries[pos] = make_uint2((uint32_t)(sig >> 32), meta);
+    }
+}
+
+template <int K, int PW>
+__device__ __forceinline__ void process_edge(const PassParams &P, uint32_t ui, uint32_t uj,
+                                             uint32_t ci, uint32_t cj, const Key<K, PW> &ki,
+                                             const Key<K, PW> &kj, uint32_t &merges)
+{
+    if (uf_union(P.parent_full, ui, uj)) merges++;
+    if (P.method == METHOD_DIRECTIONAL) {
+        // closed form of reference __init__.py:60-91 (DESIGN.md "directional")
+        if (ci >= 2 && (unsigned long long)cj >= 2ull * ci - 1ull) P.dominated[ui] = 1;
+        if (cj >= 2 && (unsigned long long)ci >= 2ull * cj - 1ull) P.dominated[uj] = 1;
+        if (ci == 1 && cj == 1) uf_union(P.parent_one, ui, uj);
+        else if (ci == 1) P.dead[ui] = 1;
+        else if (cj == 1) P.dead[uj] = 1;
+    } else if (P.method == METHOD_ADJACENCY) {
+        const bool i_less = prio_less<K, PW>(ci, ki, cj, kj, P.rank_of_code);
+        const unsigned long long pos = aggregated_inc64(&P.ctr->n_edges);
+        if (pos < P.edge_cap) P.edges[pos] = i_less ? make_uint2(uj, ui) : make_uint2(ui, uj);
+    }
+}
+
+template <int K, int PW>
+static __global__ void __launch_bounds__(256) compare_kernel(const __grid_constant__ PassParams P)
+{
+    const uint32_t i = blockIdx.x * 256u + threadIdx.x;
+    uint32_t merges = 0, cand = 0;
+    if (i < P.cnt[P.nb_mask + 1]) {   // cnt[NB] = number of entries after the scan
+        const uint2 e = P.entries[i];
+        if (!(e.y & ENT_LAST)) {
+            const uint32_t ui = e.y & ENT_UID;
+            bool loaded = false;
+            Key<K, PW> ki;
+            uint32_t li = 0, ci = 0;
+            for (uint32_t j = i + 1;; j++) {
+                const uint2 f = P.entries[j];
+                if (f.x == e.x) {
+                    const uint32_t uj = f.y & ENT_UID;
+                    if (uj != ui && ((e.y | f.y) & ENT_BUILD)) {
+                        if (!loaded) {
+                            load_key<K, PW>(P.ukey, ui, ki);
+                            li = P.varlen ? key_length(ki, P.pad_code, P.max_len) : P.max_len;
+                            ci = P.ucount[ui];
+                            loaded = true;
+                        }
+                        Key<K, PW> kj;
+                        load_key<K, PW>(P.ukey, uj, kj);
+                        cand++;
+                        bool ok;
+                        if (P.edit) {
+                            const uint32_t lj = P.varlen ? key_length(kj, P.pad_code, P.max_len) : P.max_len;
+                            ok = myers_within<K, PW>(ki, li, kj, lj, P.d);
+                        } else {
+                            ok = hamming_within<K, PW>(ki, kj, P.d, P.varlen != 0, P.pad_code);
+                        }
+                        if (ok) process_edge<K, PW>(P, ui, uj, ci, P.ucount[uj], ki, kj, merges);
+                    }
+                }
+                if (f.y & ENT_LAST) break;
+            }
+        }
+    }
+    // per-warp reduction of the two counters
+    for (int o = 16; o; o >>= 1) {
+        merges += __shfl_xor_sync(0xFFFFFFFFu, merges, o);
+        cand += __shfl_xor_sync(0xFFFFFFFFu, cand, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (merges) atomicAdd(&P.ctr->n_merges, merges);
+        if (cand) atomicAdd(&P.ctr->n_candidates, (unsigned long long)cand);
+    }
+}
+
+// ---- exclusive scan over the bucket counters (3 kernels, 4096 items per block) ---------
+
+constexpr int SCAN_ITEMS = 16, SCAN_THREADS = 256, SCAN_TILE = SCAN_ITEMS * SCAN_THREADS;
+
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t *total, uint32_t *warp_sums)
+{
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint32_t inc = v;
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t n = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+        if (lane >= o) inc += n;
+    }
+    if (lane == 31) warp_sums[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+        uint32_t w = lane < (int)(blockDim.x >> 5) ? warp_sums[lane] : 0;
+        uint32_t winc = w;
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t n = __shfl_up_sync(0xFFFFFFFFu, winc, o);
+            if (lane >= o) winc += n;
+        }
+        warp_sums[lane] = winc - w;
+        if (lane == 31) *total = winc;
+    }
+    __syncthreads();
+    return inc - v + warp_sums[wid];
+}
+
+static __global__ void __launch_bounds__(SCAN_THREADS) scan_reduce_kernel(const uint32_t *in, uint32_t n,
+                                                                   uint32_t *block_sums)
+{
+    __shared__ uint32_t warp_sums[32];
+    __shared__ uint32_t total;
+    const uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+    uint32_t s = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) s += (base + k < n) ? in[base + k] : 0u;
+    block_exclusive_scan(s, &total, warp_sums);
+    if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
+}
+
+// single block: exclusive scan of up to 1024*SCAN_ITEMS block sums in place
+static __global__ void __launch_bounds__(1024) scan_sums_kernel(uint32_t *block_sums, uint32_t nblocks,
+                                                         uint32_t *grand_total)
+{
+    __shared__ uint32_t warp_sums[32];
+    __shared__ uint32_t total;
+    const uint32_t base = threadIdx.x * SCAN_ITEMS;
+    uint32_t v[SCAN_ITEMS];
+    uint32_t s = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) { v[k] = (base + k < nblocks) ? block_sums[base + k] : 0u; s += v[k]; }
+    uint32_t off = block_exclusive_scan(s, &total, warp_sums);
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) { if (base + k < nblocks) block_sums[base + k] = off; off += v[k]; }
+    if (threadIdx.x == 0) *grand_total = total;
+}
+
+// writes exclusive offsets in place; element n receives the grand total
+static __global__ void __launch_bounds__(SCAN_THREADS) scan_apply_kernel(uint32_t *data, uint32_t n,
+                                                                  const uint32_t *block_sums,
+                                                                  const uint32_t *grand_total)
+{
+    __shared__ uint32_t warp_sums[32];
+    __shared__ uint32_t total;
+    const uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+    uint32_t v[SCAN_ITEMS];
+    uint32_t s = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) { v[k] = (base + k < n) ? data[base + k] : 0u; s += v[k]; }
+    uint32_t off = block_exclusive_scan(s, &total, warp_sums) + block_sums[blockIdx.x];
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) { if (base + k < n) data[base + k] = off; off += v[k]; }
+    if (blockIdx.x == 0 && threadIdx.x == 0) data[n] = *grand_total;
+}
+
+// ---- selection ----------------------------------------------------------------------------
+
+struct SelectParams {
+    uint32_t U;
+    const uint32_t *ukey;
+    const uint32_t *ucount;
+    const uint32_t *ufirst;
+    uint32_t *parent_full;
+    uint32_t *parent_one;
+    uint32_t *best;          // per root: uid of the best member so far
+    uint32_t *root;          // per unique: root used by the dissection
+    uint8_t *dominated;
+    uint8_t *dead;
+    uint8_t *deadroot;
+    uint8_t *selected;
+    uint8_t *state;          // adjacency: 0 undecided, 1 selected, 2 removed
+    uint32_t *stamp;
+    const uint2 *edges;
+    unsigned long long n_edges;
+    uint32_t round;
+    uint32_t *bitmap;
+    uint32_t *minfirst;
+    int method;
+    DevCounters *ctr;
+    uint8_t rank_of_code[256];
+};
+
+// Per root keep the member with the largest (count, key): the head of the reference's
+// descending sort (__init__.py:99-101) resp. the survivor of a singleton chain.
+template <int K, int PW>
+static __global__ void __launch_bounds__(256) root_best_kernel(const __grid_constant__ SelectParams P, int only_singletons)
+{
+    const uint32_t u = blockIdx.x * 256u + threadIdx.x;
+    if (u >= P.U) return;
+    const uint32_t cu = P.ucount[u];
+    uint32_t *parent = only_singletons ? P.parent_one : P.parent_full;
+    if (only_singletons && cu != 1) { P.root[u] = u; return; }
+    const uint32_t r = uf_find(parent, u);
+    P.root[u] = r;
+    if (only_singletons && P.dead[u]) P.deadroot[r] = 1;
+    Key<K, PW> ku;
+    bool loaded = false;
+    uint32_t cur = ld_relaxed_u32(P.best + r);
+    while (cur != u) {
+        if (!loaded) { load_key<K, PW>(P.ukey, u, ku); loaded = true; }
+        Key<K, PW> kc;
+        load_key<K, PW>(P.ukey, cur, kc);
+        const uint32_t cc = P.ucount[cur];
+        if (!prio_less<K, PW>(cc, kc, cu, ku, P.rank_of_code)) break;   // cur >= u
+        const uint32_t old = atomicCAS(P.best + r, cur, u);
+        if (old == cur) break;
+        cur = old;
+    }
+}
+
+static __global__ void __launch_bounds__(256) select_kernel(const __grid_constant__ SelectParams P)
+{
+    const uint32_t u = blockIdx.x * 256u + threadIdx.x;
+    bool sel = false;
+    if (u < P.U) {
+        if (P.method == METHOD_DIRECTIONAL) {
+            const uint32_t c = P.ucount[u];
+            if (c >= 2) sel = !P.dominated[u];
+            else { const uint32_t r = P.root[u]; sel = !P.deadroot[r] && P.best[r] == u; }
+        } else if (P.method == METHOD_HIGHEST) {
+            sel = P.best[P.root[u]] == u;
+        } else {
+            sel = P.state[u] == 1;
+        }
+        P.selected[u] = sel ? 1 : 0;
+        if (sel && P.bitmap) {
+            const uint32_t f = P.ufirst[u];
+            atomicOr(P.bitmap + (f >> 5), 1u << (f & 31));
+        }
+    }
+    const uint32_t b = __ballot_sync(0xFFFFFFFFu, sel);
+    if ((threadIdx.x & 31) == 0 && b) atomicAdd(&P.ctr->n_selected, (uint32_t)__popc(b));
+}
+
+// adjacency (__init__.py:105-122) == greedy maximal independent set in descending
+// (count, key) order.  Round r: an undecided key whose undecided/selected higher
+// neighbours are all gone becomes selected; a key with a selected higher neighbour is
+// removed.  edges hold (higher, lower).
+static __global__ void __launch_bounds__(256) adj_edge_kernel(const __grid_constant__ SelectParams P)
+{
+    const unsigned long long e = (unsigned long long)blockIdx.x * 256u + threadIdx.x;
+    if (e >= P.n_edges) return;
+    const uint2 ed = P.edges[e];
+    const uint8_t sh = P.state[ed.x], sl = P.state[ed.y];
+    if (sl != 0) return;
+    if (sh == 1) P.state[ed.y] = 2;
+    else if (sh == 0) P.stamp[ed.y] = P.round;
+}
+static __global__ void __launch_bounds__(256) adj_node_kernel(const __grid_constant__ SelectParams P)
+{
+    const uint32_t u = blockIdx.x * 256u + threadIdx.x;
+    bool und = false;
+    if (u < P.U && P.state[u] == 0) {
+        if (P.stamp[u] != P.round) P.state[u] = 1;
+        else und = true;
+    }
+    const uint32_t b = __ballot_sync(0xFFFFFFFFu, und);
+    if ((threadIdx.x & 31) == 0 && b) atomicAdd(&P.ctr->undecided, (uint32_t)__popc(b));
+}
+
+// canonical cluster label for the result view: smallest `first` among the members
+static __global__ void __launch_bounds__(256) label_min_kernel(const __grid_constant__ SelectParams P)
+{
+    const uint32_t u = blockIdx.x * 256u + threadIdx.x;
+    if (u >= P.U) return;
+    const uint32_t r = uf_find(P.parent_full, u);
+    P.root[u] = r;
+    atomicMin(P.minfirst + r, P.ufirst[u]);
+}
+
+// ---- function-level kernels (batched _fastq / _distance entry points) -------------------
+
+static __global__ void __launch_bounds__(128) error_rate_kernel(const uint8_t *phred, const uint64_t *off,
+                                                         uint64_t n, uint32_t phred_offset,
+                                                         double *out, DevCounters *ctr)
+{
+    __shared__ double lut_d[128];
+    if (threadIdx.x < 128) lut_d[threadIdx.x] = __longlong_as_double((long long)FQD_PHRED_LUT_BITS[threadIdx.x]);
+    __syncthreads();
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const uint8_t *q = phred + off[t];
+    const uint64_t len = off[t + 1] - off[t];
+    const uint32_t max_score = (126u - phred_offset) & 0xFFu;
+    double total = 0.0;
+    for (uint64_t i = 0; i < len; i++) {
+        const uint32_t c = q[i];
+        const uint32_t score = (c - phred_offset) & 0xFFu;
+        if (score > max_score) {
+            atomicMin(&ctr->phred_err, (unsigned long long)((t << 8) | c));
+            return;
+        }
+        total = __dadd_rn(total, lut_d[score]);
+    }
+    out[t] = __ddiv_rn(total, (double)len);
+}
+
+// Byte-level predicates for arbitrary (latin-1) strings of any length: the reference's
+// within_distance accepts any 1-byte-kind str (_distancemodule.c:64-73).  Hamming: byte
+// compare with early exit (distances.h:8-31).  Levenshtein: banded DP, band |i-j| <= d,
+// three rolling rows in local memory are avoided by keeping one row of 2d+1 cells.
+constexpr int MAX_BAND_D = 31;
+static __global__ void __launch_bounds__(128) within_distance_kernel(const uint8_t *a, const uint64_t *aoff,
+                                                              const uint8_t *b, const uint64_t *boff,
+                                                              uint64_t n, int d, int edit, uint8_t *out)
+{
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const uint8_t *x = a + aoff[t], *y = b + boff[t];
+    const long long lx = (long long)(aoff[t + 1] - aoff[t]), ly = (long long)(boff[t + 1] - boff[t]);
+    if (!edit) {
+        if (lx != ly) { out[t] = 0; return; }
+        int budget = d;
+        for (long long i = 0; i < lx; i++) {
+            if (x[i] != y[i]) { if (--budget < 0) { out[t] = 0; return; } }
+        }
+        out[t] = 1;
+        return;
+    }
+    const long long diff = lx > ly ? lx - ly : ly - lx;
+    if (d < 0 || diff > d) { out[t] = 0; return; }
+    // row[k] holds D[i][i - d + k] for k in 0..2d
+    const int INF = 1 << 28;
+    int row[2 * MAX_BAND_D + 1];
+    const int bw = 2 * d + 1;
+    for (int k = 0; k < bw; k++) { const long long j = (long long)k - d; row[k] = (j >= 0 && j <= ly && j <= d) ? (int)j : INF; }
+    for (long long i = 1; i <= lx; i++) {
+        int prev_left = INF;   // D[i][j-1] of the new row
+        for (int k = 0; k < bw; k++) {
+            const long long j = i - d + k;
+            int v = INF;
+            if (j >= 0 && j <= ly) {
+                if (j == 0) v = i <= d ? (int)i : INF;
+                else {
+                    const int sub = row[k] + (x[i - 1] != y[j - 1]);       // D[i-1][j-1]
+                    const int del = (k + 1 < bw) ? row[k + 1] + 1 : INF;   // D[i-1][j]
+                    const int ins = prev_left + 1;                          // D[i][j-1]
+                    v = min(sub, min(del, ins));
+                }
+            }
+            row[k] = v;
+            prev_left = v;
+        }
+    }
+    const long long kk = ly - lx + d;   // column of D[lx][ly] in the last row
+    out[t] = (kk >= 0 && kk < bw && row[kk] <= d) ? 1 : 0;
+}
+
+}  // namespace fqd
