@@ -1,0 +1,459 @@
+#!/usr/bin/env python3
+"""bench.py -- unique keys clustered per second on BASELINE.json's headline workload
+(config 5: 100 M reads, 12-nt UMI + 24-nt prefix = 36-nt key, Hamming d=1, directional).
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (CUDA path)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path
+
+One "step" is one complete pass of the hot path (quality filter off for this config, pack,
+exact dedupe, neighbour search, components, dissection) over the whole synthetic batch.
+``value`` is measured with the batch resident in HBM (CUDA events inside the library, on its
+stream); ``e2e`` repeats it through the same C-ABI call with pinned HOST buffers, H2D and
+D2H inside the timed region.  Inputs (3.6 GB) are far larger than the 126 MB L2, so no
+explicit flush is needed between iterations.  The JSON line is printed by rank 0.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "unique UMIs clustered/sec (d=1, directional)"
+UNIT = "unique keys/s"
+
+
+def env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+# ---------------------------------------------------------------------------------------
+# workload
+# ---------------------------------------------------------------------------------------
+
+def make_config(args):
+    from fastqdedup_b200 import synth
+    cfg = synth.CONFIGS[args.config]
+    n = env_int("FQD_BENCH_READS", 0) or args.reads or cfg.n_reads
+    if n != cfg.n_reads:
+        cfg = cfg.scaled(n)
+    return cfg
+
+
+def generate_into(cfg, start, stop, out_keys, out_quals=None, threads=8):
+    """Fill out_keys[(stop-start), L] with reads [start, stop) of the synthetic data set."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    from fastqdedup_b200 import synth
+    src = synth.SynthSource(cfg)
+    step = synth.CHUNK
+    bounds = []
+    t = start
+    while t < stop:
+        hi = min(stop, (t // step + 1) * step)
+        bounds.append((t, hi))
+        t = hi
+
+    def work(b):
+        lo, hi = b
+        k, _, q = src.reads(lo, hi)
+        out_keys[lo - start:hi - start] = k
+        if out_quals is not None and q is not None:
+            out_quals[lo - start:hi - start] = q
+
+    with ThreadPoolExecutor(max_workers=threads) as ex:
+        list(ex.map(work, bounds))
+
+
+class PinnedArray:
+    """uint8 [n, L] array in cudaHostAlloc'ed memory (so H2D copies can stream)."""
+
+    def __init__(self, lib, shape):
+        self.lib = lib
+        self.nbytes = int(np.prod(shape))
+        p = ctypes.c_void_p()
+        from fastqdedup_b200 import _native
+        _native.check(lib.fqd_host_alloc(max(self.nbytes, 16), ctypes.byref(p)))
+        self.ptr = p.value
+        buf = (ctypes.c_uint8 * max(self.nbytes, 1)).from_address(self.ptr)
+        self.array = np.frombuffer(buf, dtype=np.uint8, count=self.nbytes).reshape(shape)
+
+    def free(self):
+        if self.ptr:
+            self.array = None
+            self.lib.fqd_host_free(ctypes.c_void_p(self.ptr))
+            self.ptr = None
+
+
+# ---------------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------------
+
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap,power.draw")
+
+    def __init__(self, device):
+        self.device = device
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.device}", f"--query-gpu={self.FIELDS}",
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0])); smax.append(float(parts[1]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[2:6]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": max(smax) if smax else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------------------
+# roofline bookkeeping (DESIGN.md "Algorithmic bytes")
+# ---------------------------------------------------------------------------------------
+
+def survey_key_bytes(L):
+    """W of SURVEY.md section 8: 2-bit plane + N-mask plane, in bytes."""
+    return 4 * ((L + 15) // 16) + 4 * ((L + 31) // 32)
+
+
+def algorithmic_bytes(cfg, n, n_ok, u, passes, filter_on):
+    W = survey_key_bytes(cfg.key_length)
+    R = W + 4
+    total = (n * cfg.key_length if filter_on else 0) + n_ok * W + u * (R + 4) + 3 * passes * u * R + 9 * u
+    ingest = (n * cfg.key_length if filter_on else 0) + n_ok * W + u * (R + 4)
+    return total, ingest
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ---------------------------------------------------------------------------------------
+# CPU reference timing (oracle/_ref: the unmodified reference, single thread by construction)
+# ---------------------------------------------------------------------------------------
+
+def time_reference(cfg, keys, quals):
+    """Exactly the loops of deduplicate_cluster (reference __init__.py:240-276) without file
+    I/O.  Returns (uniques, seconds_total, split dict)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import ref_loader
+    ref = ref_loader.load_reference()
+    kind = "reference"
+    if ref is None:
+        # no compiled reference on this box: the C port of the same algorithm (brute-force
+        # neighbour search, so only a small sample finishes in seconds)
+        import oracle
+        cap = 40_000
+        keys = keys[:cap]
+        quals = None if quals is None else quals[:cap]
+        t0 = time.perf_counter()
+        r = oracle.cluster(keys, quals, cfg.max_distance, cfg.use_edit_distance, cfg.method,
+                           cfg.max_average_error_rate)
+        dt = time.perf_counter() - t0
+        return r["number_of_uniques"], dt, {"total_s": dt}, "port"
+    key_strs = [bytes(row).decode("latin-1") for row in keys]
+    filter_on = cfg.max_average_error_rate < 1.0 and quals is not None
+    qual_strs = [bytes(row).decode("latin-1") for row in quals] if filter_on else None
+    func = ref.CLUSTER_DISSECTION_METHODS[cfg.method]
+    t0 = time.perf_counter()
+    trie = ref.Trie(alphabet="ACGTN")
+    for t, key in enumerate(key_strs):
+        if filter_on and ref.fastq_average_error_rate(qual_strs[t]) > cfg.max_average_error_rate:
+            continue
+        trie.add_sequence(key)
+    t1 = time.perf_counter()
+    clusters = []
+    while trie.number_of_sequences:
+        clusters.append(trie.pop_cluster(cfg.max_distance, cfg.use_edit_distance))
+    t2 = time.perf_counter()
+    selected = set()
+    uniques = 0
+    for cl in clusters:
+        uniques += len(cl)
+        for k in func(cl, cfg.max_distance, cfg.use_edit_distance):
+            selected.add(hash(k))
+    t3 = time.perf_counter()
+    split = {"add_s": round(t1 - t0, 3), "pop_s": round(t2 - t1, 3), "dissect_s": round(t3 - t2, 3)}
+    return uniques, t3 - t0, split, kind
+
+
+def run_reference_arm(args, rank, world):
+    if rank != 0:
+        return
+    cfg = make_config(args)
+    sample = min(cfg.n_reads, env_int("FQD_REF_SAMPLE", 1_000_000))
+    from fastqdedup_b200 import synth
+    src = synth.SynthSource(cfg)
+    keys, _, quals = src.reads(0, sample)
+    times, uniques = [], 0
+    for it in range(args.warmup + args.steps):
+        uniques, dt, split, kind = time_reference(cfg, keys, quals)
+        if it >= args.warmup:
+            times.append(dt)
+        log(f"[reference] step {it}: {uniques} uniques in {dt:.2f}s {split}")
+    ms = 1e3 * sum(times) / len(times)
+    value = uniques / (ms / 1e3)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u32",
+        "data": "synthetic",
+        "config": workload_config(cfg, args.gpus),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": kind,
+                         "sample": f"first {sample} of {cfg.n_reads} reads per step "
+                                   f"({uniques} unique keys); add+pop_cluster+dissection, "
+                                   f"single thread (the reference has no threading)"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(cfg, gpus):
+    return {"workload": f"BASELINE config 5: {cfg.n_reads} reads, {cfg.key_length}-nt key "
+                        f"(12-nt UMI + 24-nt prefix), Hamming d={cfg.max_distance}, {cfg.method}, "
+                        f"quality filter off (-E)",
+            "reads": cfg.n_reads, "key_length": cfg.key_length, "molecules": cfg.n_molecules,
+            "max_distance": cfg.max_distance, "method": cfg.method,
+            "sharding": "1 GPU" if gpus == 1 else f"{gpus} GPUs, reads split contiguously",
+            "l2": "inputs (reads x key bytes) exceed the 126 MB L2; no flush needed"}
+
+
+# ---------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------
+
+def run_ours(args, rank, world, local_rank):
+    from fastqdedup_b200 import _native
+    from fastqdedup_b200.clustering import cluster_device
+    from fastqdedup_b200._native import ClusterJob, METHODS, MEM_HOST
+
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist_mod
+        torch.cuda.set_device(local_rank)
+        dist_mod.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist = dist_mod
+
+    cfg = make_config(args)
+    if world > 1:
+        from fastqdedup_b200 import multigpu
+        return multigpu.bench_entry(args, cfg, rank, world, local_rank, dist, globals())
+
+    lib = _native.load()
+    if lib.fqd_device_count() < 1:
+        raise SystemExit("bench.py: no CUDA device (the product has no CPU fallback)")
+    ctx = _native.Context(local_rank)
+    n, L = cfg.n_reads, cfg.key_length
+    filter_on = cfg.max_average_error_rate < 1.0
+
+    t0 = time.time()
+    host_keys = PinnedArray(lib, (n, L))
+    host_quals = PinnedArray(lib, (n, L)) if cfg.quality_mix else None
+    generate_into(cfg, 0, n, host_keys.array, None if host_quals is None else host_quals.array)
+    log(f"[bench] generated {n} reads x {L} nt in {time.time() - t0:.1f}s")
+
+    d_keys = ctx.upload(host_keys.array)
+    d_quals = ctx.upload(host_quals.array) if host_quals is not None else None
+    bitmap_words = (n + 31) // 32
+    d_bitmap = ctx.device_alloc(bitmap_words * 4)
+
+    def device_step():
+        return cluster_device(ctx, n, d_keys, L, quals_ptr=d_quals, qual_length=L,
+                              max_distance=cfg.max_distance, use_edit_distance=cfg.use_edit_distance,
+                              method=cfg.method, max_average_error_rate=cfg.max_average_error_rate,
+                              bitmap_ptr=d_bitmap)
+
+    for _ in range(args.warmup):
+        st = device_step()
+    ctx.synchronize()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    stats = []
+    wall0 = time.perf_counter()
+    for _ in range(args.steps):
+        stats.append(device_step())
+    ctx.synchronize()
+    wall = time.perf_counter() - wall0
+    clocks = sampler.stop()
+
+    dev_ms = [s.ms_total for s in stats]
+    ms_per_step = float(np.mean(dev_ms))
+    st = stats[-1]
+    U = st.number_of_uniques
+    value = U / (ms_per_step / 1e3)
+
+    # ---- e2e: same call with pinned host buffers, copies inside the timed region ----
+    host_bitmap = PinnedArray(lib, (bitmap_words * 4,))
+    job = ClusterJob()
+    job.n_records = n
+    job.keys = host_keys.ptr
+    job.key_stride = job.key_length = L
+    if host_quals is not None:
+        job.quals = host_quals.ptr
+        job.qual_stride = job.qual_length = L
+    job.max_distance = cfg.max_distance
+    job.use_edit_distance = int(cfg.use_edit_distance)
+    job.method = METHODS[cfg.method]
+    job.memory_space = MEM_HOST
+    job.max_average_error_rate = cfg.max_average_error_rate
+    job.phred_offset = 33
+    e2e_steps = max(1, min(args.steps, 5))
+    ctx.cluster(job, host_bitmap.ptr)          # warm-up
+    e0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        est = ctx.cluster(job, host_bitmap.ptr)
+    e2e_s = (time.perf_counter() - e0) / e2e_steps
+    h2d = n * L * (2 if host_quals is not None else 1)
+    d2h = bitmap_words * 4
+    # the e2e result is the same set as the device-resident one
+    dev_bitmap = ctx.download(d_bitmap, bitmap_words * 4, np.uint32)
+    assert np.array_equal(dev_bitmap, host_bitmap.array.view(np.uint32)), "e2e and device-resident results differ"
+    assert est.number_selected == st.number_selected
+
+    # ---- roofline of the dominant kernel ----
+    total_b, ingest_b = algorithmic_bytes(cfg, n, st.number_of_sequences, U, st.n_passes, filter_on)
+    peak, peak_src = measured_peak()
+    kernels = {"ingest_kernel": float(np.mean([s.ms_ingest_kernel for s in stats])),
+               "compare_kernel(all passes)": float(np.mean([s.ms_compare for s in stats])),
+               "bucket build (sig+scan+scatter)": float(np.mean([s.ms_bucket_build for s in stats])),
+               "table clear (memset)": float(np.mean([s.ms_table_clear for s in stats])),
+               "gather": float(np.mean([s.ms_gather for s in stats])),
+               "select": float(np.mean([s.ms_select for s in stats]))}
+    ingest_ms = kernels["ingest_kernel"]
+    achieved = ingest_b / (ingest_ms / 1e3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get("ingest_kernel_dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "kernel": "ingest_kernel<3,2> (filter+pack+exact dedupe)",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": ingest_b,
+                "kernel_ms": ingest_ms,
+                "whole_path": {"algorithmic_bytes": total_b,
+                               "bytes_per_unique": total_b / max(U, 1),
+                               "achieved_gbs": total_b / (ms_per_step / 1e3) / 1e9,
+                               "frac": total_b / (ms_per_step / 1e3) / 1e9 / peak},
+                "stage_ms": kernels}
+
+    # ---- CPU baseline on a bounded sample of the same workload ----
+    sample = min(n, env_int("FQD_CPU_SAMPLE", 2_000_000))
+    uniq_s, secs, split, kind = time_reference(
+        cfg, host_keys.array[:sample], None if host_quals is None else host_quals.array[:sample])
+    cpu = {"value": uniq_s / secs, "unit": UNIT, "cores": 1, "kind": kind,
+           "sample": f"first {sample} of {n} reads ({uniq_s} unique keys) in {secs:.1f}s {split}; "
+                     f"single thread (the reference has no threading), "
+                     f"host has {os.cpu_count()} logical cores"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+        "config": workload_config(cfg, 1),
+        "unique_keys": int(U), "clusters": int(st.number_of_clusters),
+        "selected": int(st.number_selected), "candidate_pairs": int(st.candidate_pairs),
+        "wall_ms_per_step": 1e3 * wall / args.steps,
+        "e2e": {"value": U / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+                "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * e2e_s,
+                "steps": e2e_steps, "h2d_ms": est.ms_h2d},
+        "gpu_launches": int(sum(s.launches for s in stats)),
+        "clocks": clocks,
+        "roofline": roofline,
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line), flush=True)
+    ctx.device_free(d_keys)
+    if d_quals:
+        ctx.device_free(d_quals)
+    ctx.device_free(d_bitmap)
+    host_bitmap.free()
+    host_keys.free()
+    if host_quals is not None:
+        host_quals.free()
+    ctx.close()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=("ours", "reference"), default="ours")
+    ap.add_argument("--config", default="cfg5")
+    ap.add_argument("--reads", type=int, default=0, help="override the read count (debugging)")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+    if env_int("FQD_WATCHDOG", 0):
+        import faulthandler
+        faulthandler.dump_traceback_later(env_int("FQD_WATCHDOG", 0), exit=True)
+    rank = env_int("RANK", 0)
+    world = env_int("WORLD_SIZE", 1)
+    local_rank = env_int("LOCAL_RANK", 0)
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+    if args.warmup < 3:
+        log("[bench] note: fewer than 3 warm-up steps requested; using 3")
+        args.warmup = 3
+    run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -65,11 +65,12 @@ class ClusterStats(Structure):
         ("n_passes", c_uint32),
         ("ms_total", c_float), ("ms_ingest", c_float), ("ms_gather", c_float),
         ("ms_neighbour", c_float), ("ms_select", c_float), ("ms_h2d", c_float),
-        ("ms_compare", c_float), ("reserved_f", c_float),
+        ("ms_compare", c_float), ("ms_ingest_kernel", c_float), ("ms_table_clear", c_float),
+        ("ms_bucket_build", c_float), ("launches", c_uint32), ("reserved_u", c_uint32),
     ]
 
     def as_dict(self):
-        return {name: getattr(self, name) for name, _ in self._fields_ if name != "reserved_f"}
+        return {name: getattr(self, name) for name, _ in self._fields_ if name != "reserved_u"}
 
 
 # every symbol include/fqd_b200.h declares (tests/test_abi.py checks the library exports them)

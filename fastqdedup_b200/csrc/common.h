@@ -48,7 +48,7 @@ struct fqd_context {
     cudaMemPool_t pool = nullptr;
     fqd::DevCounters *d_ctr = nullptr;
     fqd::DevCounters *h_ctr = nullptr;   // pinned
-    cudaEvent_t ev[8] = {};
+    cudaEvent_t ev[12] = {};
     fqd_result res;
     int sm_count = 148;
 };

@@ -88,6 +88,8 @@ int run_typed(fqd_context *ctx, const DeviceJob &job, const Codec &codec, fqd_cl
     FQD_TRY(uslot.alloc(ctx, n * sizeof(uint32_t)));
     FQD_TRY(keepmask.alloc(ctx, (size_t)cdiv(n, 32) * sizeof(uint32_t)));
     FQD_CUDA(cudaMemsetAsync(table.p, 0xFF, capacity * RW * sizeof(uint32_t), s));
+    const int t_cleared = tm.mark();
+    uint32_t launches = 0;
 
     IngestParams ip{};
     ip.n = n;
@@ -121,6 +123,8 @@ int run_typed(fqd_context *ctx, const DeviceJob &job, const Codec &codec, fqd_cl
                                   (int)smem));
     ip.phase = 0;
     ingest_kernel<K, PW><<<cdiv(n, 256), 256, smem, s>>>(ip);
+    launches++;
+    const int t_ingest_k = tm.mark();
     FQD_CUDA(cudaGetLastError());
     FQD_TRY(fetch_counters(ctx));
     const DevCounters c1 = *ctx->h_ctr;
@@ -138,6 +142,7 @@ int run_typed(fqd_context *ctx, const DeviceJob &job, const Codec &codec, fqd_cl
     if (job.filter_on && c1.n_discarded) {
         ip.phase = 1;
         ingest_kernel<K, PW><<<cdiv(n, 256), 256, smem, s>>>(ip);
+        launches++;
         FQD_CUDA(cudaGetLastError());
     }
     const uint32_t U = c1.n_unique;
@@ -158,6 +163,7 @@ int run_typed(fqd_context *ctx, const DeviceJob &job, const Codec &codec, fqd_cl
     FQD_TRY(selected.alloc(ctx, (size_t)U));
     if (directional) FQD_TRY(parent_one.alloc(ctx, (size_t)U * 4));
     if (job.method != METHOD_ADJACENCY) FQD_TRY(best.alloc(ctx, (size_t)U * 4));
+    if (U) launches++;
     if (U)
         gather_kernel<K, PW><<<cdiv(U, 256), 256, 0, s>>>(U, table.as<uint32_t>(), uslot.as<uint32_t>(),
                                                           ukey.as<uint32_t>(), ucount.as<uint32_t>(),
@@ -217,6 +223,7 @@ int run_typed(fqd_context *ctx, const DeviceJob &job, const Codec &codec, fqd_cl
                                                grand.as<uint32_t>()));
                 scatter_kernel<K, PW><<<cdiv(U, 256), 256, 0, s>>>(pp);
                 pp.n_entries = (uint32_t)E;   // upper bound; the kernel stops at cnt[NB]
+                launches += 6;   // sig_count, 3 scan kernels, scatter, compare
                 FQD_CUDA(cudaEventRecord(cev[2 * j], s));
                 compare_kernel<K, PW><<<cdiv(E, 256), 256, 0, s>>>(pp);
                 FQD_CUDA(cudaEventRecord(cev[2 * j + 1], s));
@@ -233,6 +240,7 @@ int run_typed(fqd_context *ctx, const DeviceJob &job, const Codec &codec, fqd_cl
             ctx->h_ctr->n_edges = 0; ctx->h_ctr->n_merges = 0; ctx->h_ctr->n_candidates = 0;
             FQD_CUDA(cudaMemcpyAsync(ctx->d_ctr, ctx->h_ctr, sizeof(DevCounters), cudaMemcpyHostToDevice, s));
             iota_kernel<<<cdiv(U, 256), 256, 0, s>>>(parent_full.as<uint32_t>(), U);
+            launches++;
         }
         FQD_CUDA(cudaStreamSynchronize(s));
         for (int j = 0; j < npass; j++) {
@@ -258,8 +266,10 @@ int run_typed(fqd_context *ctx, const DeviceJob &job, const Codec &codec, fqd_cl
     if (U) {
         if (job.method == METHOD_DIRECTIONAL) {
             root_best_kernel<K, PW><<<cdiv(U, 256), 256, 0, s>>>(sp, 1);
+            launches++;
         } else if (job.method == METHOD_HIGHEST) {
             root_best_kernel<K, PW><<<cdiv(U, 256), 256, 0, s>>>(sp, 0);
+            launches++;
         } else {
             FQD_TRY(state.alloc(ctx, U)); FQD_TRY(stamp.alloc(ctx, (size_t)U * 4));
             FQD_CUDA(cudaMemsetAsync(state.p, 0, U, s));
@@ -272,14 +282,16 @@ int run_typed(fqd_context *ctx, const DeviceJob &job, const Codec &codec, fqd_cl
             for (uint32_t round = 1;; round++) {
                 sp.round = round;
                 FQD_CUDA(cudaMemsetAsync(&ctx->d_ctr->undecided, 0, 4, s));
-                if (sp.n_edges) adj_edge_kernel<<<cdiv(sp.n_edges, 256), 256, 0, s>>>(sp);
+                if (sp.n_edges) { adj_edge_kernel<<<cdiv(sp.n_edges, 256), 256, 0, s>>>(sp); launches++; }
                 adj_node_kernel<<<cdiv(U, 256), 256, 0, s>>>(sp);
+                launches++;
                 FQD_TRY(fetch_counters(ctx));
                 if (ctx->h_ctr->undecided == 0) break;
                 if (round > U + 2) { set_error("internal: adjacency rounds did not converge"); return FQD_ERR_CUDA; }
             }
         }
         select_kernel<<<cdiv(U, 256), 256, 0, s>>>(sp);
+        launches++;
         FQD_CUDA(cudaGetLastError());
     }
     FQD_TRY(fetch_counters(ctx));
@@ -295,6 +307,10 @@ int run_typed(fqd_context *ctx, const DeviceJob &job, const Codec &codec, fqd_cl
     st->ms_neighbour = tm.ms(t_gather, t_pass);
     st->ms_select = tm.ms(t_pass, t_end);
     st->ms_compare = ms_compare;
+    st->ms_table_clear = tm.ms(t_begin, t_cleared);
+    st->ms_ingest_kernel = tm.ms(t_cleared, t_ingest_k);
+    st->ms_bucket_build = st->ms_neighbour - ms_compare;
+    st->launches = launches;
 
     ctx->res.U = U;
     ctx->res.n_selected = c2.n_selected;

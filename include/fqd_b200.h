@@ -123,7 +123,11 @@ typedef struct {
     float ms_select;               /* components + dissection + output */
     float ms_h2d;                  /* host -> device staging (memory_space == HOST) */
     float ms_compare;              /* the compare kernels alone (inside ms_neighbour) */
-    float reserved_f;
+    float ms_ingest_kernel;        /* the ingest kernel launch alone (inside ms_ingest) */
+    float ms_table_clear;          /* clearing the dedupe table (inside ms_ingest) */
+    float ms_bucket_build;         /* signature count + scan + scatter (inside ms_neighbour) */
+    uint32_t launches;             /* kernels launched by this job */
+    uint32_t reserved_u;
 } fqd_cluster_stats;
 
 /* Runs the job.  On success the per-unique result stays in the context until the next

@@ -12,7 +12,8 @@ What it does (reference ``setup.py:52-56``):
   from the read-only reference tree into ``oracle/_ref/fastqdedup/_X<EXT_SUFFIX>``;
 * byte-compiles the reference's ``__init__.py`` (the three cluster dissection
   functions and ``deduplicate_cluster``, ``src/fastqdedup/__init__.py:60-288``) into
-  a source-less ``oracle/_ref/fastqdedup/__init__.pyc``.
+  a source-less ``oracle/_ref/fastqdedup/package_init.bin`` (CPython bytecode; not named
+  ``.pyc`` because repository snapshots drop ``*.pyc``), loaded by ``oracle/ref_loader.py``.
 
 Only binaries are written (``.so`` / ``.pyc``); no reference source file is copied
 into this repository, and ``oracle/_ref/`` is git-ignored.  The reference tree does
@@ -29,11 +30,12 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 REF_SRC = "/root/reference/src/fastqdedup"
 OUT_PKG = os.path.join(HERE, "_ref", "fastqdedup")
 MODULES = ("trie", "distance", "fastq")
+BYTECODE = "package_init.bin"
 
 
 def ref_is_built() -> bool:
     suffix = sysconfig.get_config_var("EXT_SUFFIX")
-    names = [f"_{m}{suffix}" for m in MODULES] + ["__init__.pyc"]
+    names = [f"_{m}{suffix}" for m in MODULES] + [BYTECODE]
     return all(os.path.exists(os.path.join(OUT_PKG, n)) for n in names)
 
 
@@ -53,7 +55,7 @@ def build(force: bool = False) -> bool:
                os.path.join(REF_SRC, f"_{m}module.c"), "-o", out]
         subprocess.run(cmd, check=True)
     py_compile.compile(os.path.join(REF_SRC, "__init__.py"),
-                       cfile=os.path.join(OUT_PKG, "__init__.pyc"),
+                       cfile=os.path.join(OUT_PKG, BYTECODE),
                        doraise=True)
     return True
 

@@ -6,6 +6,8 @@ The reference package is imported under its own name ``fastqdedup`` from
 ``oracle/stubs``.  Returns ``None`` when ``oracle/_ref`` was never built.
 """
 import importlib
+import importlib.machinery
+import importlib.util
 import os
 import sys
 
@@ -24,8 +26,20 @@ def load_reference():
         sys.path.pop(0)
     if not build_ref.build():
         return None
-    for p in (os.path.join(HERE, "stubs"), os.path.join(HERE, "_ref")):
-        if p not in sys.path:
-            sys.path.insert(0, p)
-    _cached = importlib.import_module("fastqdedup")
+    stubs = os.path.join(HERE, "stubs")
+    if stubs not in sys.path:
+        sys.path.insert(0, stubs)
+    pkg_dir = os.path.join(HERE, "_ref", "fastqdedup")
+    path = os.path.join(pkg_dir, build_ref.BYTECODE)
+    loader = importlib.machinery.SourcelessFileLoader("fastqdedup", path)
+    spec = importlib.util.spec_from_file_location("fastqdedup", path, loader=loader,
+                                                  submodule_search_locations=[pkg_dir])
+    module = importlib.util.module_from_spec(spec)
+    sys.modules["fastqdedup"] = module
+    try:
+        spec.loader.exec_module(module)
+    except BaseException:
+        sys.modules.pop("fastqdedup", None)
+        raise
+    _cached = module
     return _cached
