@@ -1,0 +1,70 @@
+// key_probe.cpp -- host build of fastqdedup_b200/csrc/key.cuh for the CPU test-suite.
+// The device kernels use exactly these inline functions; compiling them for the host lets
+// tests/test_key_primitives.py check packing, Hamming, Myers, ordering and block hashing
+// against the oracle where no GPU exists.  Test scaffolding only, never shipped.
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "key.cuh"
+
+using namespace fqd;
+
+namespace {
+
+struct HostCodec {
+    Codec c;
+    HostCodec(const uint8_t *alphabet, int n, bool varlen, int bits)
+    {
+        memset(c.lut, 0xFF, sizeof c.lut);
+        memset(c.rank, 0, sizeof c.rank);
+        std::vector<uint8_t> sorted(alphabet, alphabet + n);
+        std::sort(sorted.begin(), sorted.end());
+        for (int i = 0; i < n; i++) {
+            c.lut[alphabet[i]] = (uint8_t)i;
+            c.rank[i] = (uint8_t)(1 + (std::lower_bound(sorted.begin(), sorted.end(), alphabet[i]) - sorted.begin()));
+        }
+        c.pad_code = (uint8_t)n;
+        c.bits = (uint8_t)bits;
+        c.n_symbols = (uint8_t)n;
+        c.varlen = varlen;
+    }
+};
+
+template <int K, int PW>
+int run(int op, const HostCodec &hc, const uint8_t *a, uint32_t la, const uint8_t *b, uint32_t lb,
+        uint32_t max_len, int d, uint32_t p0, uint32_t p1, uint32_t p2, uint64_t *out64)
+{
+    Key<K, PW> ka, kb;
+    uint32_t bad = 0;
+    const bool varlen = hc.c.varlen;
+    if (!pack_key<K, PW>(a, la, varlen ? max_len : la, hc.c.lut, hc.c.pad_code, ka, &bad)) return -2;
+    if (!pack_key<K, PW>(b, lb, varlen ? max_len : lb, hc.c.lut, hc.c.pad_code, kb, &bad)) return -2;
+    switch (op) {
+    case 0: return hamming_within<K, PW>(ka, kb, d, varlen, hc.c.pad_code) ? 1 : 0;
+    case 1: return myers_within<K, PW>(ka, la, kb, lb, d) ? 1 : 0;
+    case 2: return key_less<K, PW>(ka, kb, hc.c.rank) ? 1 : 0;
+    case 3: return key_equal<K, PW>(ka, kb) ? 1 : 0;
+    case 4: return (int)key_length<K, PW>(ka, hc.c.pad_code, max_len);
+    case 5:   // block hash equality: a[p0:p0+p2] vs b[p1:p1+p2]
+        return block_hash<K, PW>(ka, p0, p2, 7) == block_hash<K, PW>(kb, p1, p2, 7) ? 1 : 0;
+    case 6: *out64 = hash_key<K, PW>(ka); return 0;
+    case 7: return (int)symbol_at<K, PW>(ka, p0);
+    }
+    return -1;
+}
+
+}  // namespace
+
+extern "C" int key_probe(int K, int PW, int op, const uint8_t *alphabet, int n_alpha, int varlen,
+                         const uint8_t *a, uint32_t la, const uint8_t *b, uint32_t lb,
+                         uint32_t max_len, int d, uint32_t p0, uint32_t p1, uint32_t p2,
+                         uint64_t *out64)
+{
+    HostCodec hc(alphabet, n_alpha, varlen != 0, K);
+#define CASE(K_, PW_) if (K == K_ && PW == PW_) return run<K_, PW_>(op, hc, a, la, b, lb, max_len, d, p0, p1, p2, out64);
+    CASE(3, 1) CASE(3, 2) CASE(3, 3) CASE(3, 5) CASE(4, 2) CASE(8, 1) CASE(8, 2)
+#undef CASE
+    return -3;
+}
