@@ -33,14 +33,52 @@ int cuda_fail(cudaError_t e, const char *what, const char *file, int line)
 
 int dev_alloc(fqd_context *ctx, size_t bytes, void **p)
 {
+    fqd_arena &a = ctx->arena;
+    const size_t sz = (bytes + 255) & ~(size_t)255;
     *p = nullptr;
-    FQD_CUDA(cudaMallocAsync(p, bytes, ctx->pool, ctx->stream));
+    if (a.base && a.off + sz <= a.cap) {
+        *p = a.base + a.off;
+    } else {
+        // does not fit the slab (first job, or a bigger one): a plain allocation now, a
+        // bigger slab at the next reset
+        void *q = nullptr;
+        FQD_CUDA(cudaMalloc(&q, sz));
+        a.overflow.push_back(q);
+        *p = q;
+    }
+    a.off += sz;
+    if (a.off > a.high) a.high = a.off;
     return FQD_OK;
 }
 
-void dev_free(fqd_context *ctx, void *p)
+void dev_free(fqd_context *, void *) {}
+
+int arena_reset(fqd_context *ctx)
 {
-    if (p) cudaFreeAsync(p, ctx->stream);
+    fqd_arena &a = ctx->arena;
+    if (!a.overflow.empty() || a.high > a.cap) {
+        FQD_CUDA(cudaStreamSynchronize(ctx->stream));
+        for (void *q : a.overflow) cudaFree(q);
+        a.overflow.clear();
+        if (a.high > a.cap) {
+            if (a.base) cudaFree(a.base);
+            a.base = nullptr;
+            a.cap = 0;
+            const size_t want = a.high + a.high / 8 + (64u << 20);
+            void *q = nullptr;
+            if (cudaMalloc(&q, want) == cudaSuccess) { a.base = (char *)q; a.cap = want; }
+            else cudaGetLastError();   // stay on per-buffer allocations
+        }
+    }
+    a.off = 0;
+    a.high = 0;
+    return FQD_OK;
+}
+
+void arena_release(fqd_context *ctx, size_t mark)
+{
+    fqd_arena &a = ctx->arena;
+    if (mark < a.off) a.off = mark;   // overflow chunks (if any) stay alive until the next reset
 }
 
 // Build the symbol coding for an alphabet (bytes in first-seen order, like the
@@ -119,14 +157,6 @@ int fqd_context_create(int device_ordinal, fqd_context **out)
     ctx->device = device_ordinal;
     FQD_CUDA(cudaSetDevice(device_ordinal));
     FQD_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
-    cudaMemPoolProps props{};
-    props.allocType = cudaMemAllocationTypePinned;
-    props.handleTypes = cudaMemHandleTypeNone;
-    props.location.type = cudaMemLocationTypeDevice;
-    props.location.id = device_ordinal;
-    FQD_CUDA(cudaMemPoolCreate(&ctx->pool, &props));
-    uint64_t threshold = UINT64_MAX;   // keep freed blocks cached between jobs
-    FQD_CUDA(cudaMemPoolSetAttribute(ctx->pool, cudaMemPoolAttrReleaseThreshold, &threshold));
     FQD_CUDA(cudaMalloc(&ctx->d_ctr, sizeof(DevCounters)));
     FQD_CUDA(cudaHostAlloc(&ctx->h_ctr, sizeof(DevCounters), cudaHostAllocDefault));
     for (auto &ev : ctx->ev) FQD_CUDA(cudaEventCreate(&ev));
@@ -140,13 +170,11 @@ void fqd_context_destroy(fqd_context *ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    dev_free(ctx, ctx->res.ufirst); dev_free(ctx, ctx->res.ucount);
-    dev_free(ctx, ctx->res.parent_full); dev_free(ctx, ctx->res.selected);
-    cudaStreamSynchronize(ctx->stream);
+    for (void *q : ctx->arena.overflow) cudaFree(q);
+    if (ctx->arena.base) cudaFree(ctx->arena.base);
     for (auto &ev : ctx->ev) if (ev) cudaEventDestroy(ev);
     if (ctx->d_ctr) cudaFree(ctx->d_ctr);
     if (ctx->h_ctr) cudaFreeHost(ctx->h_ctr);
-    if (ctx->pool) cudaMemPoolDestroy(ctx->pool);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -242,12 +270,9 @@ int fqd_cluster(fqd_context *ctx, const fqd_cluster_job *job, fqd_cluster_stats 
     cudaStream_t s = ctx->stream;
     const size_t bitmap_words = (size_t)((n + 31) / 32);
     stats->total_records = n;
-    if (n == 0) {
-        dev_free(ctx, ctx->res.ufirst); dev_free(ctx, ctx->res.ucount);
-        dev_free(ctx, ctx->res.parent_full); dev_free(ctx, ctx->res.selected);
-        ctx->res = fqd_result{};
-        return FQD_OK;
-    }
+    ctx->res = fqd_result{};          // the previous job's result lives in the arena: gone now
+    FQD_TRY(arena_reset(ctx));
+    if (n == 0) return FQD_OK;
 
     DeviceJob dj;
     dj.n = n;
@@ -338,7 +363,9 @@ int fqd_cluster(fqd_context *ctx, const fqd_cluster_job *job, fqd_cluster_stats 
         if (alphabet.empty()) alphabet.push_back('A');
     }
     int rc = FQD_OK;
+    const size_t inputs_mark = arena_mark(ctx);
     for (int attempt = 0; attempt < 3; attempt++) {
+        arena_release(ctx, inputs_mark);
         Codec codec;
         FQD_TRY(make_codec(alphabet, dj.varlen, &codec));
         uint32_t unknown[8] = {};
@@ -378,6 +405,7 @@ int fqd_cluster_fetch(fqd_context *ctx, uint64_t *first, uint32_t *count, uint64
     if (selected) {
         FQD_CUDA(cudaMemcpyAsync(selected, ctx->res.selected, (size_t)U, cudaMemcpyDeviceToHost, s));
     }
+    struct Scope { fqd_context *c; size_t m; ~Scope() { cudaStreamSynchronize(c->stream); arena_release(c, m); } } scope{ctx, arena_mark(ctx)};
     if (label) {
         DevBuf minfirst, root;
         FQD_TRY(minfirst.alloc(ctx, (size_t)U * 4));
@@ -427,6 +455,7 @@ int fqd_average_error_rate(fqd_context *ctx, const uint8_t *phred, const uint64_
     if (!offsets || !out) { set_error("null argument"); return FQD_ERR_ARG; }
     cudaStream_t s = ctx->stream;
     const size_t bytes = (size_t)offsets[n_strings];
+    struct Scope { fqd_context *c; size_t m; ~Scope() { cudaStreamSynchronize(c->stream); arena_release(c, m); } } scope{ctx, arena_mark(ctx)};
     DevBuf d_ph, d_off, d_out;
     FQD_TRY(d_ph.alloc(ctx, bytes)); FQD_TRY(d_off.alloc(ctx, (n_strings + 1) * 8)); FQD_TRY(d_out.alloc(ctx, n_strings * 8));
     if (bytes) FQD_CUDA(cudaMemcpyAsync(d_ph.p, phred, bytes, cudaMemcpyHostToDevice, s));
@@ -473,6 +502,7 @@ int fqd_within_distance(fqd_context *ctx, const uint8_t *a, const uint64_t *a_of
     }
     cudaStream_t s = ctx->stream;
     const size_t ab = (size_t)a_offsets[n_pairs], bb = (size_t)b_offsets[n_pairs];
+    struct Scope { fqd_context *c; size_t m; ~Scope() { cudaStreamSynchronize(c->stream); arena_release(c, m); } } scope{ctx, arena_mark(ctx)};
     DevBuf d_a, d_ao, d_b, d_bo, d_out;
     FQD_TRY(d_a.alloc(ctx, ab)); FQD_TRY(d_b.alloc(ctx, bb));
     FQD_TRY(d_ao.alloc(ctx, (n_pairs + 1) * 8)); FQD_TRY(d_bo.alloc(ctx, (n_pairs + 1) * 8));

@@ -42,10 +42,21 @@ struct fqd_result {
     uint8_t *selected = nullptr;
 };
 
+// Job-lifetime device memory: one slab, bump allocation, reset at the start of every job.
+// Steady state makes no CUDA allocation calls at all (a 100 M-read job needs ~9 GB of
+// scratch; growing a pool inside the timed region cost tens of ms).
+struct fqd_arena {
+    char *base = nullptr;
+    size_t cap = 0;
+    size_t off = 0;          // bump pointer (may exceed cap: then the job ran on overflow chunks)
+    size_t high = 0;         // high-water mark of off over the last job
+    std::vector<void *> overflow;
+};
+
 struct fqd_context {
     int device = 0;
     cudaStream_t stream = nullptr;
-    cudaMemPool_t pool = nullptr;
+    fqd_arena arena;
     fqd::DevCounters *d_ctr = nullptr;
     fqd::DevCounters *h_ctr = nullptr;   // pinned
     cudaEvent_t ev[12] = {};
@@ -55,9 +66,12 @@ struct fqd_context {
 
 namespace fqd {
 
-// stream-ordered allocation from the context's pool (cached across jobs)
+// arena allocation (see fqd_arena); dev_free is a no-op kept for symmetry
 int dev_alloc(fqd_context *ctx, size_t bytes, void **p);
 void dev_free(fqd_context *ctx, void *p);
+int arena_reset(fqd_context *ctx);                    // start of a job: everything is released
+inline size_t arena_mark(fqd_context *ctx) { return ctx->arena.off; }
+void arena_release(fqd_context *ctx, size_t mark);    // drop everything allocated after mark
 
 // RAII holder for job-lifetime device buffers
 struct DevBuf {

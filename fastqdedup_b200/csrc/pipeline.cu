@@ -54,7 +54,7 @@ template <int K, int PW>
 int run_typed(fqd_context *ctx, const DeviceJob &job, const Codec &codec, fqd_cluster_stats *st,
               uint32_t unknown_out[8])
 {
-    constexpr int KW = K * PW, RW = round_up4(KW + 2);
+    constexpr int KW = K * PW, RW = slot_words(KW), FW = fat_words(KW);
     cudaStream_t s = ctx->stream;
     Timer tm(ctx);
     const uint64_t n = job.n;
@@ -66,9 +66,6 @@ int run_typed(fqd_context *ctx, const DeviceJob &job, const Codec &codec, fqd_cl
     *ctx->h_ctr = zero;
     FQD_CUDA(cudaMemcpyAsync(ctx->d_ctr, ctx->h_ctr, sizeof(DevCounters), cudaMemcpyHostToDevice, s));
 
-    // ---- previous result is dropped ----
-    dev_free(ctx, ctx->res.ufirst); dev_free(ctx, ctx->res.ucount);
-    dev_free(ctx, ctx->res.parent_full); dev_free(ctx, ctx->res.selected);
     ctx->res = fqd_result{};
     ctx->res.n_records = n;
 
@@ -163,12 +160,13 @@ int run_typed(fqd_context *ctx, const DeviceJob &job, const Codec &codec, fqd_cl
     FQD_TRY(selected.alloc(ctx, (size_t)U));
     if (directional) FQD_TRY(parent_one.alloc(ctx, (size_t)U * 4));
     if (job.method != METHOD_ADJACENCY) FQD_TRY(best.alloc(ctx, (size_t)U * 4));
-    if (U) launches++;
-    if (U)
+    if (U) {
         gather_kernel<K, PW><<<cdiv(U, 256), 256, 0, s>>>(U, table.as<uint32_t>(), uslot.as<uint32_t>(),
                                                           ukey.as<uint32_t>(), ucount.as<uint32_t>(),
                                                           ufirst.as<uint32_t>(), parent_full.as<uint32_t>(),
                                                           parent_one.as<uint32_t>(), best.as<uint32_t>());
+        launches++;
+    }
     FQD_CUDA(cudaGetLastError());
     table.reset(); uslot.reset(); keepmask.reset();
     const int t_gather = tm.mark();
@@ -199,7 +197,8 @@ int run_typed(fqd_context *ctx, const DeviceJob &job, const Codec &codec, fqd_cl
         DevBuf cnt, rank, entries, block_sums, grand;
         FQD_TRY(cnt.alloc(ctx, ((size_t)NB + 1) * 4));
         FQD_TRY(rank.alloc(ctx, E * 4));
-        FQD_TRY(entries.alloc(ctx, E * sizeof(uint2)));
+        const bool fat = !job.edit;
+        FQD_TRY(entries.alloc(ctx, fat ? E * FW * sizeof(uint32_t) : E * sizeof(uint2)));
         FQD_TRY(block_sums.alloc(ctx, (size_t)cdiv(NB, SCAN_TILE) * 4 + 64));
         FQD_TRY(grand.alloc(ctx, 16));
         PassParams pp{};
@@ -207,7 +206,7 @@ int run_typed(fqd_context *ctx, const DeviceJob &job, const Codec &codec, fqd_cl
         pp.d = job.d; pp.edit = job.edit; pp.varlen = job.varlen ? 1 : 0; pp.method = job.method;
         pp.max_len = job.max_len; pp.pad_code = codec.pad_code;
         pp.V = V; pp.nb_mask = NB - 1;
-        pp.cnt = cnt.as<uint32_t>(); pp.rank = rank.as<uint32_t>(); pp.entries = entries.as<uint2>();
+        pp.cnt = cnt.as<uint32_t>(); pp.rank = rank.as<uint32_t>(); pp.entries = entries.as<uint2>(); pp.fat = entries.as<uint32_t>();
         pp.parent_full = parent_full.as<uint32_t>(); pp.parent_one = parent_one.as<uint32_t>();
         pp.dominated = dominated.as<uint8_t>(); pp.dead = dead.as<uint8_t>();
         pp.edges = edges.as<uint2>(); pp.edge_cap = edge_cap; pp.ctr = ctx->d_ctr;
@@ -221,11 +220,13 @@ int run_typed(fqd_context *ctx, const DeviceJob &job, const Codec &codec, fqd_cl
                 sig_count_kernel<K, PW><<<cdiv(U, 256), 256, 0, s>>>(pp);
                 FQD_TRY(exclusive_scan_inplace(ctx, cnt.as<uint32_t>(), NB, block_sums.as<uint32_t>(),
                                                grand.as<uint32_t>()));
-                scatter_kernel<K, PW><<<cdiv(U, 256), 256, 0, s>>>(pp);
+                if (fat) scatter_fat_kernel<K, PW><<<cdiv(U, 256), 256, 0, s>>>(pp);
+                else scatter_kernel<K, PW><<<cdiv(U, 256), 256, 0, s>>>(pp);
                 pp.n_entries = (uint32_t)E;   // upper bound; the kernel stops at cnt[NB]
                 launches += 6;   // sig_count, 3 scan kernels, scatter, compare
                 FQD_CUDA(cudaEventRecord(cev[2 * j], s));
-                compare_kernel<K, PW><<<cdiv(E, 256), 256, 0, s>>>(pp);
+                if (fat) compare_fat_kernel<K, PW><<<cdiv(E, 256), 256, 0, s>>>(pp);
+                else compare_kernel<K, PW><<<cdiv(E, 256), 256, 0, s>>>(pp);
                 FQD_CUDA(cudaEventRecord(cev[2 * j + 1], s));
                 FQD_CUDA(cudaGetLastError());
             }

@@ -5,7 +5,6 @@
 //              exact dedupe with counts + first index in an open-addressing table in HBM
 //              (replaces Trie.add_sequence, reference _triemodule.c:222-288, and
 //              average_error_rate, _fastqmodule.c:38-76)
-//   gather   : claimed slots -> dense unique arrays (key, count, first)
 //   passes   : pigeonhole block bucketing (counting sort of 8-byte {tag, uid} entries by
 //              block hash) + in-bucket verification with XOR/popc Hamming or Myers
 //              bit-vector Levenshtein; every verified pair is an edge
@@ -115,15 +114,62 @@ struct IngestParams {
     double max_err;
     uint32_t phred_offset;
     uint32_t pad_code;
-    uint32_t *table;
+    uint32_t *table;           // open addressing: {key[KW], count, state} per slot;
+                               // state = EMPTY | LOCKED | smallest record index seen so far
     uint64_t capacity;
-    uint32_t *uslot;
+    uint32_t *uslot;           // claimed slots in claim order (= unique ids)
     uint32_t *keepmask;        // bit per record: passed the filter
     const uint32_t *weights;   // optional multiplicity per record
     DevCounters *ctr;
     Codec codec;
 };
 
+// One probe reads a whole table record.  A 32-byte record is exactly one L2 sector and is
+// fetched by ONE 256-bit load (LDG.E.ENL2.256.STRONG.GPU): the state word and the key words
+// come from the same sector snapshot, so a published state implies the published key.
+// Larger records read the state word first and the key words after it (the loads are
+// control-dependent on the state, and the writer fences between key and state).
+template <int RW>
+__device__ __forceinline__ void load_record256(const uint32_t *rec, uint32_t (&w)[RW])
+{
+    static_assert(RW == 8, "256-bit record load");
+    asm volatile("ld.relaxed.gpu.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7])
+                 : "l"(rec) : "memory");
+}
+__device__ __forceinline__ uint4 ld_relaxed_v4(const uint32_t *p)
+{
+    uint4 v;
+    asm volatile("ld.relaxed.gpu.global.v4.b32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    return v;
+}
+
+// Slot layout: KW key words, count, state; padded to a multiple of 4 words (32 bytes = one
+// L2 sector for the 36- and 48-nt configs).
+__host__ __device__ constexpr int slot_words(int kw) { return round_up4(kw + 2); }
+
+// Whole slot in as few loads as its size allows (see load_record256).
+template <int RW>
+__device__ __forceinline__ void load_slot(const uint32_t *rec, uint32_t (&w)[RW])
+{
+    if constexpr (RW == 8) {
+        load_record256<RW>(rec, w);
+    } else {
+#pragma unroll
+        for (int c = 0; c < RW / 4; c++) {
+            const uint4 v = ld_relaxed_v4(rec + 4 * c);
+            w[4 * c] = v.x; w[4 * c + 1] = v.y; w[4 * c + 2] = v.z; w[4 * c + 3] = v.w;
+        }
+    }
+}
+
+// Exact dedupe with counts (replaces Trie.add_sequence, reference _triemodule.c:222-288).
+// The first record of a key claims a slot (CAS EMPTY -> LOCKED), writes key and count and
+// publishes its record index in the state word.  Every later record of the key finds the
+// slot with one sector read and adds to the count in that same (L2-hot) sector; the state
+// word keeps the smallest record index, which is rarely lowered because records arrive
+// roughly in index order.
 template <int K, int PW>
 __device__ __forceinline__ void table_insert(const IngestParams &P, const Key<K, PW> &key,
                                              uint32_t t)
@@ -133,37 +179,37 @@ __device__ __forceinline__ void table_insert(const IngestParams &P, const Key<K,
         weight = P.weights[t];
         atomicAdd(&P.ctr->sum_weights, (unsigned long long)weight);
     }
-    constexpr int KW = K * PW, RW = round_up4(KW + 2);
+    constexpr int KW = K * PW, RW = slot_words(KW);
     const uint64_t h = hash_key(key);
     uint64_t s = __umul64hi(h, P.capacity);
     for (uint64_t probes = 0; probes < P.capacity;) {
         uint32_t *rec = P.table + s * RW;
-        uint32_t st = ld_acquire_u32(rec + KW + 1);
+        uint32_t w[RW];
+        uint32_t st;
+        if constexpr (RW <= 8) {
+            load_slot<RW>(rec, w);      // one sector: state and key from the same snapshot
+            st = w[KW + 1];
+        } else {
+            st = ld_relaxed_u32(rec + KW + 1);
+        }
         if (st == SLOT_EMPTY) {
             const uint32_t old = atomicCAS(rec + KW + 1, SLOT_EMPTY, SLOT_LOCKED);
             if (old == SLOT_EMPTY) {
 #pragma unroll
                 for (int i = 0; i < KW; i++) rec[i] = key.w[i];
                 rec[KW] = weight;
-                __threadfence();
-                st_release_u32(rec + KW + 1, t);
-                const uint32_t pos = aggregated_inc(&P.ctr->n_unique);
-                P.uslot[pos] = (uint32_t)s;
+                st_release_u32(rec + KW + 1, t);   // orders the stores above before the index
+                const uint32_t uid = aggregated_inc(&P.ctr->n_unique);
+                P.uslot[uid] = (uint32_t)s;
                 return;
             }
-            st = old;
+            continue;   // somebody else claimed it first: look at the slot again
         }
-        if (st == SLOT_LOCKED) continue;  // another record is publishing this slot: look again
+        if (st == SLOT_LOCKED) continue;   // being published right now: look again
+        if constexpr (RW > 8) load_slot<RW>(rec, w);
         uint32_t diff = 0;
-        const uint4 *rv = reinterpret_cast<const uint4 *>(rec);
 #pragma unroll
-        for (int c = 0; c < (KW + 3) / 4; c++) {
-            const uint4 v = __ldcg(rv + c);
-            if (4 * c + 0 < KW) diff |= v.x ^ key.w[(4 * c + 0) < KW ? 4 * c + 0 : 0];
-            if (4 * c + 1 < KW) diff |= v.y ^ key.w[(4 * c + 1) < KW ? 4 * c + 1 : 0];
-            if (4 * c + 2 < KW) diff |= v.z ^ key.w[(4 * c + 2) < KW ? 4 * c + 2 : 0];
-            if (4 * c + 3 < KW) diff |= v.w ^ key.w[(4 * c + 3) < KW ? 4 * c + 3 : 0];
-        }
+        for (int i = 0; i < KW; i++) diff |= w[i] ^ key.w[i];
         if (diff == 0) {
             atomicAdd(rec + KW, weight);
             if (t < st) atomicMin(rec + KW + 1, t);
@@ -181,16 +227,18 @@ template <int K, int PW>
 __device__ __forceinline__ void table_touch_first(const IngestParams &P, const Key<K, PW> &key,
                                                   uint32_t t)
 {
-    constexpr int KW = K * PW, RW = round_up4(KW + 2);
+    constexpr int KW = K * PW, RW = slot_words(KW);
     const uint64_t h = hash_key(key);
     uint64_t s = __umul64hi(h, P.capacity);
     for (uint64_t probes = 0; probes < P.capacity; probes++) {
         uint32_t *rec = P.table + s * RW;
-        const uint32_t st = ld_relaxed_u32(rec + KW + 1);
+        uint32_t w[RW];
+        load_slot<RW>(rec, w);
+        const uint32_t st = w[KW + 1];
         if (st == SLOT_EMPTY) return;
         uint32_t diff = 0;
 #pragma unroll
-        for (int i = 0; i < KW; i++) diff |= __ldcg(rec + i) ^ key.w[i];
+        for (int i = 0; i < KW; i++) diff |= w[i] ^ key.w[i];
         if (diff == 0) {
             if (t < st) atomicMin(rec + KW + 1, t);
             return;
@@ -334,7 +382,7 @@ static __global__ void length_range_kernel(uint64_t n, const uint64_t *off, cons
     }
 }
 
-// ---- gather: claimed slots -> dense unique arrays --------------------------------------
+// ---- gather: claimed slots -> dense unique arrays + forest init --------------------------------
 
 template <int K, int PW>
 static __global__ void __launch_bounds__(256) gather_kernel(uint32_t U, const uint32_t *__restrict__ table,
@@ -346,7 +394,7 @@ static __global__ void __launch_bounds__(256) gather_kernel(uint32_t U, const ui
                                                      uint32_t *__restrict__ parent_b,
                                                      uint32_t *__restrict__ best)
 {
-    constexpr int KW = K * PW, RW = round_up4(KW + 2);
+    constexpr int KW = K * PW, RW = slot_words(KW);
     const uint32_t u = blockIdx.x * 256u + threadIdx.x;
     if (u >= U) return;
     const uint4 *rec = reinterpret_cast<const uint4 *>(table + (size_t)uslot[u] * RW);
@@ -409,7 +457,8 @@ struct PassParams {
     uint32_t nb_mask;
     uint32_t *cnt;          // NB+1 counters -> exclusive offsets after the scan
     uint32_t *rank;         // U*V
-    uint2 *entries;
+    uint2 *entries;         // thin {tag, uid|flags} entries (Levenshtein passes)
+    uint32_t *fat;          // fat {key, count, uid|flags} entries (Hamming passes)
     uint32_t n_entries;
     uint32_t *parent_full;
     uint32_t *parent_one;
@@ -556,6 +605,92 @@ static __global__ void __launch_bounds__(256) compare_kernel(const __grid_consta
         }
     }
     // per-warp reduction of the two counters
+    for (int o = 16; o; o >>= 1) {
+        merges += __shfl_xor_sync(0xFFFFFFFFu, merges, o);
+        cand += __shfl_xor_sync(0xFFFFFFFFu, cand, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (merges) atomicAdd(&P.ctr->n_merges, merges);
+        if (cand) atomicAdd(&P.ctr->n_candidates, (unsigned long long)cand);
+    }
+}
+
+// ---- Hamming passes: bucket entries carry the key --------------------------------------------
+//
+// With one variant per key (Hamming) the bucket-ordered array holds {key, count, uid|LAST}
+// records of fat_words() 32-bit words (32 bytes for keys up to 6 words): the compare kernel
+// then streams the array once and never dereferences a unique id.
+
+__host__ __device__ constexpr int fat_words(int kw) { return round_up4(kw + 2); }
+
+template <int K, int PW>
+static __global__ void __launch_bounds__(256) scatter_fat_kernel(const __grid_constant__ PassParams P)
+{
+    constexpr int KW = K * PW, FW = fat_words(KW);
+    const uint32_t u = blockIdx.x * 256u + threadIdx.x;
+    if (u >= P.U) return;
+    Key<K, PW> key;
+    load_key<K, PW>(P.ukey, u, key);
+    const uint32_t len = P.varlen ? key_length(key, P.pad_code, P.max_len) : P.max_len;
+    const uint32_t r = P.rank[u];
+    uint64_t sig;
+    bool build;
+    pass_variant<K, PW>(key, len, P, 0, sig, build);
+    const uint32_t b = (uint32_t)sig & P.nb_mask;
+    const uint32_t lo = P.cnt[b], hi = P.cnt[b + 1];
+    const uint32_t pos = lo + r;
+    uint32_t e[FW];
+#pragma unroll
+    for (int i = 0; i < FW; i++) e[i] = 0;
+#pragma unroll
+    for (int i = 0; i < KW; i++) e[i] = key.w[i];
+    e[KW] = P.ucount[u];
+    e[KW + 1] = u | (pos + 1 == hi ? ENT_LAST : 0u);
+    uint4 *dst = reinterpret_cast<uint4 *>(P.fat + (size_t)pos * FW);
+#pragma unroll
+    for (int c = 0; c < FW / 4; c++) dst[c] = make_uint4(e[4 * c], e[4 * c + 1], e[4 * c + 2], e[4 * c + 3]);
+}
+
+template <int K, int PW>
+__device__ __forceinline__ void load_fat(const uint32_t *__restrict__ fat, uint32_t i, Key<K, PW> &k,
+                                         uint32_t &count, uint32_t &meta)
+{
+    constexpr int KW = K * PW, FW = fat_words(KW);
+    const uint4 *src = reinterpret_cast<const uint4 *>(fat + (size_t)i * FW);
+    uint32_t e[FW];
+#pragma unroll
+    for (int c = 0; c < FW / 4; c++) {
+        const uint4 v = __ldg(src + c);
+        e[4 * c] = v.x; e[4 * c + 1] = v.y; e[4 * c + 2] = v.z; e[4 * c + 3] = v.w;
+    }
+#pragma unroll
+    for (int j = 0; j < KW; j++) k.w[j] = e[j];
+    count = e[KW];
+    meta = e[KW + 1];
+}
+
+template <int K, int PW>
+static __global__ void __launch_bounds__(256) compare_fat_kernel(const __grid_constant__ PassParams P)
+{
+    const uint32_t i = blockIdx.x * 256u + threadIdx.x;
+    uint32_t merges = 0, cand = 0;
+    if (i < P.cnt[P.nb_mask + 1]) {
+        Key<K, PW> ki;
+        uint32_t ci, mi;
+        load_fat<K, PW>(P.fat, i, ki, ci, mi);
+        if (!(mi & ENT_LAST)) {
+            const uint32_t ui = mi & ENT_UID;
+            for (uint32_t j = i + 1;; j++) {
+                Key<K, PW> kj;
+                uint32_t cj, mj;
+                load_fat<K, PW>(P.fat, j, kj, cj, mj);
+                cand++;
+                if (hamming_within<K, PW>(ki, kj, P.d, P.varlen != 0, P.pad_code))
+                    process_edge<K, PW>(P, ui, mj & ENT_UID, ci, cj, ki, kj, merges);
+                if (mj & ENT_LAST) break;
+            }
+        }
+    }
     for (int o = 16; o; o >>= 1) {
         merges += __shfl_xor_sync(0xFFFFFFFFu, merges, o);
         cand += __shfl_xor_sync(0xFFFFFFFFu, cand, o);

@@ -21,8 +21,15 @@ py_average_error_rate(PyObject *module, PyObject *args, PyObject *kwargs)
         return NULL;
     uint64_t offsets[2] = {0, (uint64_t)PyUnicode_GET_LENGTH(scores)};
     double result = 0.0;
+    uint32_t bad_char = 0;
     int rc = fqd_average_error_rate(ctx, (const uint8_t *)PyUnicode_DATA(scores), offsets, 1,
-                                    offset, &result, NULL, NULL);
+                                    offset, &result, NULL, &bad_char);
+    if (rc == FQD_ERR_PHRED) {
+        /* built here rather than from the C string so that a NUL byte survives */
+        PyErr_Format(PyExc_ValueError, "Character %c outside of valid phred range ('%c' to '%c')",
+                     (int)bad_char, (int)offset, 126);
+        return NULL;
+    }
     if (rc != FQD_OK)
         return fqd_py_raise(rc);
     return PyFloat_FromDouble(result);
