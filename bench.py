@@ -290,8 +290,7 @@ def run_ours(args, rank, world, local_rank):
 
     cfg = make_config(args)
     if world > 1:
-        from fastqdedup_b200 import multigpu
-        return multigpu.bench_entry(args, cfg, rank, world, local_rank, dist, globals())
+        return run_ours_sharded(args, cfg, rank, world, local_rank, dist)
 
     lib = _native.load()
     if lib.fqd_device_count() < 1:
@@ -429,6 +428,110 @@ def run_ours(args, rank, world, local_rank):
     if host_quals is not None:
         host_quals.free()
     ctx.close()
+
+
+def run_ours_sharded(args, cfg, rank, world, local_rank, dist):
+    """One process per GPU (torchrun): strong scaling of the same 100 M-read job.  Each rank
+    holds a contiguous slice of the reads; the library exchanges keys / forests over NCCL.
+    Device time is the max over ranks of the CUDA-event time of the whole job."""
+    import torch
+    from fastqdedup_b200 import _native
+    from fastqdedup_b200.multigpu import ShardComm, shard_bounds
+
+    lib = _native.load()
+    ctx = _native.Context(local_rank)
+    comm = ShardComm.from_torch_distributed(ctx, dist)
+    n, L = cfg.n_reads, cfg.key_length
+    bounds = shard_bounds(n, world)
+    lo, hi = bounds[rank], bounds[rank + 1]
+    nloc = hi - lo
+    t0 = time.time()
+    host_keys = PinnedArray(lib, (nloc, L))
+    host_quals = PinnedArray(lib, (nloc, L)) if cfg.quality_mix else None
+    generate_into(cfg, lo, hi, host_keys.array, None if host_quals is None else host_quals.array,
+                  threads=max(2, 16 // world))
+    log(f"[bench r{rank}] generated reads [{lo}, {hi}) in {time.time() - t0:.1f}s")
+    d_keys = ctx.upload(host_keys.array)
+    d_quals = ctx.upload(host_quals.array) if host_quals is not None else None
+    words = (nloc + 31) // 32
+    d_bitmap = ctx.device_alloc(max(words, 1) * 4)
+
+    def step():
+        return comm.cluster_device(nloc, lo, d_keys, L, quals_ptr=d_quals, max_distance=cfg.max_distance,
+                                   use_edit_distance=cfg.use_edit_distance, method=cfg.method,
+                                   max_average_error_rate=cfg.max_average_error_rate, bitmap_ptr=d_bitmap)
+
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device=f"cuda:{local_rank}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    for _ in range(args.warmup):
+        step()
+    dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    per_step, stats = [], []
+    wall0 = time.perf_counter()
+    for _ in range(args.steps):
+        st = step()
+        stats.append(st)
+        per_step.append(max_over_ranks(st.ms_total))
+    dist.barrier()
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - wall0
+    clocks = sampler.stop()
+    ms_per_step = float(np.mean(per_step))
+    st = stats[-1]
+    U = st.number_of_uniques
+
+    # e2e: same call with pinned host buffers (H2D of the shard + D2H of its bitmap inside)
+    host_bitmap = PinnedArray(lib, (max(words, 1) * 4,))
+    def e2e_step():
+        return comm.cluster_host(host_keys.array, lo, None if host_quals is None else host_quals.array,
+                                 cfg.max_distance, cfg.use_edit_distance, cfg.method,
+                                 cfg.max_average_error_rate, bitmap=host_bitmap.array.view(np.uint32))
+    for _ in range(2):
+        e2e_step()
+    dist.barrier()
+    e2e_steps = max(1, min(args.steps, 5))
+    e0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        est = e2e_step()
+    dist.barrier()
+    e2e_s = max_over_ranks((time.perf_counter() - e0) / e2e_steps)
+    dev_bitmap = ctx.download(d_bitmap, max(words, 1) * 4, np.uint32)
+    assert np.array_equal(dev_bitmap[:words], host_bitmap.array.view(np.uint32)[:words])
+    launches = int(sum(s.launches for s in stats))
+    lt = torch.tensor([launches], dtype=torch.int64, device=f"cuda:{local_rank}")
+    dist.all_reduce(lt)
+    if rank == 0:
+        total_b, _ = algorithmic_bytes(cfg, n, st.number_of_sequences, U, st.n_passes,
+                                       cfg.max_average_error_rate < 1.0)
+        peak, peak_src = measured_peak()
+        line = {
+            "metric": METRIC, "value": U / (ms_per_step / 1e3), "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u32",
+            "data": "synthetic", "config": workload_config(cfg, world),
+            "unique_keys": int(U), "clusters": int(st.number_of_clusters),
+            "selected": int(st.number_selected), "candidate_pairs": int(st.candidate_pairs),
+            "wall_ms_per_step": 1e3 * wall / args.steps,
+            "e2e": {"value": U / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(n * L * (2 if host_quals is not None else 1)),
+                    "d2h_bytes_per_step": int(((n + 31) // 32) * 4), "ms_per_step": 1e3 * e2e_s, "steps": e2e_steps},
+            "gpu_launches": int(lt.item()),
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": "whole sharded job (per-kernel split: see the 1-GPU line)",
+                         "achieved": total_b / (ms_per_step / 1e3) / 1e9, "peak": peak * world, "unit": "GB/s",
+                         "frac": total_b / (ms_per_step / 1e3) / 1e9 / (peak * world), "traffic": None,
+                         "peak_source": peak_src + f" x {world} GPUs"},
+            "rank0_stage_ms": {"ingest_kernel": st.ms_ingest_kernel, "compare": st.ms_compare},
+        }
+        print(json.dumps(line), flush=True)
+    comm.close()
+    dist.barrier()
+    dist.destroy_process_group()
 
 
 def main():

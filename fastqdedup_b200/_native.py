@@ -79,6 +79,8 @@ EXPORTS = [
     "fqd_default_context", "fqd_device_alloc", "fqd_device_free", "fqd_device_upload",
     "fqd_device_download", "fqd_context_synchronize", "fqd_host_alloc", "fqd_host_free",
     "fqd_cluster", "fqd_cluster_fetch", "fqd_cluster_fetch_selected",
+    "fqd_nccl_unique_id", "fqd_comm_create", "fqd_comm_destroy", "fqd_cluster_sharded",
+    "fqd_cluster_sharded_local",
     "fqd_average_error_rate", "fqd_within_distance",
     "fqd_trie_new", "fqd_trie_free", "fqd_trie_add_sequence", "fqd_trie_contains_sequence",
     "fqd_trie_pop_cluster", "fqd_trie_cluster_item", "fqd_trie_number_of_sequences",
@@ -111,6 +113,15 @@ def load():
     lib.fqd_host_alloc.argtypes = [c_size_t, POINTER(c_void_p)]
     lib.fqd_host_free.argtypes = [c_void_p]
     lib.fqd_cluster.argtypes = [c_void_p, POINTER(ClusterJob), POINTER(ClusterStats), c_void_p]
+    lib.fqd_nccl_unique_id.argtypes = [c_void_p]
+    lib.fqd_comm_create.argtypes = [c_void_p, c_int, c_int, c_void_p, POINTER(c_void_p)]
+    lib.fqd_comm_destroy.argtypes = [c_void_p]
+    lib.fqd_comm_destroy.restype = None
+    lib.fqd_cluster_sharded.argtypes = [c_void_p, c_void_p, POINTER(ClusterJob), c_uint64,
+                                        POINTER(ClusterStats), c_void_p]
+    lib.fqd_cluster_sharded_local.argtypes = [POINTER(c_void_p), c_int, POINTER(ClusterJob),
+                                              POINTER(c_uint64), POINTER(ClusterStats),
+                                              POINTER(c_void_p)]
     lib.fqd_cluster_fetch.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
     lib.fqd_cluster_fetch_selected.argtypes = [c_void_p, c_void_p]
     lib.fqd_average_error_rate.argtypes = [c_void_p, c_void_p, c_void_p, c_uint64, c_uint8,

@@ -24,8 +24,8 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xptxas", "-v",
 ]
-CU_SOURCES = ["api.cu", "pipeline.cu", "trie_shim.cu"]
-HEADERS = ["key.cuh", "pipeline.cuh", "common.h", "phred_lut.h",
+CU_SOURCES = ["api.cu", "pipeline.cu", "trie_shim.cu", "nccl_exchange.cu"]
+HEADERS = ["key.cuh", "pipeline.cuh", "common.h", "exchange.h", "phred_lut.h",
            os.path.join("..", "..", "include", "fqd_b200.h")]
 PY_MODULES = {"_trie": "py_trie.c", "_distance": "py_distance.c", "_fastq": "py_fastq.c"}
 

@@ -9,6 +9,7 @@
 #include <mutex>
 
 #include "common.h"
+#include "exchange.h"
 
 namespace fqd {
 
@@ -246,15 +247,23 @@ int fqd_host_free(void *hptr)
 }
 
 // ------------------------------------------------------------------------------------------
-// fqd_cluster
+// fqd_cluster / fqd_cluster_sharded*
 // ------------------------------------------------------------------------------------------
 
-int fqd_cluster(fqd_context *ctx, const fqd_cluster_job *job, fqd_cluster_stats *stats,
-                uint32_t *keep_bitmap)
+}  // extern "C"
+
+namespace {
+
+struct Resolved {
+    DeviceJob dj;
+    uint32_t len_min = 0, len_max = 0;
+    uint32_t *host_bitmap = nullptr;   // where to copy the bitmap back to (HOST jobs)
+    size_t bitmap_words = 0;
+    cudaEvent_t h0 = nullptr, h1 = nullptr;
+};
+
+int validate_job(const fqd_cluster_job *job)
 {
-    FQD_TRY(check_device(ctx));
-    if (!job || !stats) { set_error("null job/stats"); return FQD_ERR_ARG; }
-    memset(stats, 0, sizeof *stats);
     if (job->max_distance < 0) {
         set_error("max_distance should be non-negative");   // _triemodule.c:789-793
         return FQD_ERR_ARG;
@@ -264,17 +273,18 @@ int fqd_cluster(fqd_context *ctx, const fqd_cluster_job *job, fqd_cluster_stats 
         set_error("unknown memory space %d", job->memory_space);
         return FQD_ERR_ARG;
     }
-    const uint64_t n = job->n_records;
-    if (n && !job->keys) { set_error("keys is NULL"); return FQD_ERR_ARG; }
-    if (n >= 0xFFFFFFF0ull) { set_error("too many records for one job (%llu)", (unsigned long long)n); return FQD_ERR_UNSUPPORTED; }
-    cudaStream_t s = ctx->stream;
-    const size_t bitmap_words = (size_t)((n + 31) / 32);
-    stats->total_records = n;
-    ctx->res = fqd_result{};          // the previous job's result lives in the arena: gone now
-    FQD_TRY(arena_reset(ctx));
-    if (n == 0) return FQD_OK;
+    if (job->n_records && !job->keys) { set_error("keys is NULL"); return FQD_ERR_ARG; }
+    if (job->n_records >= 0xFFFFFFF0ull) { set_error("too many records for one job (%llu)", (unsigned long long)job->n_records); return FQD_ERR_UNSUPPORTED; }
+    if (!job->key_offsets && job->key_length > job->key_stride) { set_error("key_length > key_stride"); return FQD_ERR_ARG; }
+    return FQD_OK;
+}
 
-    DeviceJob dj;
+// Inputs -> device memory (arena), key length range of this shard.
+int resolve_job(fqd_context *ctx, const fqd_cluster_job *job, uint32_t *keep_bitmap, Resolved &r)
+{
+    cudaStream_t s = ctx->stream;
+    const uint64_t n = job->n_records;
+    DeviceJob &dj = r.dj;
     dj.n = n;
     dj.d = job->max_distance; dj.edit = job->use_edit_distance ? 1 : 0; dj.method = job->method;
     dj.max_err = job->max_average_error_rate;
@@ -282,45 +292,46 @@ int fqd_cluster(fqd_context *ctx, const fqd_cluster_job *job, fqd_cluster_stats 
     dj.phred_offset = job->phred_offset;
     dj.key_stride = job->key_stride; dj.key_len = job->key_length;
     dj.qual_stride = job->qual_stride; dj.qual_len = job->qual_length;
-    if (!job->key_offsets && job->key_length > job->key_stride) { set_error("key_length > key_stride"); return FQD_ERR_ARG; }
     if (dj.filter_on && !job->qual_offsets && job->qual_length > job->qual_stride) { set_error("qual_length > qual_stride"); return FQD_ERR_ARG; }
-
-    // ---- resolve inputs to device memory ----
-    DevBuf b_keys, b_koff, b_klen, b_quals, b_qoff, b_qlen, b_bitmap, b_weights;
-    cudaEvent_t h0, h1;
-    FQD_CUDA(cudaEventCreate(&h0)); FQD_CUDA(cudaEventCreate(&h1));
-    FQD_CUDA(cudaEventRecord(h0, s));
+    r.bitmap_words = (size_t)((n + 31) / 32);
+    FQD_CUDA(cudaEventCreate(&r.h0)); FQD_CUDA(cudaEventCreate(&r.h1));
+    FQD_CUDA(cudaEventRecord(r.h0, s));
     if (job->memory_space == FQD_MEM_HOST) {
-        auto up = [&](DevBuf &b, const void *src, size_t bytes, const void **dst) -> int {
-            FQD_TRY(b.alloc(ctx, bytes));
-            FQD_CUDA(cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, s));
-            *dst = b.p;
+        auto up = [&](const void *src, size_t bytes, const void **dst) -> int {
+            void *p = nullptr;
+            FQD_TRY(dev_alloc(ctx, bytes ? bytes : 16, &p));
+            if (bytes) FQD_CUDA(cudaMemcpyAsync(p, src, bytes, cudaMemcpyHostToDevice, s));
+            *dst = p;
             return FQD_OK;
         };
-        size_t key_bytes;
-        if (job->key_offsets) {
-            key_bytes = (size_t)job->key_offsets[n];
-            FQD_TRY(up(b_koff, job->key_offsets, (n + 1) * 8, (const void **)&dj.key_off));
-        } else {
-            key_bytes = (size_t)n * job->key_stride;
-            if (job->key_lengths) FQD_TRY(up(b_klen, job->key_lengths, n * 4, (const void **)&dj.key_lens));
-        }
-        FQD_TRY(up(b_keys, job->keys, key_bytes, (const void **)&dj.keys));
-        if (dj.filter_on) {
-            size_t qual_bytes;
-            if (job->qual_offsets) {
-                qual_bytes = (size_t)job->qual_offsets[n];
-                FQD_TRY(up(b_qoff, job->qual_offsets, (n + 1) * 8, (const void **)&dj.qual_off));
+        if (n) {
+            size_t key_bytes;
+            if (job->key_offsets) {
+                key_bytes = (size_t)job->key_offsets[n];
+                FQD_TRY(up(job->key_offsets, (n + 1) * 8, (const void **)&dj.key_off));
             } else {
-                qual_bytes = (size_t)n * job->qual_stride;
-                if (job->qual_lengths) FQD_TRY(up(b_qlen, job->qual_lengths, n * 4, (const void **)&dj.qual_lens));
+                key_bytes = (size_t)n * job->key_stride;
+                if (job->key_lengths) FQD_TRY(up(job->key_lengths, n * 4, (const void **)&dj.key_lens));
             }
-            FQD_TRY(up(b_quals, job->quals, qual_bytes, (const void **)&dj.quals));
+            FQD_TRY(up(job->keys, key_bytes, (const void **)&dj.keys));
+            if (dj.filter_on) {
+                size_t qual_bytes;
+                if (job->qual_offsets) {
+                    qual_bytes = (size_t)job->qual_offsets[n];
+                    FQD_TRY(up(job->qual_offsets, (n + 1) * 8, (const void **)&dj.qual_off));
+                } else {
+                    qual_bytes = (size_t)n * job->qual_stride;
+                    if (job->qual_lengths) FQD_TRY(up(job->qual_lengths, n * 4, (const void **)&dj.qual_lens));
+                }
+                FQD_TRY(up(job->quals, qual_bytes, (const void **)&dj.quals));
+            }
+            if (job->record_counts) FQD_TRY(up(job->record_counts, n * 4, (const void **)&dj.weights));
         }
-        if (job->record_counts) FQD_TRY(up(b_weights, job->record_counts, n * 4, (const void **)&dj.weights));
         if (keep_bitmap) {
-            FQD_TRY(b_bitmap.alloc(ctx, bitmap_words * 4));
-            dj.bitmap = b_bitmap.as<uint32_t>();
+            void *p = nullptr;
+            FQD_TRY(dev_alloc(ctx, std::max<size_t>(r.bitmap_words, 4) * 4, &p));
+            dj.bitmap = static_cast<uint32_t *>(p);
+            r.host_bitmap = keep_bitmap;
         }
     } else {
         dj.keys = job->keys; dj.key_off = job->key_offsets; dj.key_lens = job->key_offsets ? nullptr : job->key_lengths;
@@ -328,62 +339,199 @@ int fqd_cluster(fqd_context *ctx, const fqd_cluster_job *job, fqd_cluster_stats 
         dj.bitmap = keep_bitmap;
         dj.weights = job->record_counts;
     }
-    FQD_CUDA(cudaEventRecord(h1, s));
+    FQD_CUDA(cudaEventRecord(r.h1, s));
 
-    // ---- key length range: PW and whether PAD is needed ----
-    if (dj.key_off || dj.key_lens) {
+    // key length range: decides PW and whether PAD is needed
+    if ((dj.key_off || dj.key_lens) && n) {
         DevCounters init{};
         init.len_min = 0xFFFFFFFFu;
         *ctx->h_ctr = init;
         FQD_CUDA(cudaMemcpyAsync(ctx->d_ctr, ctx->h_ctr, sizeof(DevCounters), cudaMemcpyHostToDevice, s));
-        length_range_kernel<<<std::min<uint64_t>(ctx->sm_count * 8, (n + 255) / 256), 256, 0, s>>>(
+        length_range_kernel<<<(unsigned)std::min<uint64_t>(ctx->sm_count * 8, (n + 255) / 256), 256, 0, s>>>(
             n, dj.key_off, dj.key_lens, ctx->d_ctr);
         FQD_CUDA(cudaGetLastError());
         FQD_CUDA(cudaMemcpyAsync(ctx->h_ctr, ctx->d_ctr, sizeof(DevCounters), cudaMemcpyDeviceToHost, s));
         FQD_CUDA(cudaStreamSynchronize(s));
-        dj.max_len = ctx->h_ctr->len_max;
-        dj.varlen = ctx->h_ctr->len_min != ctx->h_ctr->len_max;
-        if (!dj.key_off && dj.max_len > job->key_stride) { set_error("a key length exceeds key_stride"); return FQD_ERR_ARG; }
+        r.len_min = ctx->h_ctr->len_min;
+        r.len_max = ctx->h_ctr->len_max;
+        if (!dj.key_off && r.len_max > job->key_stride) { set_error("a key length exceeds key_stride"); return FQD_ERR_ARG; }
     } else {
-        dj.max_len = job->key_length;
-        dj.varlen = false;
+        r.len_min = r.len_max = n ? job->key_length : 0;
     }
+    return FQD_OK;
+}
 
-    // ---- alphabet: start from the caller's (default "ACGTN"), grow when bytes outside it show up ----
-    std::vector<uint8_t> alphabet;
-    {
-        const char *a = job->alphabet ? job->alphabet : "ACGTN";
-        bool seen[256] = {};
-        for (const char *p = a; *p; p++) {
-            const uint8_t c = (uint8_t)*p;
-            if (seen[c]) { set_error("Alphabet should consist of unique characters.Character %c was repeated. ", c); return FQD_ERR_ARG; }
-            seen[c] = true;
-            alphabet.push_back(c);
-        }
-        if (alphabet.empty()) alphabet.push_back('A');
+int parse_alphabet(const fqd_cluster_job *job, std::vector<uint8_t> &alphabet)
+{
+    const char *a = job->alphabet ? job->alphabet : "ACGTN";
+    bool seen[256] = {};
+    for (const char *p = a; *p; p++) {
+        const uint8_t c = (uint8_t)*p;
+        if (seen[c]) { set_error("Alphabet should consist of unique characters.Character %c was repeated. ", c); return FQD_ERR_ARG; }
+        seen[c] = true;
+        alphabet.push_back(c);
     }
+    if (alphabet.empty()) alphabet.push_back('A');
+    return FQD_OK;
+}
+
+int finish_job(fqd_context *ctx, Resolved &r, fqd_cluster_stats *stats)
+{
+    cudaStream_t s = ctx->stream;
+    if (r.host_bitmap && r.bitmap_words)
+        FQD_CUDA(cudaMemcpyAsync(r.host_bitmap, r.dj.bitmap, r.bitmap_words * 4, cudaMemcpyDeviceToHost, s));
+    FQD_CUDA(cudaStreamSynchronize(s));
+    if (r.h0) {
+        cudaEventElapsedTime(&stats->ms_h2d, r.h0, r.h1);
+        cudaEventDestroy(r.h0); cudaEventDestroy(r.h1);
+        r.h0 = r.h1 = nullptr;
+    }
+    return FQD_OK;
+}
+
+}  // namespace
+
+struct fqd_comm {
+    Exchange *ex = nullptr;
+};
+
+extern "C" {
+
+int fqd_cluster(fqd_context *ctx, const fqd_cluster_job *job, fqd_cluster_stats *stats,
+                uint32_t *keep_bitmap)
+{
+    FQD_TRY(check_device(ctx));
+    if (!job || !stats) { set_error("null job/stats"); return FQD_ERR_ARG; }
+    memset(stats, 0, sizeof *stats);
+    FQD_TRY(validate_job(job));
+    stats->total_records = job->n_records;
+    ctx->res = fqd_result{};          // the previous job's result lives in the arena: gone now
+    FQD_TRY(arena_reset(ctx));
+    if (job->n_records == 0) return FQD_OK;
+    Resolved r;
+    FQD_TRY(resolve_job(ctx, job, keep_bitmap, r));
+    r.dj.max_len = r.len_max;
+    r.dj.varlen = r.len_min != r.len_max;
+    std::vector<uint8_t> alphabet;
+    FQD_TRY(parse_alphabet(job, alphabet));
     int rc = FQD_OK;
     const size_t inputs_mark = arena_mark(ctx);
     for (int attempt = 0; attempt < 3; attempt++) {
         arena_release(ctx, inputs_mark);
         Codec codec;
-        FQD_TRY(make_codec(alphabet, dj.varlen, &codec));
+        FQD_TRY(make_codec(alphabet, r.dj.varlen, &codec));
         uint32_t unknown[8] = {};
-        rc = run_pipeline(ctx, dj, codec, stats, unknown);
+        rc = run_pipeline(ctx, r.dj, codec, stats, unknown);
         if (rc != RC_RETRY_ALPHABET) break;
         for (int c = 0; c < 256; c++)
             if (unknown[c >> 5] & (1u << (c & 31))) alphabet.push_back((uint8_t)c);
     }
     if (rc == RC_RETRY_ALPHABET) { set_error("internal: alphabet did not converge"); rc = FQD_ERR_CUDA; }
-    if (rc != FQD_OK) { cudaEventDestroy(h0); cudaEventDestroy(h1); return rc; }
+    if (rc != FQD_OK) return rc;
+    return finish_job(ctx, r, stats);
+}
 
-    if (job->memory_space == FQD_MEM_HOST && keep_bitmap) {
-        FQD_CUDA(cudaMemcpyAsync(keep_bitmap, dj.bitmap, bitmap_words * 4, cudaMemcpyDeviceToHost, s));
+// Shared by the two sharded entry points: `n_local` shards of a `world`-rank job.
+static int cluster_sharded_common(fqd_context **ctxs, int n_local, Exchange *ex, int world,
+                                  const fqd_cluster_job *jobs, const uint64_t *index_bases,
+                                  fqd_cluster_stats *stats, uint32_t **keep_bitmaps)
+{
+    std::vector<Resolved> R(n_local);
+    std::vector<uint8_t> alphabet;
+    FQD_TRY(parse_alphabet(&jobs[0], alphabet));
+    uint32_t lmin = 0xFFFFFFFFu, lmax = 0;
+    for (int i = 0; i < n_local; i++) {
+        FQD_TRY(check_device(ctxs[i]));
+        memset(&stats[i], 0, sizeof stats[i]);
+        FQD_TRY(validate_job(&jobs[i]));
+        if (index_bases[i] + jobs[i].n_records >= 0xFFFFFFF0ull) { set_error("global record index exceeds 32 bits"); return FQD_ERR_UNSUPPORTED; }
+        ctxs[i]->res = fqd_result{};
+        FQD_TRY(arena_reset(ctxs[i]));
+        FQD_TRY(resolve_job(ctxs[i], &jobs[i], keep_bitmaps ? keep_bitmaps[i] : nullptr, R[i]));
+        if (jobs[i].n_records) { lmin = std::min(lmin, R[i].len_min); lmax = std::max(lmax, R[i].len_max); }
     }
-    FQD_CUDA(cudaStreamSynchronize(s));
-    cudaEventElapsedTime(&stats->ms_h2d, h0, h1);
-    cudaEventDestroy(h0); cudaEventDestroy(h1);
+    if (ex) {   // agree on the global key length range
+        fqd_context *ctx = ctxs[0];
+        const size_t mark = arena_mark(ctx);
+        void *din = nullptr, *dout = nullptr;
+        FQD_TRY(dev_alloc(ctx, 16, &din));
+        FQD_TRY(dev_alloc(ctx, (size_t)world * 8 + 16, &dout));
+        uint32_t mine[2] = {lmin, lmax};
+        std::vector<uint32_t> all((size_t)world * 2);
+        FQD_CUDA(cudaMemcpyAsync(din, mine, 8, cudaMemcpyHostToDevice, ctx->stream));
+        FQD_TRY(ex->allgather(din, dout, 8, ctx->stream));
+        FQD_CUDA(cudaMemcpyAsync(all.data(), dout, (size_t)world * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        FQD_CUDA(cudaStreamSynchronize(ctx->stream));
+        for (int g = 0; g < world; g++) { lmin = std::min(lmin, all[2 * g]); lmax = std::max(lmax, all[2 * g + 1]); }
+        arena_release(ctx, mark);
+    }
+    if (lmin == 0xFFFFFFFFu) lmin = lmax = 0;   // no records anywhere
+    std::vector<DeviceJob> dj(n_local);
+    std::vector<uint32_t> bases(n_local);
+    std::vector<fqd_cluster_stats *> sp(n_local);
+    std::vector<size_t> marks(n_local);
+    for (int i = 0; i < n_local; i++) {
+        R[i].dj.max_len = lmax;
+        R[i].dj.varlen = lmin != lmax;
+        bases[i] = (uint32_t)index_bases[i];
+        sp[i] = &stats[i];
+        marks[i] = arena_mark(ctxs[i]);
+    }
+    int rc = FQD_OK;
+    for (int attempt = 0; attempt < 3; attempt++) {
+        for (int i = 0; i < n_local; i++) { arena_release(ctxs[i], marks[i]); dj[i] = R[i].dj; }
+        Codec codec;
+        FQD_TRY(make_codec(alphabet, lmin != lmax, &codec));
+        uint32_t unknown[8] = {};
+        rc = run_sharded(ctxs, dj.data(), bases.data(), sp.data(), n_local, ex, world, codec, lmax, unknown);
+        if (rc != RC_RETRY_ALPHABET) break;
+        for (int c = 0; c < 256; c++)
+            if (unknown[c >> 5] & (1u << (c & 31))) alphabet.push_back((uint8_t)c);
+    }
+    if (rc == RC_RETRY_ALPHABET) { set_error("internal: alphabet did not converge"); rc = FQD_ERR_CUDA; }
+    if (rc != FQD_OK) return rc;
+    for (int i = 0; i < n_local; i++) {
+        FQD_CUDA(cudaSetDevice(ctxs[i]->device));
+        FQD_TRY(finish_job(ctxs[i], R[i], &stats[i]));
+    }
     return FQD_OK;
+}
+
+int fqd_nccl_unique_id(uint8_t id[128]) { return nccl_unique_id(id); }
+
+int fqd_comm_create(fqd_context *ctx, int rank, int world, const uint8_t id[128], fqd_comm **out)
+{
+    FQD_TRY(check_device(ctx));
+    if (!out || world < 1 || rank < 0 || rank >= world) { set_error("bad rank/world"); return FQD_ERR_ARG; }
+    if (world > 64) { set_error("at most 64 ranks"); return FQD_ERR_UNSUPPORTED; }
+    Exchange *ex = nullptr;
+    FQD_TRY(nccl_exchange_create(rank, world, id, &ex));
+    *out = new fqd_comm{ex};
+    return FQD_OK;
+}
+
+void fqd_comm_destroy(fqd_comm *comm)
+{
+    if (!comm) return;
+    delete comm->ex;
+    delete comm;
+}
+
+int fqd_cluster_sharded(fqd_context *ctx, fqd_comm *comm, const fqd_cluster_job *job,
+                        uint64_t index_base, fqd_cluster_stats *stats, uint32_t *keep_bitmap)
+{
+    if (!ctx || !comm || !job || !stats) { set_error("null argument"); return FQD_ERR_ARG; }
+    uint32_t *bm[1] = {keep_bitmap};
+    return cluster_sharded_common(&ctx, 1, comm->ex, comm->ex->world, job, &index_base, stats, bm);
+}
+
+int fqd_cluster_sharded_local(fqd_context **ctxs, int world, const fqd_cluster_job *jobs,
+                              const uint64_t *index_bases, fqd_cluster_stats *stats,
+                              uint32_t **keep_bitmaps)
+{
+    if (!ctxs || !jobs || !stats || !index_bases || world < 1) { set_error("null argument"); return FQD_ERR_ARG; }
+    if (world > 64) { set_error("at most 64 ranks"); return FQD_ERR_UNSUPPORTED; }
+    return cluster_sharded_common(ctxs, world, nullptr, world, jobs, index_bases, stats, keep_bitmaps);
 }
 
 int fqd_cluster_fetch(fqd_context *ctx, uint64_t *first, uint32_t *count, uint64_t *label,

@@ -17,15 +17,15 @@ namespace fqd {
 void set_error(const char *fmt, ...);
 int cuda_fail(cudaError_t e, const char *what, const char *file, int line);
 
-#define FQD_CUDA(call)                                                            \
-    do {                                                                          \
-        cudaError_t _e = (call);                                                  \
-        if (_e != cudaSuccess) return ::fqd::cuda_fail(_e, #call, __FILE__, __LINE__); \
+#define FQD_CUDA(...)                                                                    \
+    do {                                                                                 \
+        cudaError_t _e = (__VA_ARGS__);                                                  \
+        if (_e != cudaSuccess) return ::fqd::cuda_fail(_e, #__VA_ARGS__, __FILE__, __LINE__); \
     } while (0)
 
-#define FQD_TRY(call)                \
-    do {                             \
-        int _rc = (call);            \
+#define FQD_TRY(...)                   \
+    do {                               \
+        int _rc = (__VA_ARGS__);       \
         if (_rc != FQD_OK) return _rc; \
     } while (0)
 
@@ -62,6 +62,9 @@ struct fqd_context {
     cudaEvent_t ev[12] = {};
     fqd_result res;
     int sm_count = 148;
+    // dedupe table of the running job (arena memory), handed from the ingest to the gather
+    uint32_t *scratch_table = nullptr;
+    uint32_t *scratch_uslot = nullptr;
 };
 
 namespace fqd {
@@ -129,6 +132,12 @@ constexpr int RC_RETRY_ALPHABET = -100;   // internal: unknown bytes were seen, 
 // pipeline.cu: runs the stages for one (K, PW) instantiation
 int run_pipeline(fqd_context *ctx, const DeviceJob &job, const Codec &codec,
                  fqd_cluster_stats *stats, uint32_t unknown_out[8]);
+// sharded plan over `world` ranks; this process drives n_local of them (all of them as
+// virtual ranks when ex == nullptr, exactly one over NCCL otherwise)
+struct Exchange;
+int run_sharded(fqd_context **ctxs, const DeviceJob *jobs, const uint32_t *index_base,
+                fqd_cluster_stats **stats, int n_local, Exchange *ex, int world, const Codec &codec,
+                uint32_t max_len, uint32_t unknown_out[8]);
 
 // largest key (in symbols) this build can pack for a given number of code bits
 uint32_t max_supported_length(int bits);

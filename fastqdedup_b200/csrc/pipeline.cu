@@ -1,8 +1,11 @@
-// pipeline.cu -- launch plan of the clustering job on one B200 (see pipeline.cuh for the
-// kernels and DESIGN.md for the data layout / rooflines).
+// pipeline.cu -- launch plans of the clustering job: one B200 (run_pipeline) and sharded over
+// several ranks (run_sharded).  Kernels are in pipeline.cuh; DESIGN.md has the data layout and
+// the per-kernel rooflines.
 #include <algorithm>
+#include <vector>
 
 #include "common.h"
+#include "exchange.h"
 
 namespace fqd {
 
@@ -10,28 +13,21 @@ namespace {
 
 inline uint32_t cdiv(uint64_t a, uint32_t b) { return (uint32_t)((a + b - 1) / b); }
 
-struct Timer {
-    fqd_context *ctx;
-    int next = 0;
-    explicit Timer(fqd_context *c) : ctx(c) {}
-    int mark()
-    {
-        cudaEventRecord(ctx->ev[next], ctx->stream);
-        return next++;
-    }
-    float ms(int a, int b)
-    {
-        float t = 0.f;
-        cudaEventElapsedTime(&t, ctx->ev[a], ctx->ev[b]);
-        return t;
-    }
-};
-
 int fetch_counters(fqd_context *ctx)
 {
     FQD_CUDA(cudaMemcpyAsync(ctx->h_ctr, ctx->d_ctr, sizeof(DevCounters), cudaMemcpyDeviceToHost,
                              ctx->stream));
     FQD_CUDA(cudaStreamSynchronize(ctx->stream));
+    return FQD_OK;
+}
+
+int reset_counters(fqd_context *ctx)
+{
+    DevCounters zero{};
+    zero.phred_err = ~0ull;
+    zero.len_min = 0xFFFFFFFFu;
+    *ctx->h_ctr = zero;
+    FQD_CUDA(cudaMemcpyAsync(ctx->d_ctr, ctx->h_ctr, sizeof(DevCounters), cudaMemcpyHostToDevice, ctx->stream));
     return FQD_OK;
 }
 
@@ -50,43 +46,61 @@ int exclusive_scan_inplace(fqd_context *ctx, uint32_t *data, uint32_t n, uint32_
     return FQD_OK;
 }
 
-template <int K, int PW>
-int run_typed(fqd_context *ctx, const DeviceJob &job, const Codec &codec, fqd_cluster_stats *st,
-              uint32_t unknown_out[8])
+// ---- the dense unique set and the per-unique state of one rank -------------------------------
+
+struct Uniques {
+    uint32_t U = 0;
+    uint32_t *ukey = nullptr, *ucount = nullptr, *ufirst = nullptr;
+};
+
+struct Forest {
+    uint32_t *parent_full = nullptr, *parent_one = nullptr, *best = nullptr, *root = nullptr;
+    uint8_t *dominated = nullptr, *dead = nullptr, *deadroot = nullptr, *selected = nullptr;
+    uint2 *edges = nullptr;
+    unsigned long long edge_cap = 0, n_edges = 0;
+};
+
+struct StageTimes {
+    float table_clear = 0, ingest_kernel = 0, ingest = 0, compare = 0;
+    uint32_t launches = 0;
+};
+
+template <typename T>
+int arena(fqd_context *ctx, size_t count, T **p)
 {
-    constexpr int KW = K * PW, RW = slot_words(KW), FW = fat_words(KW);
+    void *q = nullptr;
+    FQD_TRY(dev_alloc(ctx, std::max<size_t>(count * sizeof(T), 16), &q));
+    *p = static_cast<T *>(q);
+    return FQD_OK;
+}
+
+// ---- stage 1: filter + pack + exact dedupe of this rank's records ----------------------------
+// Leaves the table in ctx->scratch_table / scratch_uslot for the gather and allocates the
+// dense arrays of `uq` (U entries).
+
+template <int K, int PW>
+int stage_dedupe(fqd_context *ctx, const DeviceJob &job, const Codec &codec, uint32_t index_base,
+                 bool sharded, fqd_cluster_stats *st, uint32_t unknown_out[8], Uniques &uq,
+                 StageTimes &tt)
+{
+    constexpr int KW = K * PW, RW = slot_words(KW);
     cudaStream_t s = ctx->stream;
-    Timer tm(ctx);
     const uint64_t n = job.n;
+    FQD_TRY(reset_counters(ctx));
+    cudaEvent_t *ev = ctx->ev;
+    FQD_CUDA(cudaEventRecord(ev[0], s));
 
-    // ---- counters ----
-    DevCounters zero{};
-    zero.phred_err = ~0ull;
-    zero.len_min = 0xFFFFFFFFu;
-    *ctx->h_ctr = zero;
-    FQD_CUDA(cudaMemcpyAsync(ctx->d_ctr, ctx->h_ctr, sizeof(DevCounters), cudaMemcpyHostToDevice, s));
-
-    ctx->res = fqd_result{};
-    ctx->res.n_records = n;
-
-    st->key_bits = K;
-    st->key_words = KW;
-
-    const int t_begin = tm.mark();
-
-    // ---- ingest: filter + pack + exact dedupe into the HBM table ----
     const uint64_t capacity = std::max<uint64_t>(1024, n + (n >> 1) + 64);
     if (capacity >= 0xFFFFFFF0ull) {
         set_error("too many records for one job on one GPU (%llu)", (unsigned long long)n);
         return FQD_ERR_UNSUPPORTED;
     }
-    DevBuf table, uslot, keepmask;
-    FQD_TRY(table.alloc(ctx, capacity * RW * sizeof(uint32_t)));
-    FQD_TRY(uslot.alloc(ctx, n * sizeof(uint32_t)));
-    FQD_TRY(keepmask.alloc(ctx, (size_t)cdiv(n, 32) * sizeof(uint32_t)));
-    FQD_CUDA(cudaMemsetAsync(table.p, 0xFF, capacity * RW * sizeof(uint32_t), s));
-    const int t_cleared = tm.mark();
-    uint32_t launches = 0;
+    uint32_t *table, *uslot, *keepmask;
+    FQD_TRY(arena(ctx, capacity * RW, &table));
+    FQD_TRY(arena(ctx, std::max<uint64_t>(n, 1), &uslot));
+    FQD_TRY(arena(ctx, cdiv(std::max<uint64_t>(n, 1), 32), &keepmask));
+    FQD_CUDA(cudaMemsetAsync(table, 0xFF, capacity * RW * sizeof(uint32_t), s));
+    FQD_CUDA(cudaEventRecord(ev[1], s));
 
     IngestParams ip{};
     ip.n = n;
@@ -99,11 +113,11 @@ int run_typed(fqd_context *ctx, const DeviceJob &job, const Codec &codec, fqd_cl
     ip.max_err = job.max_err;
     ip.phred_offset = job.phred_offset;
     ip.pad_code = codec.pad_code;
-    ip.table = table.as<uint32_t>();
-    ip.capacity = capacity;
-    ip.uslot = uslot.as<uint32_t>();
-    ip.keepmask = keepmask.as<uint32_t>();
+    ip.tab.table = table; ip.tab.capacity = capacity; ip.tab.uslot = uslot; ip.tab.ctr = ctx->d_ctr;
+    ip.keepmask = keepmask;
     ip.weights = job.weights;
+    ip.index_base = index_base;
+    ip.sharded = sharded ? 1 : 0;
     ip.ctr = ctx->d_ctr;
     ip.codec = codec;
     // shared-memory staging of fixed-stride rows
@@ -119,206 +133,691 @@ int run_typed(fqd_context *ctx, const DeviceJob &job, const Codec &codec, fqd_cl
     FQD_CUDA(cudaFuncSetAttribute(ingest_kernel<K, PW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)smem));
     ip.phase = 0;
-    ingest_kernel<K, PW><<<cdiv(n, 256), 256, smem, s>>>(ip);
-    launches++;
-    const int t_ingest_k = tm.mark();
+    if (n) { ingest_kernel<K, PW><<<cdiv(n, 256), 256, smem, s>>>(ip); tt.launches++; }
+    FQD_CUDA(cudaEventRecord(ev[2], s));
     FQD_CUDA(cudaGetLastError());
     FQD_TRY(fetch_counters(ctx));
     const DevCounters c1 = *ctx->h_ctr;
+    bool any_unknown = false;
+    for (int i = 0; i < 8; i++) { unknown_out[i] = c1.unknown[i]; any_unknown |= c1.unknown[i] != 0; }
+    st->bad_record = ~0ull;
     if (c1.phred_err != ~0ull) {
         st->bad_record = c1.phred_err >> 8;
         st->bad_char = (uint32_t)(c1.phred_err & 0xFF);
-        set_error("Character %c outside of valid phred range ('%c' to '%c')",
-                  (int)st->bad_char, (int)job.phred_offset, 126);
-        return FQD_ERR_PHRED;
+        if (!sharded) {
+            set_error("Character %c outside of valid phred range ('%c' to '%c')",
+                      (int)st->bad_char, (int)job.phred_offset, 126);
+            return FQD_ERR_PHRED;
+        }
     }
-    bool any_unknown = false;
-    for (int i = 0; i < 8; i++) { unknown_out[i] = c1.unknown[i]; any_unknown |= c1.unknown[i] != 0; }
-    if (any_unknown) return RC_RETRY_ALPHABET;
+    if (any_unknown && !sharded) return RC_RETRY_ALPHABET;
     if (c1.table_full) { set_error("internal: dedupe table overflow"); return FQD_ERR_NOMEM; }
-    if (job.filter_on && c1.n_discarded) {
+    if (job.filter_on && c1.n_discarded && !sharded) {
         ip.phase = 1;
         ingest_kernel<K, PW><<<cdiv(n, 256), 256, smem, s>>>(ip);
-        launches++;
+        tt.launches++;
         FQD_CUDA(cudaGetLastError());
     }
+    FQD_CUDA(cudaEventRecord(ev[3], s));
     const uint32_t U = c1.n_unique;
     st->total_records = n;
     st->discarded_records = c1.n_discarded;
     st->number_of_sequences = job.weights ? c1.sum_weights : n - c1.n_discarded;
-    st->number_of_uniques = U;
-    const int t_ingest = tm.mark();
-    if (U > ENT_UID) { set_error("too many unique keys for one GPU (%u)", U); return FQD_ERR_UNSUPPORTED; }
 
-    // ---- gather ----
-    const bool directional = job.method == METHOD_DIRECTIONAL;
-    DevBuf ukey, ucount, ufirst, parent_full, parent_one, best, selected;
-    FQD_TRY(ukey.alloc(ctx, (size_t)U * KW * 4));
-    FQD_TRY(ucount.alloc(ctx, (size_t)U * 4));
-    FQD_TRY(ufirst.alloc(ctx, (size_t)U * 4));
-    FQD_TRY(parent_full.alloc(ctx, (size_t)U * 4));
-    FQD_TRY(selected.alloc(ctx, (size_t)U));
-    if (directional) FQD_TRY(parent_one.alloc(ctx, (size_t)U * 4));
-    if (job.method != METHOD_ADJACENCY) FQD_TRY(best.alloc(ctx, (size_t)U * 4));
-    if (U) {
-        gather_kernel<K, PW><<<cdiv(U, 256), 256, 0, s>>>(U, table.as<uint32_t>(), uslot.as<uint32_t>(),
-                                                          ukey.as<uint32_t>(), ucount.as<uint32_t>(),
-                                                          ufirst.as<uint32_t>(), parent_full.as<uint32_t>(),
-                                                          parent_one.as<uint32_t>(), best.as<uint32_t>());
-        launches++;
-    }
-    FQD_CUDA(cudaGetLastError());
-    table.reset(); uslot.reset(); keepmask.reset();
-    const int t_gather = tm.mark();
+    uq.U = U;
+    FQD_TRY(arena(ctx, (size_t)U * KW, &uq.ukey));
+    FQD_TRY(arena(ctx, U, &uq.ucount));
+    FQD_TRY(arena(ctx, U, &uq.ufirst));
+    ctx->scratch_table = table;
+    ctx->scratch_uslot = uslot;
+    FQD_CUDA(cudaEventSynchronize(ev[3]));
+    cudaEventElapsedTime(&tt.table_clear, ev[0], ev[1]);
+    cudaEventElapsedTime(&tt.ingest_kernel, ev[1], ev[2]);
+    cudaEventElapsedTime(&tt.ingest, ev[0], ev[3]);
+    return FQD_OK;
+}
 
-    // ---- pigeonhole passes ----
-    DevBuf dominated, dead, deadroot, edges, rootbuf;
-    FQD_TRY(rootbuf.alloc(ctx, (size_t)U * 4));
-    if (directional) {
-        FQD_TRY(dominated.alloc(ctx, U)); FQD_TRY(dead.alloc(ctx, U)); FQD_TRY(deadroot.alloc(ctx, U));
-        FQD_CUDA(cudaMemsetAsync(dominated.p, 0, U ? U : 1, s));
-        FQD_CUDA(cudaMemsetAsync(dead.p, 0, U ? U : 1, s));
-        FQD_CUDA(cudaMemsetAsync(deadroot.p, 0, U ? U : 1, s));
+// ---- stage 2: forest / flag arrays over U uniques ----------------------------------------------
+
+int stage_forest_alloc(fqd_context *ctx, int method, uint32_t U, Forest &f)
+{
+    cudaStream_t s = ctx->stream;
+    FQD_TRY(arena(ctx, U, &f.parent_full));
+    FQD_TRY(arena(ctx, U, &f.root));
+    FQD_TRY(arena(ctx, U, &f.selected));
+    if (method == METHOD_DIRECTIONAL) {
+        FQD_TRY(arena(ctx, U, &f.parent_one));
+        FQD_TRY(arena(ctx, U, &f.dominated));
+        FQD_TRY(arena(ctx, U, &f.dead));
+        FQD_TRY(arena(ctx, U, &f.deadroot));
+        FQD_CUDA(cudaMemsetAsync(f.dominated, 0, std::max<size_t>(U, 1), s));
+        FQD_CUDA(cudaMemsetAsync(f.dead, 0, std::max<size_t>(U, 1), s));
+        FQD_CUDA(cudaMemsetAsync(f.deadroot, 0, std::max<size_t>(U, 1), s));
     }
-    unsigned long long edge_cap = 0;
-    if (job.method == METHOD_ADJACENCY) {
-        edge_cap = 2ull * U + (1ull << 16);
-        FQD_TRY(edges.alloc(ctx, edge_cap * sizeof(uint2)));
+    if (method != METHOD_ADJACENCY) FQD_TRY(arena(ctx, U, &f.best));
+    if (method == METHOD_ADJACENCY) {
+        f.edge_cap = 2ull * U + (1ull << 16);
+        FQD_TRY(arena(ctx, f.edge_cap, &f.edges));
     }
+    return FQD_OK;
+}
+
+// ---- stage 3: pigeonhole passes over the buckets this rank owns --------------------------------
+
+template <int K, int PW>
+int stage_passes(fqd_context *ctx, const DeviceJob &job, const Codec &codec, const Uniques &uq,
+                 Forest &f, int rank, int world, fqd_cluster_stats *st, StageTimes &tt)
+{
+    constexpr int KW = K * PW, FW = fat_words(KW);
+    cudaStream_t s = ctx->stream;
+    const uint32_t U = uq.U;
     const int npass = (job.d > 0 && U > 1) ? job.d + 1 : 0;
     st->n_passes = npass;
-    float ms_compare = 0.f;
-    if (npass) {
-        const int V = job.edit ? (job.varlen ? 2 * job.d + 1 : 1) * (job.d + 1) : 1;
-        const uint64_t E = (uint64_t)U * V;
-        if (E >= 0xFFFFFFF0ull) { set_error("too many pigeonhole entries (%llu)", (unsigned long long)E); return FQD_ERR_UNSUPPORTED; }
-        uint32_t NB = 1024;
-        while (NB < (1u << 24) && NB < E / 2) NB <<= 1;
-        DevBuf cnt, rank, entries, block_sums, grand;
-        FQD_TRY(cnt.alloc(ctx, ((size_t)NB + 1) * 4));
-        FQD_TRY(rank.alloc(ctx, E * 4));
-        const bool fat = !job.edit;
-        FQD_TRY(entries.alloc(ctx, fat ? E * FW * sizeof(uint32_t) : E * sizeof(uint2)));
-        FQD_TRY(block_sums.alloc(ctx, (size_t)cdiv(NB, SCAN_TILE) * 4 + 64));
-        FQD_TRY(grand.alloc(ctx, 16));
-        PassParams pp{};
-        pp.U = U; pp.ukey = ukey.as<uint32_t>(); pp.ucount = ucount.as<uint32_t>();
-        pp.d = job.d; pp.edit = job.edit; pp.varlen = job.varlen ? 1 : 0; pp.method = job.method;
-        pp.max_len = job.max_len; pp.pad_code = codec.pad_code;
-        pp.V = V; pp.nb_mask = NB - 1;
-        pp.cnt = cnt.as<uint32_t>(); pp.rank = rank.as<uint32_t>(); pp.entries = entries.as<uint2>(); pp.fat = entries.as<uint32_t>();
-        pp.parent_full = parent_full.as<uint32_t>(); pp.parent_one = parent_one.as<uint32_t>();
-        pp.dominated = dominated.as<uint8_t>(); pp.dead = dead.as<uint8_t>();
-        pp.edges = edges.as<uint2>(); pp.edge_cap = edge_cap; pp.ctr = ctx->d_ctr;
-        for (int i = 0; i < 256; i++) pp.rank_of_code[i] = codec.rank[i];
-        std::vector<cudaEvent_t> cev(2 * npass);
-        for (auto &e : cev) FQD_CUDA(cudaEventCreate(&e));
-        for (int attempt = 0; attempt < 2; attempt++) {
-            for (int j = 0; j < npass; j++) {
-                pp.pass_j = j;
-                FQD_CUDA(cudaMemsetAsync(cnt.p, 0, ((size_t)NB + 1) * 4, s));
-                sig_count_kernel<K, PW><<<cdiv(U, 256), 256, 0, s>>>(pp);
-                FQD_TRY(exclusive_scan_inplace(ctx, cnt.as<uint32_t>(), NB, block_sums.as<uint32_t>(),
-                                               grand.as<uint32_t>()));
-                if (fat) scatter_fat_kernel<K, PW><<<cdiv(U, 256), 256, 0, s>>>(pp);
-                else scatter_kernel<K, PW><<<cdiv(U, 256), 256, 0, s>>>(pp);
-                pp.n_entries = (uint32_t)E;   // upper bound; the kernel stops at cnt[NB]
-                launches += 6;   // sig_count, 3 scan kernels, scatter, compare
-                FQD_CUDA(cudaEventRecord(cev[2 * j], s));
-                if (fat) compare_fat_kernel<K, PW><<<cdiv(E, 256), 256, 0, s>>>(pp);
-                else compare_kernel<K, PW><<<cdiv(E, 256), 256, 0, s>>>(pp);
-                FQD_CUDA(cudaEventRecord(cev[2 * j + 1], s));
-                FQD_CUDA(cudaGetLastError());
-            }
-            if (job.method != METHOD_ADJACENCY) break;
-            FQD_TRY(fetch_counters(ctx));
-            if (ctx->h_ctr->n_edges <= edge_cap) break;
-            if (attempt == 1) { set_error("internal: adjacency edge list overflow"); return FQD_ERR_NOMEM; }
-            // edge list overflowed: size it exactly, reset the forest and redo the passes
-            edge_cap = ctx->h_ctr->n_edges + 16;
-            FQD_TRY(edges.alloc(ctx, edge_cap * sizeof(uint2)));
-            pp.edges = edges.as<uint2>(); pp.edge_cap = edge_cap;
-            ctx->h_ctr->n_edges = 0; ctx->h_ctr->n_merges = 0; ctx->h_ctr->n_candidates = 0;
-            FQD_CUDA(cudaMemcpyAsync(ctx->d_ctr, ctx->h_ctr, sizeof(DevCounters), cudaMemcpyHostToDevice, s));
-            iota_kernel<<<cdiv(U, 256), 256, 0, s>>>(parent_full.as<uint32_t>(), U);
-            launches++;
-        }
-        FQD_CUDA(cudaStreamSynchronize(s));
+    if (!npass) return FQD_OK;
+    const int V = job.edit ? (job.varlen ? 2 * job.d + 1 : 1) * (job.d + 1) : 1;
+    const uint64_t E = (uint64_t)U * V;
+    if (E >= 0xFFFFFFF0ull) { set_error("too many pigeonhole entries (%llu)", (unsigned long long)E); return FQD_ERR_UNSUPPORTED; }
+    uint32_t NB = 1024;
+    while (NB < (1u << 24) && NB < E / 2) NB <<= 1;
+    const bool fat = !job.edit;
+    uint32_t *cnt, *rank_arr, *entries, *block_sums, *grand;
+    FQD_TRY(arena(ctx, (size_t)NB + 1, &cnt));
+    FQD_TRY(arena(ctx, E, &rank_arr));
+    FQD_TRY(arena(ctx, fat ? E * FW : E * 2, &entries));
+    FQD_TRY(arena(ctx, (size_t)cdiv(NB, SCAN_TILE) + 16, &block_sums));
+    FQD_TRY(arena(ctx, 4, &grand));
+    PassParams pp{};
+    pp.U = U; pp.ukey = uq.ukey; pp.ucount = uq.ucount;
+    pp.d = job.d; pp.edit = job.edit; pp.varlen = job.varlen ? 1 : 0; pp.method = job.method;
+    pp.max_len = job.max_len; pp.pad_code = codec.pad_code;
+    pp.V = V; pp.nb_mask = NB - 1; pp.my_rank = rank; pp.world = world;
+    pp.cnt = cnt; pp.rank = rank_arr; pp.entries = reinterpret_cast<uint2 *>(entries); pp.fat = entries;
+    pp.parent_full = f.parent_full; pp.parent_one = f.parent_one;
+    pp.dominated = f.dominated; pp.dead = f.dead;
+    pp.edges = f.edges; pp.edge_cap = f.edge_cap; pp.ctr = ctx->d_ctr;
+    for (int i = 0; i < 256; i++) pp.rank_of_code[i] = codec.rank[i];
+    std::vector<cudaEvent_t> cev(2 * npass);
+    for (auto &e : cev) FQD_CUDA(cudaEventCreate(&e));
+    for (int attempt = 0; attempt < 2; attempt++) {
         for (int j = 0; j < npass; j++) {
-            float t = 0.f;
-            cudaEventElapsedTime(&t, cev[2 * j], cev[2 * j + 1]);
-            ms_compare += t;
+            pp.pass_j = j;
+            FQD_CUDA(cudaMemsetAsync(cnt, 0, ((size_t)NB + 1) * 4, s));
+            sig_count_kernel<K, PW><<<cdiv(U, 256), 256, 0, s>>>(pp);
+            FQD_TRY(exclusive_scan_inplace(ctx, cnt, NB, block_sums, grand));
+            if (fat) scatter_fat_kernel<K, PW><<<cdiv(U, 256), 256, 0, s>>>(pp);
+            else scatter_kernel<K, PW><<<cdiv(U, 256), 256, 0, s>>>(pp);
+            pp.n_entries = (uint32_t)E;   // upper bound; the kernel stops at cnt[NB]
+            tt.launches += 6;             // sig_count, 3 scan kernels, scatter, compare
+            FQD_CUDA(cudaEventRecord(cev[2 * j], s));
+            if (fat) compare_fat_kernel<K, PW><<<cdiv(E, 256), 256, 0, s>>>(pp);
+            else compare_kernel<K, PW><<<cdiv(E, 256), 256, 0, s>>>(pp);
+            FQD_CUDA(cudaEventRecord(cev[2 * j + 1], s));
+            FQD_CUDA(cudaGetLastError());
         }
-        for (auto &e : cev) cudaEventDestroy(e);
+        if (job.method != METHOD_ADJACENCY) break;
+        FQD_TRY(fetch_counters(ctx));
+        if (ctx->h_ctr->n_edges <= f.edge_cap) break;
+        if (attempt == 1) { set_error("internal: adjacency edge list overflow"); return FQD_ERR_NOMEM; }
+        // edge list overflowed: size it exactly, reset the forest and redo the passes
+        f.edge_cap = ctx->h_ctr->n_edges + 16;
+        FQD_TRY(arena(ctx, f.edge_cap, &f.edges));
+        pp.edges = f.edges; pp.edge_cap = f.edge_cap;
+        ctx->h_ctr->n_edges = 0; ctx->h_ctr->n_merges = 0; ctx->h_ctr->n_candidates = 0;
+        FQD_CUDA(cudaMemcpyAsync(ctx->d_ctr, ctx->h_ctr, sizeof(DevCounters), cudaMemcpyHostToDevice, s));
+        iota_kernel<<<cdiv(U, 256), 256, 0, s>>>(f.parent_full, U);
+        tt.launches++;
     }
-    const int t_pass = tm.mark();
+    FQD_CUDA(cudaStreamSynchronize(s));
+    for (int j = 0; j < npass; j++) {
+        float t = 0.f;
+        cudaEventElapsedTime(&t, cev[2 * j], cev[2 * j + 1]);
+        tt.compare += t;
+    }
+    for (auto &e : cev) cudaEventDestroy(e);
+    return FQD_OK;
+}
 
-    // ---- components + dissection ----
+// ---- stage 4: dissection + output ------------------------------------------------------------------
+
+template <int K, int PW>
+int stage_select(fqd_context *ctx, const DeviceJob &job, const Codec &codec, const Uniques &uq,
+                 Forest &f, uint32_t bitmap_base, uint32_t bitmap_n, StageTimes &tt)
+{
+    cudaStream_t s = ctx->stream;
+    const uint32_t U = uq.U;
     SelectParams sp{};
-    sp.U = U; sp.ukey = ukey.as<uint32_t>(); sp.ucount = ucount.as<uint32_t>(); sp.ufirst = ufirst.as<uint32_t>();
-    sp.parent_full = parent_full.as<uint32_t>(); sp.parent_one = parent_one.as<uint32_t>();
-    sp.best = best.as<uint32_t>(); sp.root = rootbuf.as<uint32_t>();
-    sp.dominated = dominated.as<uint8_t>(); sp.dead = dead.as<uint8_t>(); sp.deadroot = deadroot.as<uint8_t>();
-    sp.selected = selected.as<uint8_t>();
-    sp.method = job.method; sp.ctr = ctx->d_ctr; sp.bitmap = job.bitmap;
+    sp.U = U; sp.ukey = uq.ukey; sp.ucount = uq.ucount; sp.ufirst = uq.ufirst;
+    sp.parent_full = f.parent_full; sp.parent_one = f.parent_one;
+    sp.best = f.best; sp.root = f.root;
+    sp.dominated = f.dominated; sp.dead = f.dead; sp.deadroot = f.deadroot;
+    sp.selected = f.selected;
+    sp.method = job.method; sp.ctr = ctx->d_ctr;
+    sp.bitmap = job.bitmap; sp.bitmap_base = bitmap_base; sp.bitmap_n = bitmap_n;
     for (int i = 0; i < 256; i++) sp.rank_of_code[i] = codec.rank[i];
-    if (job.bitmap) FQD_CUDA(cudaMemsetAsync(job.bitmap, 0, (size_t)cdiv(n, 32) * 4, s));
-    DevBuf state, stamp;
-    if (U) {
-        if (job.method == METHOD_DIRECTIONAL) {
-            root_best_kernel<K, PW><<<cdiv(U, 256), 256, 0, s>>>(sp, 1);
-            launches++;
-        } else if (job.method == METHOD_HIGHEST) {
-            root_best_kernel<K, PW><<<cdiv(U, 256), 256, 0, s>>>(sp, 0);
-            launches++;
-        } else {
-            FQD_TRY(state.alloc(ctx, U)); FQD_TRY(stamp.alloc(ctx, (size_t)U * 4));
-            FQD_CUDA(cudaMemsetAsync(state.p, 0, U, s));
-            FQD_CUDA(cudaMemsetAsync(stamp.p, 0, (size_t)U * 4, s));
-            sp.state = state.as<uint8_t>(); sp.stamp = stamp.as<uint32_t>();
-            sp.edges = edges.as<uint2>();
+    if (job.bitmap) FQD_CUDA(cudaMemsetAsync(job.bitmap, 0, (size_t)cdiv(std::max<uint32_t>(bitmap_n, 1), 32) * 4, s));
+    if (!U) return FQD_OK;
+    if (job.method == METHOD_DIRECTIONAL) {
+        root_best_kernel<K, PW><<<cdiv(U, 256), 256, 0, s>>>(sp, 1);
+        tt.launches++;
+    } else if (job.method == METHOD_HIGHEST) {
+        root_best_kernel<K, PW><<<cdiv(U, 256), 256, 0, s>>>(sp, 0);
+        tt.launches++;
+    } else {
+        FQD_TRY(arena(ctx, U, &sp.state));
+        FQD_TRY(arena(ctx, U, &sp.stamp));
+        FQD_CUDA(cudaMemsetAsync(sp.state, 0, U, s));
+        FQD_CUDA(cudaMemsetAsync(sp.stamp, 0, (size_t)U * 4, s));
+        sp.edges = f.edges;
+        sp.n_edges = f.n_edges;
+        for (uint32_t round = 1;; round++) {
+            sp.round = round;
+            FQD_CUDA(cudaMemsetAsync(&ctx->d_ctr->undecided, 0, 4, s));
+            if (sp.n_edges) { adj_edge_kernel<<<cdiv(sp.n_edges, 256), 256, 0, s>>>(sp); tt.launches++; }
+            adj_node_kernel<<<cdiv(U, 256), 256, 0, s>>>(sp);
+            tt.launches++;
             FQD_TRY(fetch_counters(ctx));
-            sp.n_edges = std::min<unsigned long long>(ctx->h_ctr->n_edges, edge_cap);
-            if (ctx->h_ctr->n_edges > edge_cap) { set_error("internal: adjacency edge list overflow"); return FQD_ERR_NOMEM; }
-            for (uint32_t round = 1;; round++) {
-                sp.round = round;
-                FQD_CUDA(cudaMemsetAsync(&ctx->d_ctr->undecided, 0, 4, s));
-                if (sp.n_edges) { adj_edge_kernel<<<cdiv(sp.n_edges, 256), 256, 0, s>>>(sp); launches++; }
-                adj_node_kernel<<<cdiv(U, 256), 256, 0, s>>>(sp);
-                launches++;
-                FQD_TRY(fetch_counters(ctx));
-                if (ctx->h_ctr->undecided == 0) break;
-                if (round > U + 2) { set_error("internal: adjacency rounds did not converge"); return FQD_ERR_CUDA; }
-            }
+            if (ctx->h_ctr->undecided == 0) break;
+            if (round > U + 2) { set_error("internal: adjacency rounds did not converge"); return FQD_ERR_CUDA; }
         }
-        select_kernel<<<cdiv(U, 256), 256, 0, s>>>(sp);
-        launches++;
-        FQD_CUDA(cudaGetLastError());
     }
+    select_kernel<<<cdiv(U, 256), 256, 0, s>>>(sp);
+    tt.launches++;
+    FQD_CUDA(cudaGetLastError());
+    return FQD_OK;
+}
+
+void publish_result(fqd_context *ctx, const Uniques &uq, const Forest &f, uint64_t n_records,
+                    uint64_t n_selected)
+{
+    ctx->res.U = uq.U;
+    ctx->res.n_records = n_records;
+    ctx->res.n_selected = n_selected;
+    ctx->res.ufirst = uq.ufirst;
+    ctx->res.ucount = uq.ucount;
+    ctx->res.parent_full = f.parent_full;
+    ctx->res.selected = f.selected;
+}
+
+// ---- single-GPU plan ---------------------------------------------------------------------------------
+
+template <int K, int PW>
+int run_typed(fqd_context *ctx, const DeviceJob &job, const Codec &codec, fqd_cluster_stats *st,
+              uint32_t unknown_out[8])
+{
+    cudaStream_t s = ctx->stream;
+    ctx->res = fqd_result{};
+    st->key_bits = K;
+    st->key_words = K * PW;
+    cudaEvent_t *ev = ctx->ev;   // 4..8 belong to this plan, 0..3 to stage_dedupe
+    FQD_CUDA(cudaEventRecord(ev[4], s));
+    StageTimes tt;
+    Uniques uq;
+    FQD_TRY(stage_dedupe<K, PW>(ctx, job, codec, 0, false, st, unknown_out, uq, tt));
+    const uint32_t U = uq.U;
+    st->number_of_uniques = U;
+    if (U > ENT_UID) { set_error("too many unique keys for one GPU (%u)", U); return FQD_ERR_UNSUPPORTED; }
+    FQD_CUDA(cudaEventRecord(ev[5], s));
+    Forest f;
+    FQD_TRY(stage_forest_alloc(ctx, job.method, U, f));
+    if (U) {
+        gather_kernel<K, PW><<<cdiv(U, 256), 256, 0, s>>>(U, ctx->scratch_table, ctx->scratch_uslot, uq.ukey,
+                                                          uq.ucount, uq.ufirst, f.parent_full, f.parent_one, f.best);
+        tt.launches++;
+    }
+    FQD_CUDA(cudaGetLastError());
+    FQD_CUDA(cudaEventRecord(ev[6], s));
+    FQD_TRY(stage_passes<K, PW>(ctx, job, codec, uq, f, 0, 1, st, tt));
+    if (job.method == METHOD_ADJACENCY) {
+        FQD_TRY(fetch_counters(ctx));
+        f.n_edges = ctx->h_ctr->n_edges;
+    }
+    FQD_CUDA(cudaEventRecord(ev[7], s));
+    FQD_TRY(stage_select<K, PW>(ctx, job, codec, uq, f, 0, (uint32_t)job.n, tt));
     FQD_TRY(fetch_counters(ctx));
-    const int t_end = tm.mark();
+    FQD_CUDA(cudaEventRecord(ev[8], s));
     FQD_CUDA(cudaStreamSynchronize(s));
     const DevCounters c2 = *ctx->h_ctr;
     st->number_of_clusters = (uint64_t)U - c2.n_merges;
     st->number_selected = c2.n_selected;
     st->candidate_pairs = c2.n_candidates;
-    st->ms_total = tm.ms(t_begin, t_end);
-    st->ms_ingest = tm.ms(t_begin, t_ingest);
-    st->ms_gather = tm.ms(t_ingest, t_gather);
-    st->ms_neighbour = tm.ms(t_gather, t_pass);
-    st->ms_select = tm.ms(t_pass, t_end);
-    st->ms_compare = ms_compare;
-    st->ms_table_clear = tm.ms(t_begin, t_cleared);
-    st->ms_ingest_kernel = tm.ms(t_cleared, t_ingest_k);
-    st->ms_bucket_build = st->ms_neighbour - ms_compare;
-    st->launches = launches;
+    cudaEventElapsedTime(&st->ms_total, ev[4], ev[8]);
+    cudaEventElapsedTime(&st->ms_ingest, ev[4], ev[5]);
+    cudaEventElapsedTime(&st->ms_gather, ev[5], ev[6]);
+    cudaEventElapsedTime(&st->ms_neighbour, ev[6], ev[7]);
+    cudaEventElapsedTime(&st->ms_select, ev[7], ev[8]);
+    st->ms_compare = tt.compare;
+    st->ms_table_clear = tt.table_clear;
+    st->ms_ingest_kernel = tt.ingest_kernel;
+    st->ms_bucket_build = st->ms_neighbour - tt.compare;
+    st->launches = tt.launches;
+    publish_result(ctx, uq, f, job.n, c2.n_selected);
+    return FQD_OK;
+}
 
-    ctx->res.U = U;
-    ctx->res.n_selected = c2.n_selected;
-    ctx->res.ufirst = (uint32_t *)ufirst.release();
-    ctx->res.ucount = (uint32_t *)ucount.release();
-    ctx->res.parent_full = (uint32_t *)parent_full.release();
-    ctx->res.selected = (uint8_t *)selected.release();
+// ---- sharded plan ------------------------------------------------------------------------------------
+//
+// `S` holds one entry per rank driven by this process: exactly one when `ex` is an NCCL
+// exchange (one process per GPU), all of them when ex == nullptr (virtual ranks, exchanged
+// with device copies).  Phases are written "for every local shard"; collectives sit between.
+
+struct Shard {
+    fqd_context *ctx = nullptr;
+    DeviceJob job;
+    uint32_t index_base = 0;
+    fqd_cluster_stats *st = nullptr;
+    Uniques local, owned, all;
+    Forest f;
+    StageTimes tt;
+    std::vector<uint32_t> send_cnt, recv_cnt;    // records per peer
+    uint32_t *send = nullptr, *recv = nullptr;
+    uint32_t n_recv = 0;
+    uint2 *pairs[2] = {nullptr, nullptr};
+    uint32_t n_pairs[2] = {0, 0};
+};
+
+int sync_all(std::vector<Shard> &S)
+{
+    for (auto &sh : S) {
+        FQD_CUDA(cudaSetDevice(sh.ctx->device));
+        FQD_CUDA(cudaStreamSynchronize(sh.ctx->stream));
+    }
+    return FQD_OK;
+}
+
+// every rank learns the n values of every rank
+int gather_host_u64(std::vector<Shard> &S, Exchange *ex, int world, int n,
+                    const std::vector<std::vector<uint64_t>> &mine, std::vector<uint64_t> &all)
+{
+    all.assign((size_t)world * n, 0);
+    if (!ex) {
+        for (int g = 0; g < world; g++)
+            for (int i = 0; i < n; i++) all[(size_t)g * n + i] = mine[g][i];
+        return FQD_OK;
+    }
+    fqd_context *ctx = S[0].ctx;
+    const size_t mark = arena_mark(ctx);
+    uint64_t *d_in, *d_out;
+    FQD_TRY(arena(ctx, n, &d_in));
+    FQD_TRY(arena(ctx, (size_t)world * n, &d_out));
+    FQD_CUDA(cudaMemcpyAsync(d_in, mine[0].data(), (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    FQD_TRY(ex->allgather(d_in, d_out, (size_t)n * 8, ctx->stream));
+    FQD_CUDA(cudaMemcpyAsync(all.data(), d_out, (size_t)world * n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    FQD_CUDA(cudaStreamSynchronize(ctx->stream));
+    arena_release(ctx, mark);
+    return FQD_OK;
+}
+
+// variable all-gather of one device array per rank into dst (same layout on every rank)
+int gather_device(std::vector<Shard> &S, Exchange *ex, int world, const std::vector<const void *> &src,
+                  const std::vector<void *> &dst, const std::vector<size_t> &bytes)
+{
+    std::vector<size_t> off(world + 1, 0);
+    for (int g = 0; g < world; g++) off[g + 1] = off[g] + bytes[g];
+    if (ex) return ex->allgatherv(src[0], dst[0], off.data(), bytes.data(), S[0].ctx->stream);
+    FQD_TRY(sync_all(S));
+    for (int r = 0; r < world; r++) {
+        FQD_CUDA(cudaSetDevice(S[r].ctx->device));
+        for (int g = 0; g < world; g++)
+            if (bytes[g])
+                FQD_CUDA(cudaMemcpyAsync(static_cast<char *>(dst[r]) + off[g], src[g], bytes[g],
+                                         cudaMemcpyDefault, S[r].ctx->stream));
+    }
+    return sync_all(S);
+}
+
+template <int K, int PW>
+int run_sharded_typed(std::vector<Shard> &S, Exchange *ex, int world, const Codec &codec,
+                      uint32_t unknown_out[8])
+{
+    constexpr int KW = K * PW, RW = slot_words(KW);
+    const int L = (int)S.size();               // shards driven by this process
+    auto rank_of = [&](int i) { return ex ? ex->rank : i; };
+    std::vector<cudaEvent_t> e0(L), e1(L);
+
+    // ---- phase 1: local dedupe ----
+    for (int i = 0; i < L; i++) {
+        Shard &sh = S[i];
+        FQD_CUDA(cudaSetDevice(sh.ctx->device));
+        sh.ctx->res = fqd_result{};
+        sh.st->key_bits = K; sh.st->key_words = KW;
+        FQD_CUDA(cudaEventCreate(&e0[i])); FQD_CUDA(cudaEventCreate(&e1[i]));
+        FQD_CUDA(cudaEventRecord(e0[i], sh.ctx->stream));
+        uint32_t unk[8] = {};
+        FQD_TRY(stage_dedupe<K, PW>(sh.ctx, sh.job, codec, sh.index_base, true, sh.st, unk, sh.local, sh.tt));
+        for (int k = 0; k < 8; k++) unknown_out[k] |= unk[k];
+        const uint32_t U = sh.local.U;
+        if (U) {
+            gather_kernel<K, PW><<<cdiv(U, 256), 256, 0, sh.ctx->stream>>>(
+                U, sh.ctx->scratch_table, sh.ctx->scratch_uslot, sh.local.ukey, sh.local.ucount,
+                sh.local.ufirst, nullptr, nullptr, nullptr);
+            sh.tt.launches++;
+        }
+        FQD_CUDA(cudaGetLastError());
+    }
+    // error / alphabet agreement across ranks: [bad_record, bad_char, unknown x8]
+    {
+        std::vector<std::vector<uint64_t>> mine(L, std::vector<uint64_t>(10));
+        for (int i = 0; i < L; i++) {
+            mine[i][0] = S[i].st->bad_record;
+            mine[i][1] = S[i].st->bad_char;
+            for (int k = 0; k < 8; k++) mine[i][2 + k] = unknown_out[k];
+        }
+        std::vector<uint64_t> all;
+        FQD_TRY(gather_host_u64(S, ex, world, 10, mine, all));
+        uint64_t bad = ~0ull, bad_char = 0;
+        bool any_unknown = false;
+        for (int g = 0; g < world; g++) {
+            if (all[(size_t)g * 10] < bad) { bad = all[(size_t)g * 10]; bad_char = all[(size_t)g * 10 + 1]; }
+            for (int k = 0; k < 8; k++) {
+                unknown_out[k] |= (uint32_t)all[(size_t)g * 10 + 2 + k];
+                any_unknown |= all[(size_t)g * 10 + 2 + k] != 0;
+            }
+        }
+        if (bad != ~0ull) {
+            for (auto &sh : S) { sh.st->bad_record = bad; sh.st->bad_char = (uint32_t)bad_char; }
+            set_error("Character %c outside of valid phred range ('%c' to '%c')", (int)bad_char,
+                      (int)S[0].job.phred_offset, 126);
+            return FQD_ERR_PHRED;
+        }
+        if (any_unknown) return RC_RETRY_ALPHABET;
+    }
+
+    // ---- phase 2: send every local unique to its owner ----
+    for (auto &sh : S) {
+        FQD_CUDA(cudaSetDevice(sh.ctx->device));
+        cudaStream_t s = sh.ctx->stream;
+        const uint32_t U = sh.local.U;
+        uint32_t *owner_cnt;
+        FQD_TRY(arena(sh.ctx, 2 * 64, &owner_cnt));
+        FQD_CUDA(cudaMemsetAsync(owner_cnt, 0, 2 * 64 * 4, s));
+        if (U) owner_count_kernel<K, PW><<<cdiv(U, 256), 256, 0, s>>>(U, sh.local.ukey, (uint32_t)world, owner_cnt);
+        sh.send_cnt.assign(world, 0);
+        FQD_CUDA(cudaMemcpyAsync(sh.send_cnt.data(), owner_cnt, world * 4, cudaMemcpyDeviceToHost, s));
+        FQD_CUDA(cudaStreamSynchronize(s));
+        std::vector<uint32_t> cursor(world, 0);
+        for (int g = 1; g < world; g++) cursor[g] = cursor[g - 1] + sh.send_cnt[g - 1];
+        FQD_CUDA(cudaMemcpyAsync(owner_cnt + 64, cursor.data(), world * 4, cudaMemcpyHostToDevice, s));
+        FQD_TRY(arena(sh.ctx, (size_t)std::max<uint32_t>(U, 1) * RW, &sh.send));
+        if (U) owner_scatter_kernel<K, PW><<<cdiv(U, 256), 256, 0, s>>>(U, sh.local.ukey, sh.local.ucount, sh.local.ufirst,
+                                                                       (uint32_t)world, owner_cnt + 64, sh.send);
+        FQD_CUDA(cudaGetLastError());
+        FQD_CUDA(cudaStreamSynchronize(s));   // `cursor` is host memory
+        sh.tt.launches += 2;
+    }
+    std::vector<uint64_t> cnt_matrix;   // [src][dst]
+    {
+        std::vector<std::vector<uint64_t>> mine(L, std::vector<uint64_t>(world));
+        for (int i = 0; i < L; i++) for (int g = 0; g < world; g++) mine[i][g] = S[i].send_cnt[g];
+        FQD_TRY(gather_host_u64(S, ex, world, world, mine, cnt_matrix));
+    }
+    for (int i = 0; i < L; i++) {
+        Shard &sh = S[i];
+        const int r = rank_of(i);
+        sh.recv_cnt.assign(world, 0);
+        sh.n_recv = 0;
+        for (int g = 0; g < world; g++) { sh.recv_cnt[g] = (uint32_t)cnt_matrix[(size_t)g * world + r]; sh.n_recv += sh.recv_cnt[g]; }
+        FQD_CUDA(cudaSetDevice(sh.ctx->device));
+        FQD_TRY(arena(sh.ctx, (size_t)std::max<uint32_t>(sh.n_recv, 1) * RW, &sh.recv));
+    }
+    if (ex) {
+        Shard &sh = S[0];
+        std::vector<size_t> so(world), sb(world), ro(world), rb(world);
+        size_t a = 0, b = 0;
+        for (int g = 0; g < world; g++) {
+            so[g] = a; sb[g] = (size_t)sh.send_cnt[g] * RW * 4; a += sb[g];
+            ro[g] = b; rb[g] = (size_t)sh.recv_cnt[g] * RW * 4; b += rb[g];
+        }
+        FQD_TRY(ex->alltoallv(sh.send, so.data(), sb.data(), sh.recv, ro.data(), rb.data(), sh.ctx->stream));
+    } else {
+        FQD_TRY(sync_all(S));
+        for (int r = 0; r < world; r++) {
+            FQD_CUDA(cudaSetDevice(S[r].ctx->device));
+            size_t roff = 0;
+            for (int g = 0; g < world; g++) {
+                size_t soff = 0;
+                for (int k = 0; k < r; k++) soff += (size_t)S[g].send_cnt[k] * RW * 4;
+                const size_t bytes = (size_t)S[g].send_cnt[r] * RW * 4;
+                if (bytes)
+                    FQD_CUDA(cudaMemcpyAsync(reinterpret_cast<char *>(S[r].recv) + roff,
+                                             reinterpret_cast<char *>(S[g].send) + soff, bytes,
+                                             cudaMemcpyDefault, S[r].ctx->stream));
+                roff += bytes;
+            }
+        }
+        FQD_TRY(sync_all(S));
+    }
+
+    // ---- phase 3: owners merge (sum of counts, min of first) ----
+    for (auto &sh : S) {
+        FQD_CUDA(cudaSetDevice(sh.ctx->device));
+        cudaStream_t s = sh.ctx->stream;
+        const uint64_t n = sh.n_recv;
+        const uint64_t capacity = std::max<uint64_t>(1024, n + (n >> 1) + 64);
+        uint32_t *table, *uslot, *kept;
+        FQD_TRY(arena(sh.ctx, capacity * RW, &table));
+        FQD_TRY(arena(sh.ctx, std::max<uint64_t>(n, 1), &uslot));
+        FQD_TRY(arena(sh.ctx, 4, &kept));
+        FQD_CUDA(cudaMemsetAsync(table, 0xFF, capacity * RW * 4, s));
+        FQD_CUDA(cudaMemsetAsync(kept, 0, 16, s));
+        FQD_CUDA(cudaMemsetAsync(&sh.ctx->d_ctr->n_unique, 0, 4, s));
+        TableRef tab{table, capacity, uslot, sh.ctx->d_ctr};
+        if (n) merge_insert_kernel<K, PW><<<cdiv(n, 256), 256, 0, s>>>((uint32_t)n, sh.recv, tab);
+        FQD_CUDA(cudaGetLastError());
+        FQD_TRY(fetch_counters(sh.ctx));
+        if (sh.ctx->h_ctr->table_full) { set_error("internal: merge table overflow"); return FQD_ERR_NOMEM; }
+        const uint32_t Um = sh.ctx->h_ctr->n_unique;
+        FQD_TRY(arena(sh.ctx, (size_t)std::max<uint32_t>(Um, 1) * KW, &sh.owned.ukey));
+        FQD_TRY(arena(sh.ctx, std::max<uint32_t>(Um, 1), &sh.owned.ucount));
+        FQD_TRY(arena(sh.ctx, std::max<uint32_t>(Um, 1), &sh.owned.ufirst));
+        if (Um) gather_nonzero_kernel<K, PW><<<cdiv(Um, 256), 256, 0, s>>>(Um, table, uslot, sh.owned.ukey,
+                                                                          sh.owned.ucount, sh.owned.ufirst, kept);
+        FQD_CUDA(cudaGetLastError());
+        uint32_t h_kept = 0;
+        FQD_CUDA(cudaMemcpyAsync(&h_kept, kept, 4, cudaMemcpyDeviceToHost, s));
+        FQD_CUDA(cudaStreamSynchronize(s));
+        sh.owned.U = h_kept;
+        sh.tt.launches += 2;
+    }
+
+    // ---- phase 4: replicate the merged unique set on every rank ----
+    std::vector<uint64_t> totals;
+    {
+        std::vector<std::vector<uint64_t>> mine(L, std::vector<uint64_t>(4));
+        for (int i = 0; i < L; i++) {
+            mine[i][0] = S[i].owned.U;
+            mine[i][1] = S[i].st->total_records;
+            mine[i][2] = S[i].st->discarded_records;
+            mine[i][3] = S[i].st->number_of_sequences;
+        }
+        FQD_TRY(gather_host_u64(S, ex, world, 4, mine, totals));
+    }
+    uint64_t U_total = 0, n_total = 0, n_disc = 0, n_seq = 0;
+    std::vector<size_t> Uo(world);
+    for (int g = 0; g < world; g++) {
+        Uo[g] = (size_t)totals[(size_t)g * 4];
+        U_total += Uo[g]; n_total += totals[(size_t)g * 4 + 1];
+        n_disc += totals[(size_t)g * 4 + 2]; n_seq += totals[(size_t)g * 4 + 3];
+    }
+    if (U_total > ENT_UID) { set_error("too many unique keys (%llu)", (unsigned long long)U_total); return FQD_ERR_UNSUPPORTED; }
+    for (auto &sh : S) {
+        FQD_CUDA(cudaSetDevice(sh.ctx->device));
+        sh.all.U = (uint32_t)U_total;
+        FQD_TRY(arena(sh.ctx, (size_t)std::max<uint64_t>(U_total, 1) * KW, &sh.all.ukey));
+        FQD_TRY(arena(sh.ctx, std::max<uint64_t>(U_total, 1), &sh.all.ucount));
+        FQD_TRY(arena(sh.ctx, std::max<uint64_t>(U_total, 1), &sh.all.ufirst));
+    }
+    for (int arr = 0; arr < 3; arr++) {
+        std::vector<const void *> src(L);
+        std::vector<void *> dst(L);
+        std::vector<size_t> bytes(world);
+        const size_t unit = arr == 0 ? (size_t)KW * 4 : 4;
+        for (int g = 0; g < world; g++) bytes[g] = Uo[g] * unit;
+        for (int i = 0; i < L; i++) {
+            src[i] = arr == 0 ? (void *)S[i].owned.ukey : arr == 1 ? (void *)S[i].owned.ucount : (void *)S[i].owned.ufirst;
+            dst[i] = arr == 0 ? (void *)S[i].all.ukey : arr == 1 ? (void *)S[i].all.ucount : (void *)S[i].all.ufirst;
+        }
+        FQD_TRY(gather_device(S, ex, world, src, dst, bytes));
+    }
+
+    // ---- phase 5: pigeonhole passes over the owned buckets ----
+    const uint32_t U = (uint32_t)U_total;
+    for (int i = 0; i < L; i++) {
+        Shard &sh = S[i];
+        FQD_CUDA(cudaSetDevice(sh.ctx->device));
+        cudaStream_t s = sh.ctx->stream;
+        FQD_TRY(stage_forest_alloc(sh.ctx, sh.job.method, U, sh.f));
+        if (U) {
+            init_forest_kernel<<<cdiv(U, 256), 256, 0, s>>>(U, sh.f.parent_full, sh.f.parent_one, sh.f.best);
+            sh.tt.launches++;
+        }
+        FQD_CUDA(cudaMemsetAsync(&sh.ctx->d_ctr->n_merges, 0, 4, s));
+        FQD_CUDA(cudaMemsetAsync(&sh.ctx->d_ctr->n_edges, 0, 8, s));
+        FQD_CUDA(cudaMemsetAsync(&sh.ctx->d_ctr->n_candidates, 0, 8, s));
+        FQD_TRY(stage_passes<K, PW>(sh.ctx, sh.job, codec, sh.all, sh.f, rank_of(i), world, sh.st, sh.tt));
+    }
+
+    // ---- phase 6: merge forests, flags and edge lists across ranks ----
+    const int method = S[0].job.method;
+    for (int which = 0; which < 2; which++) {
+        if (which == 1 && method != METHOD_DIRECTIONAL) break;
+        std::vector<std::vector<uint64_t>> mine(L, std::vector<uint64_t>(1));
+        for (int i = 0; i < L; i++) {
+            Shard &sh = S[i];
+            FQD_CUDA(cudaSetDevice(sh.ctx->device));
+            cudaStream_t s = sh.ctx->stream;
+            uint32_t *np;
+            FQD_TRY(arena(sh.ctx, std::max<uint32_t>(U, 1), &sh.pairs[which]));
+            FQD_TRY(arena(sh.ctx, 4, &np));
+            FQD_CUDA(cudaMemsetAsync(np, 0, 16, s));
+            uint32_t *parent = which == 0 ? sh.f.parent_full : sh.f.parent_one;
+            if (U) forest_pairs_kernel<<<cdiv(U, 256), 256, 0, s>>>(U, parent, sh.pairs[which], np);
+            FQD_CUDA(cudaGetLastError());
+            uint32_t h = 0;
+            FQD_CUDA(cudaMemcpyAsync(&h, np, 4, cudaMemcpyDeviceToHost, s));
+            FQD_CUDA(cudaStreamSynchronize(s));
+            sh.n_pairs[which] = h;
+            mine[i][0] = h;
+            sh.tt.launches++;
+        }
+        std::vector<uint64_t> all;
+        FQD_TRY(gather_host_u64(S, ex, world, 1, mine, all));
+        size_t total = 0;
+        std::vector<size_t> bytes(world);
+        for (int g = 0; g < world; g++) { bytes[g] = (size_t)all[g] * 8; total += (size_t)all[g]; }
+        std::vector<const void *> src(L);
+        std::vector<void *> dst(L);
+        for (int i = 0; i < L; i++) {
+            FQD_CUDA(cudaSetDevice(S[i].ctx->device));
+            uint2 *buf;
+            FQD_TRY(arena(S[i].ctx, std::max<size_t>(total, 1), &buf));
+            src[i] = S[i].pairs[which];
+            dst[i] = buf;
+        }
+        FQD_TRY(gather_device(S, ex, world, src, dst, bytes));
+        for (int i = 0; i < L; i++) {
+            FQD_CUDA(cudaSetDevice(S[i].ctx->device));
+            uint32_t *parent = which == 0 ? S[i].f.parent_full : S[i].f.parent_one;
+            if (total) apply_pairs_kernel<<<cdiv(total, 256), 256, 0, S[i].ctx->stream>>>((uint32_t)total, (const uint2 *)dst[i], parent);
+            FQD_CUDA(cudaGetLastError());
+            S[i].tt.launches++;
+        }
+    }
+    if (method == METHOD_DIRECTIONAL && U) {
+        for (int which = 0; which < 2; which++) {
+            if (ex) {
+                Shard &sh = S[0];
+                FQD_TRY(ex->allreduce_max_u8(which ? sh.f.dead : sh.f.dominated, U, sh.ctx->stream));
+            } else if (world > 1) {
+                FQD_TRY(sync_all(S));
+                uint8_t *acc = which ? S[0].f.dead : S[0].f.dominated;   // arena blocks are 256-byte padded
+                const size_t n4 = ((size_t)U + 3) / 4;
+                FQD_CUDA(cudaSetDevice(S[0].ctx->device));
+                uint32_t *tmp;
+                FQD_TRY(arena(S[0].ctx, n4, &tmp));
+                for (int g = 1; g < world; g++) {
+                    FQD_CUDA(cudaMemcpyAsync(tmp, which ? S[g].f.dead : S[g].f.dominated, U, cudaMemcpyDefault, S[0].ctx->stream));
+                    max_u8_kernel<<<cdiv(n4, 256), 256, 0, S[0].ctx->stream>>>(n4, (uint32_t *)acc, tmp);
+                }
+                FQD_TRY(sync_all(S));
+                for (int g = 1; g < world; g++) {
+                    FQD_CUDA(cudaSetDevice(S[g].ctx->device));
+                    FQD_CUDA(cudaMemcpyAsync(which ? S[g].f.dead : S[g].f.dominated, acc, U, cudaMemcpyDefault, S[g].ctx->stream));
+                }
+                FQD_TRY(sync_all(S));
+            }
+        }
+    }
+    if (method == METHOD_ADJACENCY) {
+        std::vector<std::vector<uint64_t>> mine(L, std::vector<uint64_t>(1));
+        for (int i = 0; i < L; i++) {
+            FQD_CUDA(cudaSetDevice(S[i].ctx->device));
+            FQD_TRY(fetch_counters(S[i].ctx));
+            mine[i][0] = S[i].ctx->h_ctr->n_edges;
+        }
+        std::vector<uint64_t> all;
+        FQD_TRY(gather_host_u64(S, ex, world, 1, mine, all));
+        size_t total = 0;
+        std::vector<size_t> bytes(world);
+        for (int g = 0; g < world; g++) { bytes[g] = (size_t)all[g] * 8; total += (size_t)all[g]; }
+        std::vector<const void *> src(L);
+        std::vector<void *> dst(L);
+        for (int i = 0; i < L; i++) {
+            FQD_CUDA(cudaSetDevice(S[i].ctx->device));
+            uint2 *buf;
+            FQD_TRY(arena(S[i].ctx, std::max<size_t>(total, 1), &buf));
+            src[i] = S[i].f.edges;
+            dst[i] = buf;
+        }
+        FQD_TRY(gather_device(S, ex, world, src, dst, bytes));
+        for (int i = 0; i < L; i++) { S[i].f.edges = (uint2 *)dst[i]; S[i].f.n_edges = total; S[i].f.edge_cap = total; }
+    }
+
+    // ---- phase 7: every rank finishes the dissection; each writes the bitmap of its own records ----
+    uint64_t cand_total = 0;
+    {
+        std::vector<std::vector<uint64_t>> mine(L, std::vector<uint64_t>(1));
+        for (int i = 0; i < L; i++) {
+            FQD_CUDA(cudaSetDevice(S[i].ctx->device));
+            FQD_TRY(fetch_counters(S[i].ctx));
+            mine[i][0] = S[i].ctx->h_ctr->n_candidates;
+        }
+        std::vector<uint64_t> all;
+        FQD_TRY(gather_host_u64(S, ex, world, 1, mine, all));
+        for (int g = 0; g < world; g++) cand_total += all[g];
+    }
+    for (int i = 0; i < L; i++) {
+        Shard &sh = S[i];
+        FQD_CUDA(cudaSetDevice(sh.ctx->device));
+        cudaStream_t s = sh.ctx->stream;
+        FQD_CUDA(cudaMemsetAsync(&sh.ctx->d_ctr->n_selected, 0, 4, s));
+        FQD_TRY(stage_select<K, PW>(sh.ctx, sh.job, codec, sh.all, sh.f, sh.index_base, (uint32_t)sh.job.n, sh.tt));
+        uint32_t *roots;
+        FQD_TRY(arena(sh.ctx, 4, &roots));
+        FQD_CUDA(cudaMemsetAsync(roots, 0, 16, s));
+        if (U) count_roots_kernel<<<cdiv(U, 256), 256, 0, s>>>(U, sh.f.parent_full, roots);
+        FQD_CUDA(cudaGetLastError());
+        uint32_t h_roots = 0;
+        FQD_CUDA(cudaMemcpyAsync(&h_roots, roots, 4, cudaMemcpyDeviceToHost, s));
+        FQD_TRY(fetch_counters(sh.ctx));
+        FQD_CUDA(cudaEventRecord(e1[i], s));
+        FQD_CUDA(cudaStreamSynchronize(s));
+        fqd_cluster_stats *st = sh.st;
+        st->total_records = n_total;
+        st->discarded_records = n_disc;
+        st->number_of_sequences = n_seq;
+        st->number_of_uniques = U_total;
+        st->number_of_clusters = h_roots;
+        st->number_selected = sh.ctx->h_ctr->n_selected;
+        st->candidate_pairs = cand_total;
+        cudaEventElapsedTime(&st->ms_total, e0[i], e1[i]);
+        st->ms_ingest = sh.tt.ingest;
+        st->ms_ingest_kernel = sh.tt.ingest_kernel;
+        st->ms_table_clear = sh.tt.table_clear;
+        st->ms_compare = sh.tt.compare;
+        st->launches = sh.tt.launches + 1;
+        cudaEventDestroy(e0[i]); cudaEventDestroy(e1[i]);
+        publish_result(sh.ctx, sh.all, sh.f, n_total, st->number_selected);
+    }
     return FQD_OK;
 }
 
@@ -347,22 +846,46 @@ uint32_t max_supported_length(int bits)
     return best;
 }
 
-int run_pipeline(fqd_context *ctx, const DeviceJob &job, const Codec &codec,
-                 fqd_cluster_stats *stats, uint32_t unknown_out[8])
+static int pick_pw(int bits, uint32_t max_len)
 {
-    const int bits = codec.bits;
-    const uint32_t pw_needed = std::max(1u, (job.max_len + 31u) / 32u);
-    // smallest instantiated PW that fits
+    const uint32_t pw_needed = std::max(1u, (max_len + 31u) / 32u);
     int best_pw = 0;
 #define X(K_, PW_) if (bits == K_ && (uint32_t)PW_ >= pw_needed && (best_pw == 0 || PW_ < best_pw)) best_pw = PW_;
     FQD_INSTANCES(X)
 #undef X
-    if (!best_pw) {
+    if (!best_pw)
         set_error("keys of %u symbols over a %d-bit alphabet exceed what this build packs "
-                  "(max %u symbols)", job.max_len, bits, max_supported_length(bits));
-        return FQD_ERR_UNSUPPORTED;
-    }
+                  "(max %u symbols)", max_len, bits, max_supported_length(bits));
+    return best_pw;
+}
+
+int run_pipeline(fqd_context *ctx, const DeviceJob &job, const Codec &codec,
+                 fqd_cluster_stats *stats, uint32_t unknown_out[8])
+{
+    const int bits = codec.bits;
+    const int best_pw = pick_pw(bits, job.max_len);
+    if (!best_pw) return FQD_ERR_UNSUPPORTED;
 #define X(K_, PW_) if (bits == K_ && best_pw == PW_) return run_typed<K_, PW_>(ctx, job, codec, stats, unknown_out);
+    FQD_INSTANCES(X)
+#undef X
+    return FQD_ERR_UNSUPPORTED;
+}
+
+int run_sharded(fqd_context **ctxs, const DeviceJob *jobs, const uint32_t *index_base,
+                fqd_cluster_stats **stats, int n_local, Exchange *ex, int world, const Codec &codec,
+                uint32_t max_len, uint32_t unknown_out[8])
+{
+    std::vector<Shard> S(n_local);
+    for (int i = 0; i < n_local; i++) {
+        S[i].ctx = ctxs[i];
+        S[i].job = jobs[i];
+        S[i].index_base = index_base[i];
+        S[i].st = stats[i];
+    }
+    const int bits = codec.bits;
+    const int best_pw = pick_pw(bits, max_len);
+    if (!best_pw) return FQD_ERR_UNSUPPORTED;
+#define X(K_, PW_) if (bits == K_ && best_pw == PW_) return run_sharded_typed<K_, PW_>(S, ex, world, codec, unknown_out);
     FQD_INSTANCES(X)
 #undef X
     return FQD_ERR_UNSUPPORTED;

@@ -97,6 +97,15 @@ __device__ __forceinline__ void load_key(const uint32_t *__restrict__ ukey, uint
 
 // ---- ingest: filter + pack + exact dedupe ----------------------------------------------
 
+// The exact-dedupe table in HBM.
+struct TableRef {
+    uint32_t *table;           // open addressing: {key[KW], count, state} per slot;
+                               // state = EMPTY | LOCKED | smallest record index seen so far
+    uint64_t capacity;
+    uint32_t *uslot;           // claimed slots in claim order (= unique ids)
+    DevCounters *ctr;
+};
+
 struct IngestParams {
     uint64_t n;
     const uint8_t *keys;
@@ -114,12 +123,12 @@ struct IngestParams {
     double max_err;
     uint32_t phred_offset;
     uint32_t pad_code;
-    uint32_t *table;           // open addressing: {key[KW], count, state} per slot;
-                               // state = EMPTY | LOCKED | smallest record index seen so far
-    uint64_t capacity;
-    uint32_t *uslot;           // claimed slots in claim order (= unique ids)
+    TableRef tab;
     uint32_t *keepmask;        // bit per record: passed the filter
     const uint32_t *weights;   // optional multiplicity per record
+    uint32_t index_base;       // global index of record 0 of this shard
+    int sharded;               // 1: filtered records are inserted with weight 0 (their first
+                               //    index must reach the key's owner rank), no fix-up phase
     DevCounters *ctr;
     Codec codec;
 };
@@ -171,14 +180,9 @@ __device__ __forceinline__ void load_slot(const uint32_t *rec, uint32_t (&w)[RW]
 // word keeps the smallest record index, which is rarely lowered because records arrive
 // roughly in index order.
 template <int K, int PW>
-__device__ __forceinline__ void table_insert(const IngestParams &P, const Key<K, PW> &key,
-                                             uint32_t t)
+__device__ __forceinline__ void table_insert(const TableRef &P, const Key<K, PW> &key,
+                                             uint32_t t, uint32_t weight)
 {
-    uint32_t weight = 1u;
-    if (P.weights) {
-        weight = P.weights[t];
-        atomicAdd(&P.ctr->sum_weights, (unsigned long long)weight);
-    }
     constexpr int KW = K * PW, RW = slot_words(KW);
     const uint64_t h = hash_key(key);
     uint64_t s = __umul64hi(h, P.capacity);
@@ -224,7 +228,7 @@ __device__ __forceinline__ void table_insert(const IngestParams &P, const Key<K,
 // Records that failed the filter still define "first occurrence" (pass 2 of the reference
 // does not re-apply the filter, __init__.py:201-206): lower `first` of an existing key.
 template <int K, int PW>
-__device__ __forceinline__ void table_touch_first(const IngestParams &P, const Key<K, PW> &key,
+__device__ __forceinline__ void table_touch_first(const TableRef &P, const Key<K, PW> &key,
                                                   uint32_t t)
 {
     constexpr int KW = K * PW, RW = slot_words(KW);
@@ -299,7 +303,7 @@ static __global__ void __launch_bounds__(256) ingest_kernel(const __grid_constan
                 const uint32_t c = q[i];
                 const uint32_t score = (c - P.phred_offset) & 0xFFu;   // uint8 wrap (:62)
                 if (score > max_score) {
-                    atomicMin(&P.ctr->phred_err, (unsigned long long)((t << 8) | c));
+                    atomicMin(&P.ctr->phred_err, (unsigned long long)(((t + P.index_base) << 8) | c));
                     bad = true;
                     break;
                 }
@@ -345,7 +349,8 @@ static __global__ void __launch_bounds__(256) ingest_kernel(const __grid_constan
     if (P.filter_on && P.phase == 0 && !keep) {
         aggregated_inc(&P.ctr->n_discarded);
     }
-    if (!keep) return;   // phase 0: filtered out; phase 1: record was kept, nothing to fix
+    // phase 0: a filtered record stops here (unless sharded); phase 1: `keep` means "was filtered"
+    if (!keep && !(P.sharded && P.phase == 0)) return;
     if (klen > P.max_len) klen = P.max_len;
     Key<K, PW> key;
     uint32_t badbyte = 0;
@@ -357,8 +362,15 @@ static __global__ void __launch_bounds__(256) ingest_kernel(const __grid_constan
         }
         return;
     }
-    if (P.phase == 0) table_insert<K, PW>(P, key, (uint32_t)t);
-    else table_touch_first<K, PW>(P, key, (uint32_t)t);
+    const uint32_t tg = P.index_base + (uint32_t)t;
+    if (P.phase == 0) {
+        // a filtered record only gets here in sharded mode: weight 0 carries its first index
+        const uint32_t weight = keep ? (P.weights ? P.weights[t] : 1u) : 0u;
+        if (P.weights && keep) atomicAdd(&P.ctr->sum_weights, (unsigned long long)weight);
+        table_insert<K, PW>(P.tab, key, tg, weight);
+    } else {
+        table_touch_first<K, PW>(P.tab, key, tg);
+    }
 }
 
 // min / max of the key lengths (decides PW and whether PAD is needed)
@@ -408,6 +420,16 @@ static __global__ void __launch_bounds__(256) gather_kernel(uint32_t U, const ui
     for (int i = 0; i < KW; i++) ukey[(size_t)u * KW + i] = w[i];
     ucount[u] = w[KW];
     ufirst[u] = w[KW + 1];
+    if (parent_a) parent_a[u] = u;
+    if (parent_b) parent_b[u] = u;
+    if (best) best[u] = u;
+}
+
+static __global__ void __launch_bounds__(256) init_forest_kernel(uint32_t U, uint32_t *parent_a,
+                                                                 uint32_t *parent_b, uint32_t *best)
+{
+    const uint32_t u = blockIdx.x * 256u + threadIdx.x;
+    if (u >= U) return;
     parent_a[u] = u;
     if (parent_b) parent_b[u] = u;
     if (best) best[u] = u;
@@ -454,6 +476,7 @@ struct PassParams {
     int d, edit, varlen, method;
     uint32_t max_len, pad_code;
     int pass_j, V;
+    int my_rank, world;     // buckets are owned by rank (sig >> 32) % world
     uint32_t nb_mask;
     uint32_t *cnt;          // NB+1 counters -> exclusive offsets after the scan
     uint32_t *rank;         // U*V
@@ -516,7 +539,8 @@ static __global__ void __launch_bounds__(256) sig_count_kernel(const __grid_cons
         uint64_t sig;
         bool build;
         uint32_t r = RANK_INVALID;
-        if (pass_variant<K, PW>(key, len, P, v, sig, build))
+        if (pass_variant<K, PW>(key, len, P, v, sig, build) &&
+            (P.world <= 1 || (uint32_t)(sig >> 32) % (uint32_t)P.world == (uint32_t)P.my_rank))
             r = atomicAdd(P.cnt + ((uint32_t)sig & P.nb_mask), 1u);
         P.rank[(size_t)u * P.V + v] = r;
     }
@@ -633,6 +657,7 @@ static __global__ void __launch_bounds__(256) scatter_fat_kernel(const __grid_co
     load_key<K, PW>(P.ukey, u, key);
     const uint32_t len = P.varlen ? key_length(key, P.pad_code, P.max_len) : P.max_len;
     const uint32_t r = P.rank[u];
+    if (r == RANK_INVALID) return;   // bucket owned by another rank
     uint64_t sig;
     bool build;
     pass_variant<K, PW>(key, len, P, 0, sig, build);
@@ -797,7 +822,8 @@ struct SelectParams {
     const uint2 *edges;
     unsigned long long n_edges;
     uint32_t round;
-    uint32_t *bitmap;
+    uint32_t *bitmap;        // bits for records [bitmap_base, bitmap_base + bitmap_n) only
+    uint32_t bitmap_base, bitmap_n;
     uint32_t *minfirst;
     int method;
     DevCounters *ctr;
@@ -848,8 +874,8 @@ static __global__ void __launch_bounds__(256) select_kernel(const __grid_constan
         }
         P.selected[u] = sel ? 1 : 0;
         if (sel && P.bitmap) {
-            const uint32_t f = P.ufirst[u];
-            atomicOr(P.bitmap + (f >> 5), 1u << (f & 31));
+            const uint32_t f = P.ufirst[u] - P.bitmap_base;   // wraps for records of earlier shards
+            if (f < P.bitmap_n) atomicOr(P.bitmap + (f >> 5), 1u << (f & 31));
         }
     }
     const uint32_t b = __ballot_sync(0xFFFFFFFFu, sel);
@@ -890,6 +916,155 @@ static __global__ void __launch_bounds__(256) label_min_kernel(const __grid_cons
     const uint32_t r = uf_find(P.parent_full, u);
     P.root[u] = r;
     atomicMin(P.minfirst + r, P.ufirst[u]);
+}
+
+// ---- sharding across GPUs (DESIGN.md "Multi-GPU") ----------------------------------------------
+//
+// Records are split contiguously over the ranks.  Each rank dedupes its shard, sends every
+// local unique {key, count, first} to the key's owner rank (hash % world), the owners merge
+// them (sum of counts, min of first), the merged tables are all-gathered so every rank holds
+// the whole unique set, and each rank then runs the pigeonhole passes for the buckets it
+// owns.  Spanning-forest pairs and flags are exchanged at the end.
+
+__device__ __forceinline__ uint32_t key_owner(uint64_t h, uint32_t world)
+{
+    return (uint32_t)((h >> 17) % world);   // bits disjoint from the slot index (mulhi of h)
+}
+
+// counts per owner (block-local histogram first; world <= 64)
+template <int K, int PW>
+static __global__ void __launch_bounds__(256) owner_count_kernel(uint32_t U, const uint32_t *__restrict__ ukey,
+                                                                 uint32_t world, uint32_t *owner_cnt)
+{
+    __shared__ uint32_t h[64];
+    if (threadIdx.x < 64) h[threadIdx.x] = 0;
+    __syncthreads();
+    const uint32_t u = blockIdx.x * 256u + threadIdx.x;
+    if (u < U) {
+        Key<K, PW> key;
+        load_key<K, PW>(ukey, u, key);
+        atomicAdd(&h[key_owner(hash_key(key), world)], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x < world && h[threadIdx.x]) atomicAdd(owner_cnt + threadIdx.x, h[threadIdx.x]);
+}
+
+// send buffer grouped by owner: records of slot_words(KW) words {key, count, first}
+template <int K, int PW>
+static __global__ void __launch_bounds__(256) owner_scatter_kernel(uint32_t U, const uint32_t *__restrict__ ukey,
+                                                                   const uint32_t *__restrict__ ucount,
+                                                                   const uint32_t *__restrict__ ufirst,
+                                                                   uint32_t world, uint32_t *cursor /* starts at the owner offsets */,
+                                                                   uint32_t *send)
+{
+    constexpr int KW = K * PW, RW = slot_words(KW);
+    const uint32_t u = blockIdx.x * 256u + threadIdx.x;
+    if (u >= U) return;
+    Key<K, PW> key;
+    load_key<K, PW>(ukey, u, key);
+    const uint32_t o = key_owner(hash_key(key), world);
+    // one atomic per (warp, owner)
+    const uint32_t peers = __match_any_sync(__activemask(), o);
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t leader = __ffs(peers) - 1;
+    uint32_t base = 0;
+    if (lane == leader) base = atomicAdd(cursor + o, (uint32_t)__popc(peers));
+    base = __shfl_sync(peers, base, leader);
+    const uint32_t pos = base + __popc(peers & ((1u << lane) - 1u));
+    uint32_t e[RW];
+#pragma unroll
+    for (int i = 0; i < RW; i++) e[i] = 0;
+#pragma unroll
+    for (int i = 0; i < KW; i++) e[i] = key.w[i];
+    e[KW] = ucount[u];
+    e[KW + 1] = ufirst[u];
+    uint4 *dst = reinterpret_cast<uint4 *>(send + (size_t)pos * RW);
+#pragma unroll
+    for (int c = 0; c < RW / 4; c++) dst[c] = make_uint4(e[4 * c], e[4 * c + 1], e[4 * c + 2], e[4 * c + 3]);
+}
+
+// owner side: merge the received records (sum of counts, min of first)
+template <int K, int PW>
+static __global__ void __launch_bounds__(256) merge_insert_kernel(uint32_t n, const uint32_t *__restrict__ recs,
+                                                                  const __grid_constant__ TableRef tab)
+{
+    constexpr int KW = K * PW, RW = slot_words(KW);
+    const uint32_t i = blockIdx.x * 256u + threadIdx.x;
+    if (i >= n) return;
+    const uint4 *src = reinterpret_cast<const uint4 *>(recs + (size_t)i * RW);
+    uint32_t e[RW];
+#pragma unroll
+    for (int c = 0; c < RW / 4; c++) {
+        const uint4 v = __ldg(src + c);
+        e[4 * c] = v.x; e[4 * c + 1] = v.y; e[4 * c + 2] = v.z; e[4 * c + 3] = v.w;
+    }
+    Key<K, PW> key;
+#pragma unroll
+    for (int j = 0; j < KW; j++) key.w[j] = e[j];
+    table_insert<K, PW>(tab, key, e[KW + 1], e[KW]);
+}
+
+// gather that drops keys whose every record was filtered out (count 0)
+template <int K, int PW>
+static __global__ void __launch_bounds__(256) gather_nonzero_kernel(uint32_t U, const uint32_t *__restrict__ table,
+                                                                    const uint32_t *__restrict__ uslot,
+                                                                    uint32_t *__restrict__ ukey,
+                                                                    uint32_t *__restrict__ ucount,
+                                                                    uint32_t *__restrict__ ufirst,
+                                                                    uint32_t *kept)
+{
+    constexpr int KW = K * PW, RW = slot_words(KW);
+    const uint32_t u = blockIdx.x * 256u + threadIdx.x;
+    if (u >= U) return;
+    const uint4 *rec = reinterpret_cast<const uint4 *>(table + (size_t)uslot[u] * RW);
+    uint32_t w[RW];
+#pragma unroll
+    for (int c = 0; c < RW / 4; c++) {
+        const uint4 v = __ldcs(rec + c);
+        w[4 * c] = v.x; w[4 * c + 1] = v.y; w[4 * c + 2] = v.z; w[4 * c + 3] = v.w;
+    }
+    if (w[KW] == 0) return;
+    const uint32_t pos = aggregated_inc(kept);
+#pragma unroll
+    for (int i = 0; i < KW; i++) ukey[(size_t)pos * KW + i] = w[i];
+    ucount[pos] = w[KW];
+    ufirst[pos] = w[KW + 1];
+}
+
+// spanning-forest pairs (u, root(u)) of one rank's forest, to be applied on every rank
+static __global__ void __launch_bounds__(256) forest_pairs_kernel(uint32_t U, uint32_t *parent, uint2 *pairs,
+                                                                  uint32_t *n_pairs)
+{
+    const uint32_t u = blockIdx.x * 256u + threadIdx.x;
+    if (u >= U) return;
+    const uint32_t r = uf_find(parent, u);
+    if (r == u) return;
+    pairs[aggregated_inc(n_pairs)] = make_uint2(u, r);
+}
+
+static __global__ void __launch_bounds__(256) apply_pairs_kernel(uint32_t n, const uint2 *__restrict__ pairs,
+                                                                 uint32_t *parent)
+{
+    const uint32_t i = blockIdx.x * 256u + threadIdx.x;
+    if (i >= n) return;
+    const uint2 p = pairs[i];
+    uf_union(parent, p.x, p.y);
+}
+
+static __global__ void __launch_bounds__(256) max_u8_kernel(size_t n4, uint32_t *__restrict__ dst,
+                                                            const uint32_t *__restrict__ src)
+{
+    const size_t i = (size_t)blockIdx.x * 256u + threadIdx.x;
+    if (i < n4) dst[i] = __vmaxu4(dst[i], src[i]);
+}
+
+static __global__ void __launch_bounds__(256) count_roots_kernel(uint32_t U, const uint32_t *__restrict__ parent,
+                                                                 uint32_t *n_roots)
+{
+    const uint32_t u = blockIdx.x * 256u + threadIdx.x;
+    const bool root = u < U && parent[u] == u;
+    const uint32_t b = __ballot_sync(0xFFFFFFFFu, root);
+    if ((threadIdx.x & 31) == 0 && b) atomicAdd(n_roots, (uint32_t)__popc(b));
 }
 
 // ---- function-level kernels (batched _fastq / _distance entry points) -------------------

@@ -150,6 +150,28 @@ int fqd_cluster_fetch(fqd_context *ctx, uint64_t *first, uint32_t *count, uint64
 int fqd_cluster_fetch_selected(fqd_context *ctx, uint64_t *indices);
 
 /* ------------------------------------------------------------------------------------
+ * The same job sharded over the GPUs of one box (BASELINE.json config 5).  Records are split
+ * contiguously over `world` ranks; rank r passes its own records and the global index of its
+ * first record.  Exchange steps (NCCL over NVLink): all-to-all of the locally deduplicated
+ * keys to their owner rank, all-gather of the merged unique set, all-gather of the
+ * spanning-forest pairs / flags found by each rank.  Every rank ends with the complete
+ * per-unique result (fqd_cluster_fetch) and the keep bitmap of ITS OWN records.
+ * ------------------------------------------------------------------------------------ */
+typedef struct fqd_comm fqd_comm;
+/* rank 0 creates the id and hands the 128 bytes to the other ranks by any means */
+int fqd_nccl_unique_id(uint8_t id[128]);
+int fqd_comm_create(fqd_context *ctx, int rank, int world, const uint8_t id[128], fqd_comm **out);
+void fqd_comm_destroy(fqd_comm *comm);
+int fqd_cluster_sharded(fqd_context *ctx, fqd_comm *comm, const fqd_cluster_job *local_job,
+                        uint64_t index_base, fqd_cluster_stats *stats, uint32_t *keep_bitmap);
+/* All `world` ranks driven by one process (one context each; contexts may share a GPU):
+ * the exchanges become device-to-device copies.  jobs/index_bases/stats/keep_bitmaps have
+ * `world` entries. */
+int fqd_cluster_sharded_local(fqd_context **ctxs, int world, const fqd_cluster_job *jobs,
+                              const uint64_t *index_bases, fqd_cluster_stats *stats,
+                              uint32_t **keep_bitmaps);
+
+/* ------------------------------------------------------------------------------------
  * Function-level entry points mirroring the reference's C extensions one to one.
  * ------------------------------------------------------------------------------------ */
 
