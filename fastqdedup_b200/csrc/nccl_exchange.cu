@@ -74,8 +74,11 @@ int load_api()
 
 struct NcclExchange : Exchange {
     ncclComm_t comm = nullptr;
+    void *scratch = nullptr;      // staging of the padded all-gather (grown on demand, kept)
+    size_t scratch_cap = 0;
     ~NcclExchange() override
     {
+        if (scratch) cudaFree(scratch);
         if (comm) g_api.CommDestroy(comm);
     }
     int allgather(const void *send, void *recv, size_t bytes, cudaStream_t s) override
@@ -86,13 +89,26 @@ struct NcclExchange : Exchange {
     int allgatherv(const void *send, void *recv, const size_t *off, const size_t *bytes,
                    cudaStream_t s) override
     {
-        // one broadcast per root inside a group: every rank receives every part in place
-        FQD_NCCL(g_api.GroupStart());
-        for (int g = 0; g < world; g++) {
-            const void *src = g == rank ? send : static_cast<const char *>(recv) + off[g];
-            FQD_NCCL(g_api.Broadcast(src, static_cast<char *>(recv) + off[g], bytes[g], ncclUint8, g, comm, s));
+        // Parts are hash-balanced, so pad them to the largest and use the real all-gather
+        // (ring / NVLS tuned) instead of `world` broadcasts; then compact with local copies.
+        size_t mx = 0, total = 0;
+        for (int g = 0; g < world; g++) { mx = bytes[g] > mx ? bytes[g] : mx; total += bytes[g]; }
+        if (!mx) return FQD_OK;
+        mx = (mx + 255) & ~(size_t)255;
+        if (scratch_cap < mx * (size_t)(world + 1)) {
+            if (scratch) cudaFree(scratch);
+            scratch = nullptr;
+            scratch_cap = mx * (size_t)(world + 1) + (mx * (size_t)(world + 1)) / 4;
+            FQD_CUDA(cudaMalloc(&scratch, scratch_cap));
         }
-        FQD_NCCL(g_api.GroupEnd());
+        char *stage_in = static_cast<char *>(scratch);
+        char *stage_out = stage_in + mx;
+        if (bytes[rank]) FQD_CUDA(cudaMemcpyAsync(stage_in, send, bytes[rank], cudaMemcpyDeviceToDevice, s));
+        FQD_NCCL(g_api.AllGather(stage_in, stage_out, mx, ncclUint8, comm, s));
+        for (int g = 0; g < world; g++)
+            if (bytes[g])
+                FQD_CUDA(cudaMemcpyAsync(static_cast<char *>(recv) + off[g], stage_out + (size_t)g * mx, bytes[g],
+                                         cudaMemcpyDeviceToDevice, s));
         return FQD_OK;
     }
     int alltoallv(const void *send, const size_t *send_off, const size_t *send_bytes, void *recv,

@@ -1,7 +1,10 @@
 // pipeline.cu -- launch plans of the clustering job: one B200 (run_pipeline) and sharded over
 // several ranks (run_sharded).  Kernels are in pipeline.cuh; DESIGN.md has the data layout and
 // the per-kernel rooflines.
+#include <stdlib.h>
+
 #include <algorithm>
+#include <chrono>
 #include <vector>
 
 #include "common.h"
@@ -281,7 +284,7 @@ int stage_passes(fqd_context *ctx, const DeviceJob &job, const Codec &codec, con
 
 template <int K, int PW>
 int stage_select(fqd_context *ctx, const DeviceJob &job, const Codec &codec, const Uniques &uq,
-                 Forest &f, uint32_t bitmap_base, uint32_t bitmap_n, StageTimes &tt)
+                 Forest &f, uint32_t bitmap_base, uint32_t bitmap_n, StageTimes &tt, bool own_only = false)
 {
     cudaStream_t s = ctx->stream;
     const uint32_t U = uq.U;
@@ -293,6 +296,7 @@ int stage_select(fqd_context *ctx, const DeviceJob &job, const Codec &codec, con
     sp.selected = f.selected;
     sp.method = job.method; sp.ctr = ctx->d_ctr;
     sp.bitmap = job.bitmap; sp.bitmap_base = bitmap_base; sp.bitmap_n = bitmap_n;
+    sp.own_only = own_only ? 1 : 0;
     for (int i = 0; i < 256; i++) sp.rank_of_code[i] = codec.rank[i];
     if (job.bitmap) FQD_CUDA(cudaMemsetAsync(job.bitmap, 0, (size_t)cdiv(std::max<uint32_t>(bitmap_n, 1), 32) * 4, s));
     if (!U) return FQD_OK;
@@ -473,6 +477,17 @@ int run_sharded_typed(std::vector<Shard> &S, Exchange *ex, int world, const Code
     const int L = (int)S.size();               // shards driven by this process
     auto rank_of = [&](int i) { return ex ? ex->rank : i; };
     std::vector<cudaEvent_t> e0(L), e1(L);
+    // FQD_TRACE=1: host wall-clock per phase (every phase ends synchronised)
+    const bool trace = getenv("FQD_TRACE") && rank_of(0) == 0;
+    auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    double t_prev = now();
+    auto lap = [&](const char *what) {
+        if (!trace) return;
+        for (auto &sh : S) { cudaSetDevice(sh.ctx->device); cudaStreamSynchronize(sh.ctx->stream); }
+        const double t = now();
+        fprintf(stderr, "[fqd trace] %-28s %8.3f ms\n", what, t - t_prev);
+        t_prev = t;
+    };
 
     // ---- phase 1: local dedupe ----
     for (int i = 0; i < L; i++) {
@@ -494,6 +509,7 @@ int run_sharded_typed(std::vector<Shard> &S, Exchange *ex, int world, const Code
         }
         FQD_CUDA(cudaGetLastError());
     }
+    lap("local dedupe + gather");
     // error / alphabet agreement across ranks: [bad_record, bad_char, unknown x8]
     {
         std::vector<std::vector<uint64_t>> mine(L, std::vector<uint64_t>(10));
@@ -522,6 +538,7 @@ int run_sharded_typed(std::vector<Shard> &S, Exchange *ex, int world, const Code
         if (any_unknown) return RC_RETRY_ALPHABET;
     }
 
+    lap("agreement");
     // ---- phase 2: send every local unique to its owner ----
     for (auto &sh : S) {
         FQD_CUDA(cudaSetDevice(sh.ctx->device));
@@ -544,6 +561,7 @@ int run_sharded_typed(std::vector<Shard> &S, Exchange *ex, int world, const Code
         FQD_CUDA(cudaStreamSynchronize(s));   // `cursor` is host memory
         sh.tt.launches += 2;
     }
+    lap("owner partition");
     std::vector<uint64_t> cnt_matrix;   // [src][dst]
     {
         std::vector<std::vector<uint64_t>> mine(L, std::vector<uint64_t>(world));
@@ -587,6 +605,7 @@ int run_sharded_typed(std::vector<Shard> &S, Exchange *ex, int world, const Code
         FQD_TRY(sync_all(S));
     }
 
+    lap("all-to-all");
     // ---- phase 3: owners merge (sum of counts, min of first) ----
     for (auto &sh : S) {
         FQD_CUDA(cudaSetDevice(sh.ctx->device));
@@ -619,6 +638,7 @@ int run_sharded_typed(std::vector<Shard> &S, Exchange *ex, int world, const Code
         sh.tt.launches += 2;
     }
 
+    lap("owner merge");
     // ---- phase 4: replicate the merged unique set on every rank ----
     std::vector<uint64_t> totals;
     {
@@ -659,6 +679,7 @@ int run_sharded_typed(std::vector<Shard> &S, Exchange *ex, int world, const Code
         FQD_TRY(gather_device(S, ex, world, src, dst, bytes));
     }
 
+    lap("replicate (allgather)");
     // ---- phase 5: pigeonhole passes over the owned buckets ----
     const uint32_t U = (uint32_t)U_total;
     for (int i = 0; i < L; i++) {
@@ -676,6 +697,7 @@ int run_sharded_typed(std::vector<Shard> &S, Exchange *ex, int world, const Code
         FQD_TRY(stage_passes<K, PW>(sh.ctx, sh.job, codec, sh.all, sh.f, rank_of(i), world, sh.st, sh.tt));
     }
 
+    lap("passes");
     // ---- phase 6: merge forests, flags and edge lists across ranks ----
     const int method = S[0].job.method;
     for (int which = 0; which < 2; which++) {
@@ -772,6 +794,7 @@ int run_sharded_typed(std::vector<Shard> &S, Exchange *ex, int world, const Code
         for (int i = 0; i < L; i++) { S[i].f.edges = (uint2 *)dst[i]; S[i].f.n_edges = total; S[i].f.edge_cap = total; }
     }
 
+    lap("forest/flag merge");
     // ---- phase 7: every rank finishes the dissection; each writes the bitmap of its own records ----
     uint64_t cand_total = 0;
     {
@@ -790,7 +813,7 @@ int run_sharded_typed(std::vector<Shard> &S, Exchange *ex, int world, const Code
         FQD_CUDA(cudaSetDevice(sh.ctx->device));
         cudaStream_t s = sh.ctx->stream;
         FQD_CUDA(cudaMemsetAsync(&sh.ctx->d_ctr->n_selected, 0, 4, s));
-        FQD_TRY(stage_select<K, PW>(sh.ctx, sh.job, codec, sh.all, sh.f, sh.index_base, (uint32_t)sh.job.n, sh.tt));
+        FQD_TRY(stage_select<K, PW>(sh.ctx, sh.job, codec, sh.all, sh.f, sh.index_base, (uint32_t)sh.job.n, sh.tt, true));
         uint32_t *roots;
         FQD_TRY(arena(sh.ctx, 4, &roots));
         FQD_CUDA(cudaMemsetAsync(roots, 0, 16, s));
@@ -807,7 +830,7 @@ int run_sharded_typed(std::vector<Shard> &S, Exchange *ex, int world, const Code
         st->number_of_sequences = n_seq;
         st->number_of_uniques = U_total;
         st->number_of_clusters = h_roots;
-        st->number_selected = sh.ctx->h_ctr->n_selected;
+        st->number_selected = sh.ctx->h_ctr->n_selected;   // own keys only; summed below
         st->candidate_pairs = cand_total;
         cudaEventElapsedTime(&st->ms_total, e0[i], e1[i]);
         st->ms_ingest = sh.tt.ingest;
@@ -816,8 +839,20 @@ int run_sharded_typed(std::vector<Shard> &S, Exchange *ex, int world, const Code
         st->ms_compare = sh.tt.compare;
         st->launches = sh.tt.launches + 1;
         cudaEventDestroy(e0[i]); cudaEventDestroy(e1[i]);
-        publish_result(sh.ctx, sh.all, sh.f, n_total, st->number_selected);
     }
+    {
+        std::vector<std::vector<uint64_t>> mine(L, std::vector<uint64_t>(1));
+        for (int i = 0; i < L; i++) mine[i][0] = S[i].st->number_selected;
+        std::vector<uint64_t> all;
+        FQD_TRY(gather_host_u64(S, ex, world, 1, mine, all));
+        uint64_t total = 0;
+        for (int g = 0; g < world; g++) total += all[g];
+        for (auto &sh : S) {
+            sh.st->number_selected = total;
+            publish_result(sh.ctx, sh.all, sh.f, n_total, total);
+        }
+    }
+    lap("select + stats");
     return FQD_OK;
 }
 

@@ -824,6 +824,7 @@ struct SelectParams {
     uint32_t round;
     uint32_t *bitmap;        // bits for records [bitmap_base, bitmap_base + bitmap_n) only
     uint32_t bitmap_base, bitmap_n;
+    int own_only;
     uint32_t *minfirst;
     int method;
     DevCounters *ctr;
@@ -863,20 +864,21 @@ static __global__ void __launch_bounds__(256) select_kernel(const __grid_constan
     const uint32_t u = blockIdx.x * 256u + threadIdx.x;
     bool sel = false;
     if (u < P.U) {
-        if (P.method == METHOD_DIRECTIONAL) {
-            const uint32_t c = P.ucount[u];
-            if (c >= 2) sel = !P.dominated[u];
-            else { const uint32_t r = P.root[u]; sel = !P.deadroot[r] && P.best[r] == u; }
-        } else if (P.method == METHOD_HIGHEST) {
-            sel = P.best[P.root[u]] == u;
-        } else {
-            sel = P.state[u] == 1;
+        const uint32_t f = P.ufirst[u] - P.bitmap_base;   // wraps for records of other shards
+        // sharded jobs: a rank only decides the keys whose first record is its own
+        if (!P.own_only || f < P.bitmap_n) {
+            if (P.method == METHOD_DIRECTIONAL) {
+                const uint32_t c = P.ucount[u];
+                if (c >= 2) sel = !P.dominated[u];
+                else { const uint32_t r = P.root[u]; sel = !P.deadroot[r] && P.best[r] == u; }
+            } else if (P.method == METHOD_HIGHEST) {
+                sel = P.best[P.root[u]] == u;
+            } else {
+                sel = P.state[u] == 1;
+            }
         }
         P.selected[u] = sel ? 1 : 0;
-        if (sel && P.bitmap) {
-            const uint32_t f = P.ufirst[u] - P.bitmap_base;   // wraps for records of earlier shards
-            if (f < P.bitmap_n) atomicOr(P.bitmap + (f >> 5), 1u << (f & 31));
-        }
+        if (sel && P.bitmap && f < P.bitmap_n) atomicOr(P.bitmap + (f >> 5), 1u << (f & 31));
     }
     const uint32_t b = __ballot_sync(0xFFFFFFFFu, sel);
     if ((threadIdx.x & 31) == 0 && b) atomicAdd(&P.ctr->n_selected, (uint32_t)__popc(b));

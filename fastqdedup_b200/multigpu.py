@@ -124,6 +124,8 @@ def cluster_keys_sharded_local(keys, quals=None, max_distance=1, use_edit_distan
         res.per_rank_stats = [stats[r].as_dict() for r in range(world)]
         if want_uniques:
             first, count, label, sel = contexts[0].fetch(st.number_of_uniques)
+            for c in contexts[1:]:       # a rank decides only the keys whose first record is its own
+                sel |= c.fetch(st.number_of_uniques)[3]
             order = np.argsort(first, kind="stable")
             res.first, res.count = first[order], count[order]
             res.label, res.selected = label[order], sel[order].astype(bool)

@@ -154,8 +154,10 @@ int fqd_cluster_fetch_selected(fqd_context *ctx, uint64_t *indices);
  * contiguously over `world` ranks; rank r passes its own records and the global index of its
  * first record.  Exchange steps (NCCL over NVLink): all-to-all of the locally deduplicated
  * keys to their owner rank, all-gather of the merged unique set, all-gather of the
- * spanning-forest pairs / flags found by each rank.  Every rank ends with the complete
- * per-unique result (fqd_cluster_fetch) and the keep bitmap of ITS OWN records.
+ * spanning-forest pairs / flags found by each rank.  Every rank ends with the keep bitmap of
+ * ITS OWN records and the per-unique view of the whole job (fqd_cluster_fetch: first, count,
+ * label for every key; `selected` only for the keys whose first record is the rank's own --
+ * the union over ranks is the complete set).
  * ------------------------------------------------------------------------------------ */
 typedef struct fqd_comm fqd_comm;
 /* rank 0 creates the id and hands the 128 bytes to the other ranks by any means */
