@@ -100,6 +100,26 @@ static int make_codec(const std::vector<uint8_t> &alphabet, bool varlen, Codec *
     }
     std::vector<uint8_t> sorted(alphabet);
     std::sort(sorted.begin(), sorted.end());
+    c->swar = 0;
+    // DNA: when every symbol is one of ACGTN use the table-free code of pack_key_acgtn
+    bool dna = bits == 3;
+    for (uint8_t ch : alphabet) dna = dna && (ch == 'A' || ch == 'C' || ch == 'G' || ch == 'T' || ch == 'N');
+    if (dna) {
+        const uint8_t letters[5] = {'A', 'C', 'G', 'N', 'T'};      // ASCII order
+        for (int r = 0; r < 5; r++) {
+            const uint8_t code = (letters[r] >> 1) & 7u;
+            c->lut[letters[r]] = code;
+            c->rank[code] = (uint8_t)(r + 1);
+        }
+        c->pad_code = SWAR_PAD_CODE;
+        c->bits = 3;
+        c->n_symbols = 5;
+        c->varlen = varlen ? 1 : 0;
+        // measured on B200 (100 M x 36 nt): the table-free packer is ~9 % slower than the shared-memory
+        // table loop inside the latency-bound ingest kernel, so it is opt-in (FQD_SWAR=1)
+        c->swar = getenv("FQD_SWAR") ? 1 : 0;
+        return FQD_OK;
+    }
     for (int i = 0; i < n; i++) {
         c->lut[alphabet[i]] = (uint8_t)i;
         const int r = (int)(std::lower_bound(sorted.begin(), sorted.end(), alphabet[i]) - sorted.begin());
@@ -158,6 +178,16 @@ int fqd_context_create(int device_ordinal, fqd_context **out)
     ctx->device = device_ordinal;
     FQD_CUDA(cudaSetDevice(device_ordinal));
     FQD_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    FQD_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    // The hot kernels touch random 32-byte sectors (hash slots, union-find parents): ask L2 not
+    // to fetch whole 128-byte lines for them.  FQD_L2_FETCH overrides (32 / 64 / 128).
+    {
+        size_t gran = 32;
+        if (const char *e = getenv("FQD_L2_FETCH")) gran = (size_t)atoi(e);
+        if (gran == 32 || gran == 64 || gran == 128) {
+            if (cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, gran) != cudaSuccess) cudaGetLastError();
+        }
+    }
     FQD_CUDA(cudaMalloc(&ctx->d_ctr, sizeof(DevCounters)));
     FQD_CUDA(cudaHostAlloc(&ctx->h_ctr, sizeof(DevCounters), cudaHostAllocDefault));
     for (auto &ev : ctx->ev) FQD_CUDA(cudaEventCreate(&ev));
@@ -176,6 +206,8 @@ void fqd_context_destroy(fqd_context *ctx)
     for (auto &ev : ctx->ev) if (ev) cudaEventDestroy(ev);
     if (ctx->d_ctr) cudaFree(ctx->d_ctr);
     if (ctx->h_ctr) cudaFreeHost(ctx->h_ctr);
+    for (auto &ev : ctx->chunk_events) cudaEventDestroy(ev);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -313,7 +345,15 @@ int resolve_job(fqd_context *ctx, const fqd_cluster_job *job, uint32_t *keep_bit
                 key_bytes = (size_t)n * job->key_stride;
                 if (job->key_lengths) FQD_TRY(up(job->key_lengths, n * 4, (const void **)&dj.key_lens));
             }
-            FQD_TRY(up(job->keys, key_bytes, (const void **)&dj.keys));
+            const bool stream_rows = !job->key_offsets && n >= (1u << 20) && !getenv("FQD_NO_OVERLAP");
+            if (stream_rows) {
+                void *p = nullptr;
+                FQD_TRY(dev_alloc(ctx, key_bytes, &p));
+                dj.keys = static_cast<const uint8_t *>(p);
+                dj.host_keys = job->keys;
+            } else {
+                FQD_TRY(up(job->keys, key_bytes, (const void **)&dj.keys));
+            }
             if (dj.filter_on) {
                 size_t qual_bytes;
                 if (job->qual_offsets) {
@@ -323,7 +363,14 @@ int resolve_job(fqd_context *ctx, const fqd_cluster_job *job, uint32_t *keep_bit
                     qual_bytes = (size_t)n * job->qual_stride;
                     if (job->qual_lengths) FQD_TRY(up(job->qual_lengths, n * 4, (const void **)&dj.qual_lens));
                 }
-                FQD_TRY(up(job->quals, qual_bytes, (const void **)&dj.quals));
+                if (dj.host_keys && !job->qual_offsets) {
+                    void *p = nullptr;
+                    FQD_TRY(dev_alloc(ctx, qual_bytes, &p));
+                    dj.quals = static_cast<const uint8_t *>(p);
+                    dj.host_quals = job->quals;
+                } else {
+                    FQD_TRY(up(job->quals, qual_bytes, (const void **)&dj.quals));
+                }
             }
             if (job->record_counts) FQD_TRY(up(job->record_counts, n * 4, (const void **)&dj.weights));
         }
@@ -382,7 +429,9 @@ int finish_job(fqd_context *ctx, Resolved &r, fqd_cluster_stats *stats)
         FQD_CUDA(cudaMemcpyAsync(r.host_bitmap, r.dj.bitmap, r.bitmap_words * 4, cudaMemcpyDeviceToHost, s));
     FQD_CUDA(cudaStreamSynchronize(s));
     if (r.h0) {
-        cudaEventElapsedTime(&stats->ms_h2d, r.h0, r.h1);
+        float t = 0.f;
+        cudaEventElapsedTime(&t, r.h0, r.h1);
+        stats->ms_h2d += t;
         cudaEventDestroy(r.h0); cudaEventDestroy(r.h1);
         r.h0 = r.h1 = nullptr;
     }

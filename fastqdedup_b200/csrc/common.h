@@ -56,6 +56,8 @@ struct fqd_arena {
 struct fqd_context {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;
+    std::vector<cudaEvent_t> chunk_events;
     fqd_arena arena;
     fqd::DevCounters *d_ctr = nullptr;
     fqd::DevCounters *h_ctr = nullptr;   // pinned
@@ -124,6 +126,11 @@ struct DeviceJob {
     uint32_t max_len = 0;
     bool varlen = false;
     const uint32_t *weights = nullptr;
+    // HOST jobs with fixed-stride rows: the rows are still in host memory; stage_dedupe copies
+    // them chunk by chunk on the copy stream and ingests each chunk as soon as it has landed
+    // (keys / quals above are the device destinations)
+    const uint8_t *host_keys = nullptr;
+    const uint8_t *host_quals = nullptr;
     uint32_t *bitmap = nullptr;   // device, (n+31)/32 words, zeroed by the pipeline; may be null
 };
 

@@ -44,7 +44,12 @@ struct Codec {
     uint8_t bits;      // K
     uint8_t n_symbols;
     uint8_t varlen;    // 1: keys of several lengths are present (PAD in use)
+    uint8_t swar;      // 1: the ACGTN code of pack_key_acgtn (codes = ASCII bits 1..3) is in use
 };
+
+// Codes of the five DNA letters when the code is simply bits 1..3 of the ASCII byte:
+// A 0x41 -> 0, C 0x43 -> 1, T 0x54 -> 2, G 0x47 -> 3, N 0x4E -> 7; 4 is free and serves as PAD.
+constexpr uint32_t SWAR_PAD_CODE = 4;
 
 template <int K, int PW>
 struct Key {
@@ -109,6 +114,55 @@ FQD_HD bool pack_key(const uint8_t *bytes, uint32_t len, uint32_t padded_len,
         for (int p = 0; p < K; p++) out.w[p * PW + wi] = acc[p];
     }
     return ok;
+}
+
+// SWAR packing for the ACGTN alphabet: four ASCII bytes per 32-bit word, no table.  The code
+// of a letter is bits 1..3 of its byte; the remaining bits are a function of those three for
+// exactly the five letters, which is how a foreign byte is detected (returns false; the caller
+// then reports the bytes one by one through the table path).  `words` must be 4-byte aligned.
+template <int PW>
+FQD_HD bool pack_key_acgtn(const uint32_t *words, uint32_t len, uint32_t padded_len, Key<3, PW> &out)
+{
+    const uint32_t M = 0x01010101u;
+    uint32_t bad = 0;
+#pragma unroll
+    for (int wi = 0; wi < PW; wi++) {
+        uint32_t p0 = 0, p1 = 0, p2 = 0;
+        const uint32_t base = 32u * wi;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const uint32_t pos = base + 4u * j;
+            if (pos < len) {
+                uint32_t w = words[pos >> 2];
+                const uint32_t rem = len - pos;                 // symbols of this word that count
+                if (rem < 4) {
+                    const uint32_t keep = (1u << (8u * rem)) - 1u;
+                    w = (w & keep) | (0x41414141u & ~keep);     // the rest reads as 'A' (code 0)
+                }
+                const uint32_t x0 = w & M, x1 = (w >> 1) & M, x2 = (w >> 2) & M, x3 = (w >> 3) & M,
+                               x4 = (w >> 4) & M;
+                const uint32_t is_t = x2 & (x1 ^ M) & (x3 ^ M);
+                bad |= ((w & 0xE0E0E0E0u) ^ 0x40404040u) | (x3 & ~(x1 & x2)) | (x4 ^ is_t) |
+                       (x0 ^ ((x3 ^ M) & (is_t ^ M)));
+                // gather the four byte-LSBs into a nibble (byte 0 -> bit 0)
+                p0 |= ((x1 * 0x01020408u) >> 24 & 0xFu) << (4 * j);
+                p1 |= ((x2 * 0x01020408u) >> 24 & 0xFu) << (4 * j);
+                p2 |= ((x3 * 0x01020408u) >> 24 & 0xFu) << (4 * j);
+            }
+        }
+        // PAD (code 4 = plane 2 only) on [len, padded_len)
+        if (padded_len > len && padded_len > base && len < base + 32u) {
+            const uint32_t lo = len > base ? len - base : 0u;
+            const uint32_t hi = padded_len - base >= 32u ? 32u : padded_len - base;
+            const uint32_t upto = hi >= 32u ? 0xFFFFFFFFu : ((1u << hi) - 1u);
+            const uint32_t from = lo >= 32u ? 0xFFFFFFFFu : ((1u << lo) - 1u);
+            p2 |= upto & ~from;
+        }
+        out.w[0 * PW + wi] = p0;
+        out.w[1 * PW + wi] = p1;
+        out.w[2 * PW + wi] = p2;
+    }
+    return bad == 0;
 }
 
 // Bit mask (per plane word i) of the positions holding PAD.

@@ -64,8 +64,9 @@ struct Forest {
 };
 
 struct StageTimes {
-    float table_clear = 0, ingest_kernel = 0, ingest = 0, compare = 0;
+    float table_clear = 0, ingest_kernel = 0, ingest = 0, compare = 0, h2d = 0;
     uint32_t launches = 0;
+    bool streamed = false;
 };
 
 template <typename T>
@@ -136,7 +137,47 @@ int stage_dedupe(fqd_context *ctx, const DeviceJob &job, const Codec &codec, uin
     FQD_CUDA(cudaFuncSetAttribute(ingest_kernel<K, PW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)smem));
     ip.phase = 0;
-    if (n) { ingest_kernel<K, PW><<<cdiv(n, 256), 256, smem, s>>>(ip); tt.launches++; }
+    if (n && job.host_keys) {
+        // H2D of chunk i+1 overlaps the ingest of chunk i (PCIe is the e2e bottleneck)
+        const uint64_t chunk = 4u << 20;   // records; a multiple of 256 and of 32
+        const size_t nchunks = (size_t)((n + chunk - 1) / chunk);
+        while (ctx->chunk_events.size() < nchunks) {
+            cudaEvent_t e;
+            FQD_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            ctx->chunk_events.push_back(e);
+        }
+        FQD_CUDA(cudaEventRecord(ctx->ev[9], s));
+        FQD_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev[9], 0));   // buffers are allocated / idle
+        FQD_CUDA(cudaEventRecord(ctx->ev[10], ctx->copy_stream));
+        IngestParams cp = ip;
+        for (size_t i = 0; i < nchunks; i++) {
+            const uint64_t c0 = i * chunk, cn = std::min<uint64_t>(chunk, n - c0);
+            FQD_CUDA(cudaMemcpyAsync(const_cast<uint8_t *>(job.keys) + c0 * job.key_stride,
+                                     job.host_keys + c0 * job.key_stride, cn * job.key_stride,
+                                     cudaMemcpyHostToDevice, ctx->copy_stream));
+            if (job.host_quals)
+                FQD_CUDA(cudaMemcpyAsync(const_cast<uint8_t *>(job.quals) + c0 * job.qual_stride,
+                                         job.host_quals + c0 * job.qual_stride, cn * job.qual_stride,
+                                         cudaMemcpyHostToDevice, ctx->copy_stream));
+            FQD_CUDA(cudaEventRecord(ctx->chunk_events[i], ctx->copy_stream));
+            FQD_CUDA(cudaStreamWaitEvent(s, ctx->chunk_events[i], 0));
+            cp.n = cn;
+            cp.keys = job.keys + c0 * job.key_stride;
+            cp.key_lens = job.key_lens ? job.key_lens + c0 : nullptr;
+            cp.quals = job.quals ? job.quals + c0 * job.qual_stride : nullptr;
+            cp.qual_lens = job.qual_lens ? job.qual_lens + c0 : nullptr;
+            cp.keepmask = keepmask + c0 / 32;
+            cp.weights = job.weights ? job.weights + c0 : nullptr;
+            cp.index_base = index_base + (uint32_t)c0;
+            ingest_kernel<K, PW><<<cdiv(cn, 256), 256, smem, s>>>(cp);
+            tt.launches++;
+        }
+        FQD_CUDA(cudaEventRecord(ctx->ev[11], ctx->copy_stream));
+        tt.streamed = true;
+    } else if (n) {
+        ingest_kernel<K, PW><<<cdiv(n, 256), 256, smem, s>>>(ip);
+        tt.launches++;
+    }
     FQD_CUDA(cudaEventRecord(ev[2], s));
     FQD_CUDA(cudaGetLastError());
     FQD_TRY(fetch_counters(ctx));
@@ -177,6 +218,11 @@ int stage_dedupe(fqd_context *ctx, const DeviceJob &job, const Codec &codec, uin
     cudaEventElapsedTime(&tt.table_clear, ev[0], ev[1]);
     cudaEventElapsedTime(&tt.ingest_kernel, ev[1], ev[2]);
     cudaEventElapsedTime(&tt.ingest, ev[0], ev[3]);
+    if (tt.streamed) {
+        FQD_CUDA(cudaEventSynchronize(ctx->ev[11]));
+        cudaEventElapsedTime(&tt.h2d, ctx->ev[10], ctx->ev[11]);
+    }
+    st->ms_h2d = tt.h2d;
     return FQD_OK;
 }
 

@@ -199,6 +199,8 @@ __device__ __forceinline__ void table_insert(const TableRef &P, const Key<K, PW>
         if (st == SLOT_EMPTY) {
             const uint32_t old = atomicCAS(rec + KW + 1, SLOT_EMPTY, SLOT_LOCKED);
             if (old == SLOT_EMPTY) {
+                // (a single 256-bit store of the whole sector was measured 20 % slower than
+                // scalar stores + release on B200: it collides with the CAS in flight)
 #pragma unroll
                 for (int i = 0; i < KW; i++) rec[i] = key.w[i];
                 rec[KW] = weight;
@@ -354,7 +356,15 @@ static __global__ void __launch_bounds__(256) ingest_kernel(const __grid_constan
     if (klen > P.max_len) klen = P.max_len;
     Key<K, PW> key;
     uint32_t badbyte = 0;
-    if (!pack_key<K, PW>(kb, klen, P.codec.varlen ? P.max_len : klen, lut, P.pad_code, key, &badbyte)) {
+    bool packed = false;
+    if constexpr (K == 3) {
+        // table-free DNA packing from the 4-byte aligned staged row
+        if (P.codec.swar && P.stage_bytes && !P.key_off && (P.key_stride & 3u) == 0)
+            packed = pack_key_acgtn<PW>(reinterpret_cast<const uint32_t *>(kb), klen,
+                                        P.codec.varlen ? P.max_len : klen, key);
+    }
+    if (!packed &&
+        !pack_key<K, PW>(kb, klen, P.codec.varlen ? P.max_len : klen, lut, P.pad_code, key, &badbyte)) {
         // report every unknown byte of this key so one retry with a grown alphabet suffices
         for (uint32_t i = 0; i < klen; i++) {
             const uint32_t c = kb[i];

@@ -26,6 +26,19 @@ struct HostCodec {
             c.rank[i] = (uint8_t)(1 + (std::lower_bound(sorted.begin(), sorted.end(), alphabet[i]) - sorted.begin()));
         }
         c.pad_code = (uint8_t)n;
+        bool dna = bits == 3;
+        for (int i = 0; i < n; i++) dna = dna && strchr("ACGTN", alphabet[i]) != nullptr;
+        if (dna) {
+            memset(c.lut, 0xFF, sizeof c.lut);
+            memset(c.rank, 0, sizeof c.rank);
+            const char *letters = "ACGNT";
+            for (int r = 0; r < 5; r++) {
+                const uint8_t code = ((uint8_t)letters[r] >> 1) & 7u;
+                c.lut[(uint8_t)letters[r]] = code;
+                c.rank[code] = (uint8_t)(r + 1);
+            }
+            c.pad_code = SWAR_PAD_CODE;
+        }
         c.bits = (uint8_t)bits;
         c.n_symbols = (uint8_t)n;
         c.varlen = varlen;
@@ -51,6 +64,16 @@ int run(int op, const HostCodec &hc, const uint8_t *a, uint32_t la, const uint8_
         return block_hash<K, PW>(ka, p0, p2, 7) == block_hash<K, PW>(kb, p1, p2, 7) ? 1 : 0;
     case 6: *out64 = hash_key<K, PW>(ka); return 0;
     case 7: return (int)symbol_at<K, PW>(ka, p0);
+    case 8:   // table-free ACGTN packing == table packing (or both reject)
+        if constexpr (K == 3) {
+            alignas(4) uint8_t buf[4 * 8 * PW + 8] = {};
+            memcpy(buf, a, la);
+            for (uint32_t i = la; i < sizeof buf; i++) buf[i] = (uint8_t)(0x5A + i);   // garbage tail
+            Key<K, PW> ks;
+            const bool ok = pack_key_acgtn<PW>(reinterpret_cast<const uint32_t *>(buf), la, varlen ? max_len : la, ks);
+            return ok ? (key_equal<K, PW>(ks, ka) ? 1 : 0) : 2;
+        }
+        return -1;
     }
     return -1;
 }

@@ -11,7 +11,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SRC = os.path.join(ROOT, "tests", "probe", "key_probe.cpp")
 OUT = os.path.join(ROOT, "tests", "probe", "build", "key_probe.so")
 
-OPS = dict(hamming=0, myers=1, less=2, equal=3, length=4, blockeq=5, hash=6, symbol=7)
+OPS = dict(hamming=0, myers=1, less=2, equal=3, length=4, blockeq=5, hash=6, symbol=7, swar=8)
 
 
 @pytest.fixture(scope="module")
@@ -32,7 +32,7 @@ def probe():
         out = ctypes.c_uint64()
         r = lib.key_probe(K, PW, OPS[op], alphabet, len(alphabet), int(varlen), a, len(a), b, len(b),
                           max_len, d, p0, p1, p2, ctypes.byref(out))
-        assert r >= 0, r
+        assert r >= 0 or (op == "swar" and r == -2), r
         return out.value if op == "hash" else r
     return call
 
@@ -92,7 +92,10 @@ def test_order_equality_length(probe, K, PW, alphabet, L):
         if la:
             p = int(rng.integers(0, la))
             code = probe(K, PW, "symbol", alphabet, True, a, b, L, p0=p)
-            assert alphabet[code] == a[p]
+            if alphabet == b"ACGTN":
+                assert code == (a[p] >> 1) & 7          # the table-free DNA code
+            else:
+                assert alphabet[code] == a[p]
 
 
 @pytest.mark.parametrize("K,PW,alphabet,L", CASES[:5])
@@ -120,3 +123,21 @@ def test_hash_separates_keys(probe):
         a = bytes(rng.choice(list(b"ACGTN"), size=36).astype(np.uint8))
         h = probe(3, 2, "hash", b"ACGTN", False, a, a, 36)
         assert seen.setdefault(h, a) == a
+
+
+@pytest.mark.parametrize("PW,L", [(1, 12), (1, 32), (2, 36), (2, 48), (2, 64), (3, 90), (5, 150)])
+def test_table_free_dna_packing(probe, PW, L):
+    """pack_key_acgtn (4 bytes per step, validity by bit algebra) == the table packer for every
+    length / padding, and rejects every byte that is not one of ACGTN."""
+    rng = np.random.default_rng(PW * 100 + L)
+    for it in range(1500):
+        la = L if it % 2 else int(rng.integers(0, L + 1))
+        a = bytes(rng.choice(list(b"ACGTN"), size=la).astype(np.uint8))
+        for varlen in (False, True):
+            assert probe(3, PW, "swar", b"ACGTN", varlen, a, a, L) == 1, (a, varlen)
+    for byte in range(256):
+        for pos in (0, 1, 2, 3, 5, L - 1):
+            a = bytearray(b"ACGT" * 40)[:L]
+            a[pos] = byte
+            r = probe(3, PW, "swar", b"ACGTN", False, bytes(a), bytes(a), L)
+            assert r == (1 if byte in b"ACGTN" else -2), (byte, pos, r)
