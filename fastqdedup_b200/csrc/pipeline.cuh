@@ -95,6 +95,22 @@ __device__ __forceinline__ void load_key(const uint32_t *__restrict__ ukey, uint
     for (int i = 0; i < K * PW; i++) k.w[i] = __ldg(p + i);
 }
 
+// streaming variant for kernels that read every key once (keeps the bucket counters in L2)
+template <int K, int PW>
+__device__ __forceinline__ void load_key_stream(const uint32_t *__restrict__ ukey, uint32_t u,
+                                                Key<K, PW> &k)
+{
+    const uint32_t *p = ukey + (size_t)u * (K * PW);
+    if constexpr ((K * PW) % 2 == 0) {
+        const uint2 *p2 = reinterpret_cast<const uint2 *>(p);
+#pragma unroll
+        for (int i = 0; i < K * PW / 2; i++) { const uint2 v = __ldcs(p2 + i); k.w[2 * i] = v.x; k.w[2 * i + 1] = v.y; }
+    } else {
+#pragma unroll
+        for (int i = 0; i < K * PW; i++) k.w[i] = __ldcs(p + i);
+    }
+}
+
 // ---- ingest: filter + pack + exact dedupe ----------------------------------------------
 
 // The exact-dedupe table in HBM.
@@ -543,7 +559,7 @@ static __global__ void __launch_bounds__(256) sig_count_kernel(const __grid_cons
     const uint32_t u = blockIdx.x * 256u + threadIdx.x;
     if (u >= P.U) return;
     Key<K, PW> key;
-    load_key<K, PW>(P.ukey, u, key);
+    load_key_stream<K, PW>(P.ukey, u, key);
     const uint32_t len = P.varlen ? key_length(key, P.pad_code, P.max_len) : P.max_len;
     for (int v = 0; v < P.V; v++) {
         uint64_t sig;
@@ -552,7 +568,7 @@ static __global__ void __launch_bounds__(256) sig_count_kernel(const __grid_cons
         if (pass_variant<K, PW>(key, len, P, v, sig, build) &&
             (P.world <= 1 || (uint32_t)(sig >> 32) % (uint32_t)P.world == (uint32_t)P.my_rank))
             r = atomicAdd(P.cnt + ((uint32_t)sig & P.nb_mask), 1u);
-        P.rank[(size_t)u * P.V + v] = r;
+        __stcs(P.rank + (size_t)u * P.V + v, r);
     }
 }
 
@@ -562,10 +578,10 @@ static __global__ void __launch_bounds__(256) scatter_kernel(const __grid_consta
     const uint32_t u = blockIdx.x * 256u + threadIdx.x;
     if (u >= P.U) return;
     Key<K, PW> key;
-    load_key<K, PW>(P.ukey, u, key);
+    load_key_stream<K, PW>(P.ukey, u, key);
     const uint32_t len = P.varlen ? key_length(key, P.pad_code, P.max_len) : P.max_len;
     for (int v = 0; v < P.V; v++) {
-        const uint32_t r = P.rank[(size_t)u * P.V + v];
+        const uint32_t r = __ldcs(P.rank + (size_t)u * P.V + v);
         if (r == RANK_INVALID) continue;
         uint64_t sig;
         bool build;
@@ -664,9 +680,9 @@ static __global__ void __launch_bounds__(256) scatter_fat_kernel(const __grid_co
     const uint32_t u = blockIdx.x * 256u + threadIdx.x;
     if (u >= P.U) return;
     Key<K, PW> key;
-    load_key<K, PW>(P.ukey, u, key);
+    load_key_stream<K, PW>(P.ukey, u, key);
     const uint32_t len = P.varlen ? key_length(key, P.pad_code, P.max_len) : P.max_len;
-    const uint32_t r = P.rank[u];
+    const uint32_t r = __ldcs(P.rank + u);
     if (r == RANK_INVALID) return;   // bucket owned by another rank
     uint64_t sig;
     bool build;
@@ -679,11 +695,11 @@ static __global__ void __launch_bounds__(256) scatter_fat_kernel(const __grid_co
     for (int i = 0; i < FW; i++) e[i] = 0;
 #pragma unroll
     for (int i = 0; i < KW; i++) e[i] = key.w[i];
-    e[KW] = P.ucount[u];
+    e[KW] = __ldcs(P.ucount + u);
     e[KW + 1] = u | (pos + 1 == hi ? ENT_LAST : 0u);
     uint4 *dst = reinterpret_cast<uint4 *>(P.fat + (size_t)pos * FW);
 #pragma unroll
-    for (int c = 0; c < FW / 4; c++) dst[c] = make_uint4(e[4 * c], e[4 * c + 1], e[4 * c + 2], e[4 * c + 3]);
+    for (int c = 0; c < FW / 4; c++) __stcs(dst + c, make_uint4(e[4 * c], e[4 * c + 1], e[4 * c + 2], e[4 * c + 3]));
 }
 
 template <int K, int PW>
@@ -874,15 +890,18 @@ static __global__ void __launch_bounds__(256) select_kernel(const __grid_constan
     const uint32_t u = blockIdx.x * 256u + threadIdx.x;
     bool sel = false;
     if (u < P.U) {
-        const uint32_t f = P.ufirst[u] - P.bitmap_base;   // wraps for records of other shards
+        // independent loads first (the kernel is latency-bound), dependent ones after
+        const uint32_t f = __ldcs(P.ufirst + u) - P.bitmap_base;   // wraps for records of other shards
+        const uint32_t c = __ldcs(P.ucount + u);
+        const uint32_t r = P.method != METHOD_ADJACENCY ? __ldcs(P.root + u) : 0u;
+        const uint8_t dom = P.method == METHOD_DIRECTIONAL ? P.dominated[u] : (uint8_t)0;
         // sharded jobs: a rank only decides the keys whose first record is its own
         if (!P.own_only || f < P.bitmap_n) {
             if (P.method == METHOD_DIRECTIONAL) {
-                const uint32_t c = P.ucount[u];
-                if (c >= 2) sel = !P.dominated[u];
-                else { const uint32_t r = P.root[u]; sel = !P.deadroot[r] && P.best[r] == u; }
+                if (c >= 2) sel = !dom;
+                else sel = !P.deadroot[r] && P.best[r] == u;
             } else if (P.method == METHOD_HIGHEST) {
-                sel = P.best[P.root[u]] == u;
+                sel = P.best[r] == u;
             } else {
                 sel = P.state[u] == 1;
             }
