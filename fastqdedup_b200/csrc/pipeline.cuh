@@ -49,6 +49,7 @@ struct DevCounters {
     uint32_t undecided;
     uint32_t unknown[8];              // bitmap of key bytes outside the alphabet
     uint32_t len_min, len_max;
+    uint32_t n_pairs[2];              // sharded jobs: successful hooks recorded per forest
 };
 
 // ---- small device helpers -----------------------------------------------------------
@@ -197,10 +198,9 @@ __device__ __forceinline__ void load_slot(const uint32_t *rec, uint32_t (&w)[RW]
 // roughly in index order.
 template <int K, int PW>
 __device__ __forceinline__ void table_insert(const TableRef &P, const Key<K, PW> &key,
-                                             uint32_t t, uint32_t weight)
+                                             uint64_t h, uint32_t t, uint32_t weight)
 {
     constexpr int KW = K * PW, RW = slot_words(KW);
-    const uint64_t h = hash_key(key);
     uint64_t s = __umul64hi(h, P.capacity);
     for (uint64_t probes = 0; probes < P.capacity;) {
         uint32_t *rec = P.table + s * RW;
@@ -247,10 +247,9 @@ __device__ __forceinline__ void table_insert(const TableRef &P, const Key<K, PW>
 // does not re-apply the filter, __init__.py:201-206): lower `first` of an existing key.
 template <int K, int PW>
 __device__ __forceinline__ void table_touch_first(const TableRef &P, const Key<K, PW> &key,
-                                                  uint32_t t)
+                                                  uint64_t h, uint32_t t)
 {
     constexpr int KW = K * PW, RW = slot_words(KW);
-    const uint64_t h = hash_key(key);
     uint64_t s = __umul64hi(h, P.capacity);
     for (uint64_t probes = 0; probes < P.capacity; probes++) {
         uint32_t *rec = P.table + s * RW;
@@ -269,9 +268,29 @@ __device__ __forceinline__ void table_touch_first(const TableRef &P, const Key<K
     }
 }
 
+// cooperative copy of `bytes` bytes into shared memory (16-byte loads when aligned)
+__device__ __forceinline__ void stage_rows(uint8_t *stage, const uint8_t *src, uint64_t bytes, int tid)
+{
+    if ((reinterpret_cast<uintptr_t>(src) & 15u) == 0) {
+        const uint4 *s4 = reinterpret_cast<const uint4 *>(src);
+        uint4 *d4 = reinterpret_cast<uint4 *>(stage);
+        for (uint32_t i = tid; i < bytes / 16; i += 256) d4[i] = __ldg(s4 + i);
+        for (uint32_t i = (uint32_t)(bytes & ~15ull) + tid; i < bytes; i += 256) stage[i] = __ldg(src + i);
+    } else {
+        for (uint32_t i = tid; i < bytes; i += 256) stage[i] = __ldg(src + i);
+    }
+}
+
+// Records per thread.  2 (pack the second key while the first key's prefetched table sector is
+// on its way from HBM) was measured 26 % SLOWER on B200 than 1: the kernel lives on occupancy
+// (32 registers, 8 blocks/SM), not on per-thread memory-level parallelism.
+constexpr int INGEST_ROWS = 1;
+
 template <int K, int PW>
 static __global__ void __launch_bounds__(256) ingest_kernel(const __grid_constant__ IngestParams P)
 {
+    constexpr int ROWS = INGEST_ROWS;
+    constexpr int KW = K * PW, RW = slot_words(KW);
     extern __shared__ __align__(16) uint8_t smem[];
     double *lut_d = reinterpret_cast<double *>(smem);   // 128 doubles
     uint8_t *lut = smem + 1024;                         // 256 bytes
@@ -279,41 +298,39 @@ static __global__ void __launch_bounds__(256) ingest_kernel(const __grid_constan
     const int tid = threadIdx.x;
     if (tid < 128) lut_d[tid] = __longlong_as_double((long long)FQD_PHRED_LUT_BITS[tid]);
     lut[tid] = P.codec.lut[tid];
-    const uint64_t t0 = (uint64_t)blockIdx.x * 256u;
-    const uint32_t nblk = (uint32_t)min((uint64_t)256u, P.n - t0);
-    const uint64_t t = t0 + tid;
-    const bool active = tid < (int)nblk;
+    const uint64_t t0 = (uint64_t)blockIdx.x * (256u * ROWS);
+    const uint32_t nblk = (uint32_t)min((uint64_t)(256u * ROWS), P.n - t0);
+    uint64_t t[ROWS];
+    bool active[ROWS], keep[ROWS];
+#pragma unroll
+    for (int r = 0; r < ROWS; r++) {
+        const uint32_t lr = r * 256u + tid;
+        t[r] = t0 + lr;
+        active[r] = lr < nblk;
+        keep[r] = true;
+        if (P.phase == 1) keep[r] = active[r] && !((P.keepmask[t[r] >> 5] >> (t[r] & 31)) & 1u);
+    }
     __syncthreads();
-
-    bool keep = true;
-    if (P.phase == 1) keep = active && !((P.keepmask[t >> 5] >> (t & 31)) & 1u);
 
     // ---- quality filter (reference _fastqmodule.c:58-75) ----
     if (P.filter_on && P.phase == 0) {
-        const uint8_t *q = nullptr;
-        uint32_t qlen = 0;
-        if (P.qual_off) {
-            if (active) { q = P.quals + P.qual_off[t]; qlen = (uint32_t)(P.qual_off[t + 1] - P.qual_off[t]); }
-        } else {
-            if (P.stage_bytes) {
-                const uint64_t bytes = (uint64_t)nblk * P.qual_stride;
-                const uint8_t *src = P.quals + t0 * P.qual_stride;
-                if ((reinterpret_cast<uintptr_t>(src) & 15u) == 0) {
-                    const uint4 *s4 = reinterpret_cast<const uint4 *>(src);
-                    uint4 *d4 = reinterpret_cast<uint4 *>(stage);
-                    for (uint32_t i = tid; i < bytes / 16; i += 256) d4[i] = __ldg(s4 + i);
-                    for (uint32_t i = (uint32_t)(bytes & ~15ull) + tid; i < bytes; i += 256) stage[i] = __ldg(src + i);
-                } else {
-                    for (uint32_t i = tid; i < bytes; i += 256) stage[i] = __ldg(src + i);
-                }
-                __syncthreads();
-                q = stage + (size_t)tid * P.qual_stride;
-            } else {
-                q = P.quals + t * P.qual_stride;
-            }
-            if (active) qlen = P.qual_lens ? P.qual_lens[t] : P.qual_len;
+        const bool staged = !P.qual_off && P.stage_bytes;
+        if (staged) {
+            stage_rows(stage, P.quals + t0 * P.qual_stride, (uint64_t)nblk * P.qual_stride, tid);
+            __syncthreads();
         }
-        if (active) {
+#pragma unroll
+        for (int r = 0; r < ROWS; r++) {
+            if (!active[r]) continue;
+            const uint8_t *q;
+            uint32_t qlen;
+            if (P.qual_off) {
+                q = P.quals + P.qual_off[t[r]];
+                qlen = (uint32_t)(P.qual_off[t[r] + 1] - P.qual_off[t[r]]);
+            } else {
+                q = staged ? stage + (size_t)(r * 256u + tid) * P.qual_stride : P.quals + t[r] * P.qual_stride;
+                qlen = P.qual_lens ? P.qual_lens[t[r]] : P.qual_len;
+            }
             double total = 0.0;
             const uint32_t max_score = (126u - P.phred_offset) & 0xFFu;
             bool bad = false;
@@ -321,81 +338,89 @@ static __global__ void __launch_bounds__(256) ingest_kernel(const __grid_constan
                 const uint32_t c = q[i];
                 const uint32_t score = (c - P.phred_offset) & 0xFFu;   // uint8 wrap (:62)
                 if (score > max_score) {
-                    atomicMin(&P.ctr->phred_err, (unsigned long long)(((t + P.index_base) << 8) | c));
+                    atomicMin(&P.ctr->phred_err, (unsigned long long)(((t[r] + P.index_base) << 8) | c));
                     bad = true;
                     break;
                 }
                 total = __dadd_rn(total, lut_d[score]);                // left to right (:72)
             }
             const double avg = __ddiv_rn(total, (double)qlen);         // (:74), 0/0 = NaN
-            keep = !bad && !(avg > P.max_err);                         // strict; NaN keeps
+            keep[r] = !bad && !(avg > P.max_err);                      // strict; NaN keeps
         }
         __syncthreads();   // stage is reused for the keys
     }
-    if (!active) keep = false;
-
-    if (P.phase == 0) {
-        const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, keep);
-        if ((tid & 31) == 0 && t0 + tid < P.n) P.keepmask[(t0 + tid) >> 5] = ballot;
+#pragma unroll
+    for (int r = 0; r < ROWS; r++) {
+        if (!active[r]) keep[r] = false;
+        if (P.phase == 0) {
+            const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, keep[r]);
+            if ((tid & 31) == 0 && t[r] < P.n) P.keepmask[t[r] >> 5] = ballot;
+            if (P.filter_on && active[r] && !keep[r]) aggregated_inc(&P.ctr->n_discarded);
+        }
     }
 
-    // ---- pack (bit planes) ----
-    const uint8_t *kb = nullptr;
-    uint32_t klen = 0;
-    if (P.key_off) {
-        if (active) { kb = P.keys + P.key_off[t]; klen = (uint32_t)(P.key_off[t + 1] - P.key_off[t]); }
-    } else {
-        if (P.stage_bytes) {
-            const uint64_t bytes = (uint64_t)nblk * P.key_stride;
-            const uint8_t *src = P.keys + t0 * P.key_stride;
-            if ((reinterpret_cast<uintptr_t>(src) & 15u) == 0) {
-                const uint4 *s4 = reinterpret_cast<const uint4 *>(src);
-                uint4 *d4 = reinterpret_cast<uint4 *>(stage);
-                for (uint32_t i = tid; i < bytes / 16; i += 256) d4[i] = __ldg(s4 + i);
-                for (uint32_t i = (uint32_t)(bytes & ~15ull) + tid; i < bytes; i += 256) stage[i] = __ldg(src + i);
-            } else {
-                for (uint32_t i = tid; i < bytes; i += 256) stage[i] = __ldg(src + i);
-            }
-            __syncthreads();
-            kb = stage + (size_t)tid * P.key_stride;
+    // ---- pack (bit planes), hash, prefetch the home slot ----
+    const bool kstaged = !P.key_off && P.stage_bytes;
+    if (kstaged) {
+        stage_rows(stage, P.keys + t0 * P.key_stride, (uint64_t)nblk * P.key_stride, tid);
+        __syncthreads();
+    }
+    Key<K, PW> key[ROWS];
+    uint64_t hash[ROWS];
+    bool go[ROWS];
+#pragma unroll
+    for (int r = 0; r < ROWS; r++) {
+        // phase 0: a filtered record stops here (unless sharded); phase 1: `keep` means "was filtered"
+        go[r] = active[r] && (keep[r] || (P.sharded && P.phase == 0));
+        if (!go[r]) continue;
+        const uint8_t *kb;
+        uint32_t klen;
+        if (P.key_off) {
+            kb = P.keys + P.key_off[t[r]];
+            klen = (uint32_t)(P.key_off[t[r] + 1] - P.key_off[t[r]]);
         } else {
-            kb = P.keys + t * P.key_stride;
+            kb = kstaged ? stage + (size_t)(r * 256u + tid) * P.key_stride : P.keys + t[r] * P.key_stride;
+            klen = P.key_lens ? P.key_lens[t[r]] : P.key_len;
         }
-        if (active) klen = P.key_lens ? P.key_lens[t] : P.key_len;
-    }
-    if (!active) return;
-    if (P.filter_on && P.phase == 0 && !keep) {
-        aggregated_inc(&P.ctr->n_discarded);
-    }
-    // phase 0: a filtered record stops here (unless sharded); phase 1: `keep` means "was filtered"
-    if (!keep && !(P.sharded && P.phase == 0)) return;
-    if (klen > P.max_len) klen = P.max_len;
-    Key<K, PW> key;
-    uint32_t badbyte = 0;
-    bool packed = false;
-    if constexpr (K == 3) {
-        // table-free DNA packing from the 4-byte aligned staged row
-        if (P.codec.swar && P.stage_bytes && !P.key_off && (P.key_stride & 3u) == 0)
-            packed = pack_key_acgtn<PW>(reinterpret_cast<const uint32_t *>(kb), klen,
-                                        P.codec.varlen ? P.max_len : klen, key);
-    }
-    if (!packed &&
-        !pack_key<K, PW>(kb, klen, P.codec.varlen ? P.max_len : klen, lut, P.pad_code, key, &badbyte)) {
-        // report every unknown byte of this key so one retry with a grown alphabet suffices
-        for (uint32_t i = 0; i < klen; i++) {
-            const uint32_t c = kb[i];
-            if (lut[c] == 0xFF) atomicOr(&P.ctr->unknown[c >> 5], 1u << (c & 31));
+        if (klen > P.max_len) klen = P.max_len;
+        uint32_t badbyte = 0;
+        bool packed = false;
+        if constexpr (K == 3) {
+            // table-free DNA packing from the 4-byte aligned staged row (opt-in, see api.cu)
+            if (P.codec.swar && kstaged && (P.key_stride & 3u) == 0)
+                packed = pack_key_acgtn<PW>(reinterpret_cast<const uint32_t *>(kb), klen,
+                                            P.codec.varlen ? P.max_len : klen, key[r]);
         }
-        return;
+        if (!packed &&
+            !pack_key<K, PW>(kb, klen, P.codec.varlen ? P.max_len : klen, lut, P.pad_code, key[r], &badbyte)) {
+            // report every unknown byte of this key so one retry with a grown alphabet suffices
+            for (uint32_t i = 0; i < klen; i++) {
+                const uint32_t c = kb[i];
+                if (lut[c] == 0xFF) atomicOr(&P.ctr->unknown[c >> 5], 1u << (c & 31));
+            }
+            go[r] = false;
+            continue;
+        }
+        hash[r] = hash_key(key[r]);
+        if constexpr (ROWS > 1) {
+            const uint32_t *home = P.tab.table + __umul64hi(hash[r], P.tab.capacity) * RW;
+            asm volatile("prefetch.global.L2 [%0];" :: "l"(home));
+        }
     }
-    const uint32_t tg = P.index_base + (uint32_t)t;
-    if (P.phase == 0) {
-        // a filtered record only gets here in sharded mode: weight 0 carries its first index
-        const uint32_t weight = keep ? (P.weights ? P.weights[t] : 1u) : 0u;
-        if (P.weights && keep) atomicAdd(&P.ctr->sum_weights, (unsigned long long)weight);
-        table_insert<K, PW>(P.tab, key, tg, weight);
-    } else {
-        table_touch_first<K, PW>(P.tab, key, tg);
+
+    // ---- exact dedupe ----
+#pragma unroll
+    for (int r = 0; r < ROWS; r++) {
+        if (!go[r]) continue;
+        const uint32_t tg = P.index_base + (uint32_t)t[r];
+        if (P.phase == 0) {
+            // a filtered record only gets here in sharded mode: weight 0 carries its first index
+            const uint32_t weight = keep[r] ? (P.weights ? P.weights[t[r]] : 1u) : 0u;
+            if (P.weights && keep[r]) atomicAdd(&P.ctr->sum_weights, (unsigned long long)weight);
+            table_insert<K, PW>(P.tab, key[r], hash[r], tg, weight);
+        } else {
+            table_touch_first<K, PW>(P.tab, key[r], hash[r], tg);
+        }
     }
 }
 
@@ -515,6 +540,8 @@ struct PassParams {
     uint8_t *dead;
     uint2 *edges;
     unsigned long long edge_cap;
+    uint2 *pairs_full;      // sharded jobs: every successful hook (a spanning forest of this
+    uint2 *pairs_one;       // rank's edges), to be replayed on the other ranks
     DevCounters *ctr;
     uint8_t rank_of_code[256];
 };
@@ -599,12 +626,18 @@ __device__ __forceinline__ void process_edge(const PassParams &P, uint32_t ui, u
                                              uint32_t ci, uint32_t cj, const Key<K, PW> &ki,
                                              const Key<K, PW> &kj, uint32_t &merges)
 {
-    if (uf_union(P.parent_full, ui, uj)) merges++;
+    if (uf_union(P.parent_full, ui, uj)) {
+        merges++;
+        if (P.pairs_full) P.pairs_full[aggregated_inc(&P.ctr->n_pairs[0])] = make_uint2(ui, uj);
+    }
     if (P.method == METHOD_DIRECTIONAL) {
         // closed form of reference __init__.py:60-91 (DESIGN.md "directional")
         if (ci >= 2 && (unsigned long long)cj >= 2ull * ci - 1ull) P.dominated[ui] = 1;
         if (cj >= 2 && (unsigned long long)ci >= 2ull * cj - 1ull) P.dominated[uj] = 1;
-        if (ci == 1 && cj == 1) uf_union(P.parent_one, ui, uj);
+        if (ci == 1 && cj == 1) {
+            if (uf_union(P.parent_one, ui, uj) && P.pairs_one)
+                P.pairs_one[aggregated_inc(&P.ctr->n_pairs[1])] = make_uint2(ui, uj);
+        }
         else if (ci == 1) P.dead[ui] = 1;
         else if (cj == 1) P.dead[uj] = 1;
     } else if (P.method == METHOD_ADJACENCY) {
@@ -1032,7 +1065,7 @@ static __global__ void __launch_bounds__(256) merge_insert_kernel(uint32_t n, co
     Key<K, PW> key;
 #pragma unroll
     for (int j = 0; j < KW; j++) key.w[j] = e[j];
-    table_insert<K, PW>(tab, key, e[KW + 1], e[KW]);
+    table_insert<K, PW>(tab, key, hash_key(key), e[KW + 1], e[KW]);
 }
 
 // gather that drops keys whose every record was filtered out (count 0)
@@ -1062,17 +1095,7 @@ static __global__ void __launch_bounds__(256) gather_nonzero_kernel(uint32_t U, 
     ufirst[pos] = w[KW + 1];
 }
 
-// spanning-forest pairs (u, root(u)) of one rank's forest, to be applied on every rank
-static __global__ void __launch_bounds__(256) forest_pairs_kernel(uint32_t U, uint32_t *parent, uint2 *pairs,
-                                                                  uint32_t *n_pairs)
-{
-    const uint32_t u = blockIdx.x * 256u + threadIdx.x;
-    if (u >= U) return;
-    const uint32_t r = uf_find(parent, u);
-    if (r == u) return;
-    pairs[aggregated_inc(n_pairs)] = make_uint2(u, r);
-}
-
+// replay of the hooks another rank recorded (PassParams::pairs_*)
 static __global__ void __launch_bounds__(256) apply_pairs_kernel(uint32_t n, const uint2 *__restrict__ pairs,
                                                                  uint32_t *parent)
 {
