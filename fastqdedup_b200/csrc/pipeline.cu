@@ -57,7 +57,6 @@ struct Uniques {
 };
 
 struct Forest {
-    uint2 *pairs_full = nullptr, *pairs_one = nullptr;   // sharded jobs only
     uint32_t *parent_full = nullptr, *parent_one = nullptr, *best = nullptr, *root = nullptr;
     uint8_t *dominated = nullptr, *dead = nullptr, *deadroot = nullptr, *selected = nullptr;
     uint2 *edges = nullptr;
@@ -286,7 +285,6 @@ int stage_passes(fqd_context *ctx, const DeviceJob &job, const Codec &codec, con
     pp.parent_full = f.parent_full; pp.parent_one = f.parent_one;
     pp.dominated = f.dominated; pp.dead = f.dead;
     pp.edges = f.edges; pp.edge_cap = f.edge_cap; pp.ctr = ctx->d_ctr;
-    pp.pairs_full = f.pairs_full; pp.pairs_one = f.pairs_one;
     for (int i = 0; i < 256; i++) pp.rank_of_code[i] = codec.rank[i];
     std::vector<cudaEvent_t> cev(2 * npass);
     for (auto &e : cev) FQD_CUDA(cudaEventCreate(&e));
@@ -315,7 +313,6 @@ int stage_passes(fqd_context *ctx, const DeviceJob &job, const Codec &codec, con
         FQD_TRY(arena(ctx, f.edge_cap, &f.edges));
         pp.edges = f.edges; pp.edge_cap = f.edge_cap;
         ctx->h_ctr->n_edges = 0; ctx->h_ctr->n_merges = 0; ctx->h_ctr->n_candidates = 0;
-        ctx->h_ctr->n_pairs[0] = ctx->h_ctr->n_pairs[1] = 0;
         FQD_CUDA(cudaMemcpyAsync(ctx->d_ctr, ctx->h_ctr, sizeof(DevCounters), cudaMemcpyHostToDevice, s));
         iota_kernel<<<cdiv(U, 256), 256, 0, s>>>(f.parent_full, U);
         tt.launches++;
@@ -741,9 +738,6 @@ int run_sharded_typed(std::vector<Shard> &S, Exchange *ex, int world, const Code
             init_forest_kernel<<<cdiv(U, 256), 256, 0, s>>>(U, sh.f.parent_full, sh.f.parent_one, sh.f.best);
             sh.tt.launches++;
         }
-        FQD_TRY(arena(sh.ctx, std::max<uint32_t>(U, 1), &sh.f.pairs_full));
-        if (sh.job.method == METHOD_DIRECTIONAL) FQD_TRY(arena(sh.ctx, std::max<uint32_t>(U, 1), &sh.f.pairs_one));
-        FQD_CUDA(cudaMemsetAsync(sh.ctx->d_ctr->n_pairs, 0, 8, s));
         FQD_CUDA(cudaMemsetAsync(&sh.ctx->d_ctr->n_merges, 0, 4, s));
         FQD_CUDA(cudaMemsetAsync(&sh.ctx->d_ctr->n_edges, 0, 8, s));
         FQD_CUDA(cudaMemsetAsync(&sh.ctx->d_ctr->n_candidates, 0, 8, s));
@@ -757,13 +751,22 @@ int run_sharded_typed(std::vector<Shard> &S, Exchange *ex, int world, const Code
         if (which == 1 && method != METHOD_DIRECTIONAL) break;
         std::vector<std::vector<uint64_t>> mine(L, std::vector<uint64_t>(1));
         for (int i = 0; i < L; i++) {
-            // the hooks were recorded while the passes ran (PassParams::pairs_*)
             Shard &sh = S[i];
             FQD_CUDA(cudaSetDevice(sh.ctx->device));
-            FQD_TRY(fetch_counters(sh.ctx));
-            sh.pairs[which] = which == 0 ? sh.f.pairs_full : sh.f.pairs_one;
-            sh.n_pairs[which] = sh.ctx->h_ctr->n_pairs[which];
-            mine[i][0] = sh.n_pairs[which];
+            cudaStream_t s = sh.ctx->stream;
+            uint32_t *np;
+            FQD_TRY(arena(sh.ctx, std::max<uint32_t>(U, 1), &sh.pairs[which]));
+            FQD_TRY(arena(sh.ctx, 4, &np));
+            FQD_CUDA(cudaMemsetAsync(np, 0, 16, s));
+            const uint32_t *parent = which == 0 ? sh.f.parent_full : sh.f.parent_one;
+            if (U) forest_links_kernel<<<cdiv(U, 256), 256, 0, s>>>(U, parent, sh.pairs[which], np);
+            FQD_CUDA(cudaGetLastError());
+            uint32_t h = 0;
+            FQD_CUDA(cudaMemcpyAsync(&h, np, 4, cudaMemcpyDeviceToHost, s));
+            FQD_CUDA(cudaStreamSynchronize(s));
+            sh.n_pairs[which] = h;
+            mine[i][0] = h;
+            sh.tt.launches++;
         }
         std::vector<uint64_t> all;
         FQD_TRY(gather_host_u64(S, ex, world, 1, mine, all));

@@ -49,7 +49,6 @@ struct DevCounters {
     uint32_t undecided;
     uint32_t unknown[8];              // bitmap of key bytes outside the alphabet
     uint32_t len_min, len_max;
-    uint32_t n_pairs[2];              // sharded jobs: successful hooks recorded per forest
 };
 
 // ---- small device helpers -----------------------------------------------------------
@@ -540,8 +539,6 @@ struct PassParams {
     uint8_t *dead;
     uint2 *edges;
     unsigned long long edge_cap;
-    uint2 *pairs_full;      // sharded jobs: every successful hook (a spanning forest of this
-    uint2 *pairs_one;       // rank's edges), to be replayed on the other ranks
     DevCounters *ctr;
     uint8_t rank_of_code[256];
 };
@@ -626,18 +623,12 @@ __device__ __forceinline__ void process_edge(const PassParams &P, uint32_t ui, u
                                              uint32_t ci, uint32_t cj, const Key<K, PW> &ki,
                                              const Key<K, PW> &kj, uint32_t &merges)
 {
-    if (uf_union(P.parent_full, ui, uj)) {
-        merges++;
-        if (P.pairs_full) P.pairs_full[aggregated_inc(&P.ctr->n_pairs[0])] = make_uint2(ui, uj);
-    }
+    if (uf_union(P.parent_full, ui, uj)) merges++;
     if (P.method == METHOD_DIRECTIONAL) {
         // closed form of reference __init__.py:60-91 (DESIGN.md "directional")
         if (ci >= 2 && (unsigned long long)cj >= 2ull * ci - 1ull) P.dominated[ui] = 1;
         if (cj >= 2 && (unsigned long long)ci >= 2ull * cj - 1ull) P.dominated[uj] = 1;
-        if (ci == 1 && cj == 1) {
-            if (uf_union(P.parent_one, ui, uj) && P.pairs_one)
-                P.pairs_one[aggregated_inc(&P.ctr->n_pairs[1])] = make_uint2(ui, uj);
-        }
+        if (ci == 1 && cj == 1) uf_union(P.parent_one, ui, uj);
         else if (ci == 1) P.dead[ui] = 1;
         else if (cj == 1) P.dead[uj] = 1;
     } else if (P.method == METHOD_ADJACENCY) {
@@ -1095,7 +1086,16 @@ static __global__ void __launch_bounds__(256) gather_nonzero_kernel(uint32_t U, 
     ufirst[pos] = w[KW + 1];
 }
 
-// replay of the hooks another rank recorded (PassParams::pairs_*)
+// The parent links (u, parent[u]) of one rank's forest: the same connectivity as its edges, read
+// with one streaming pass (no find), to be replayed on every other rank.
+static __global__ void __launch_bounds__(256) forest_links_kernel(uint32_t U, const uint32_t *__restrict__ parent,
+                                                                  uint2 *pairs, uint32_t *n_pairs)
+{
+    const uint32_t u = blockIdx.x * 256u + threadIdx.x;
+    const uint32_t p = u < U ? __ldcs(parent + u) : u;
+    if (p != u) pairs[aggregated_inc(n_pairs)] = make_uint2(u, p);
+}
+
 static __global__ void __launch_bounds__(256) apply_pairs_kernel(uint32_t n, const uint2 *__restrict__ pairs,
                                                                  uint32_t *parent)
 {
