@@ -66,11 +66,12 @@ class ClusterStats(Structure):
         ("ms_total", c_float), ("ms_ingest", c_float), ("ms_gather", c_float),
         ("ms_neighbour", c_float), ("ms_select", c_float), ("ms_h2d", c_float),
         ("ms_compare", c_float), ("ms_ingest_kernel", c_float), ("ms_table_clear", c_float),
-        ("ms_bucket_build", c_float), ("launches", c_uint32), ("reserved_u", c_uint32),
+        ("ms_bucket_build", c_float), ("launches", c_uint32), ("plan_flags", c_uint32),
+        ("ms_partition_kernel", c_float), ("ms_dedupe_kernel", c_float),
     ]
 
     def as_dict(self):
-        return {name: getattr(self, name) for name, _ in self._fields_ if name != "reserved_u"}
+        return {name: getattr(self, name) for name, _ in self._fields_}
 
 
 # every symbol include/fqd_b200.h declares (tests/test_abi.py checks the library exports them)

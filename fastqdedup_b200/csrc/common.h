@@ -64,9 +64,6 @@ struct fqd_context {
     cudaEvent_t ev[12] = {};
     fqd_result res;
     int sm_count = 148;
-    // dedupe table of the running job (arena memory), handed from the ingest to the gather
-    uint32_t *scratch_table = nullptr;
-    uint32_t *scratch_uslot = nullptr;
 };
 
 namespace fqd {

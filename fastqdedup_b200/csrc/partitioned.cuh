@@ -1,0 +1,331 @@
+// partitioned.cuh -- the streaming plan for large jobs (included at the end of pipeline.cuh).
+//
+// Random probes into an HBM-sized hash table (the single-table plan) pay one 128-byte DRAM line
+// per record and sit at ~30 % of HBM bandwidth; a counting sort of the bucket entries pays
+// random 32-byte scatter writes.  For large jobs both stages are therefore rebuilt around ONE
+// idea: PARTITION the 32-byte records by the top hash bits so finely (TILE_R = 1024 records per
+// region, ~65 % full) that one partition is one SHARED-MEMORY TILE, then give every partition
+// to one thread block that stages it with coalesced streaming loads and does all the random
+// work -- hash probes, key compares, counting -- inside shared memory.  HBM only ever sees
+// streaming reads and writes; there is no table in HBM or L2 at all and no inter-block
+// synchronisation.
+//
+//   ingest_kernel (partition mode)  records -> nparts regions of {key, weight, record index}
+//                          (quality filter + packing + hashing fused; one atomic on the
+//                          partition cursor + one 256-bit store per record; replaces
+//                          average_error_rate + Trie.add_sequence, reference
+//                          _fastqmodule.c:38-76, _triemodule.c:222-288)
+//   dedupe_tile_kernel     one partition: open-addressing table of RECORD INDICES in shared
+//                          memory (the keys stay in the staged tile, so a slot is claimed with
+//                          one 32-bit CAS and is readable at once -- no lock, no fence); the
+//                          winners accumulate count and smallest index, then leave as the
+//                          dense unique arrays
+//   bucket_partition_kernel  uniques -> regions of {key, count, uid} by the hash of pigeonhole
+//                          block j
+//   bucket_tile_kernel     one partition: the same index table used as a MULTIMAP keyed by the
+//                          block hash: the inserting thread walks the probe sequence and tests
+//                          every entry it passes with XOR+POPC Hamming, so bucket build and
+//                          compare are one pass over a tile (replaces TrieNode_FindNearest /
+//                          pop_cluster, _triemodule.c:380-495, :778-897).  Hits set the
+//                          directional flags at once; the union-find hooks (random HBM accesses)
+//                          are deferred to apply_edges_kernel, which runs them at full occupancy.
+//
+// Skew: a partition that outgrows its region ("oversize": one key with thousands of copies)
+// sends the surplus to a spill buffer; oversize partitions and the spill are deduplicated by
+// the single-table kernels into the same dense arrays.  A Hamming pass whose buckets outgrow a
+// tile (few distinct block values) is redone by the counting-sort plan.
+#pragma once
+
+namespace fqd {
+
+constexpr int TILE_T = 2 * TILE_R;         // table entries per tile (load <= 0.5)
+constexpr int TILE_THREADS = 256;
+constexpr int TILE_E = 512;                // edges a tile buffers in shared memory before hooking inline
+constexpr uint32_t TILE_EMPTY = 0xFFFFFFFFu;
+constexpr uint32_t EDGE_ONE = 0x80000000u; // edge flag: both ends have count 1 (also joins the count-1 forest)
+
+__device__ __forceinline__ void stage_tile(uint32_t *recs, uint32_t *tab, const uint32_t *src, uint32_t cnt)
+{
+    const uint4 *s4 = reinterpret_cast<const uint4 *>(src);
+    uint4 *d4 = reinterpret_cast<uint4 *>(recs);
+    for (uint32_t i = threadIdx.x; i < cnt * (PART_RW / 4); i += TILE_THREADS) d4[i] = __ldcs(s4 + i);
+    for (uint32_t i = threadIdx.x; i < (uint32_t)TILE_T; i += TILE_THREADS) tab[i] = TILE_EMPTY;
+}
+
+__device__ __forceinline__ void tile_load_rec(const uint32_t *recs, uint32_t i, uint32_t (&e)[PART_RW])
+{
+    const uint4 *r4 = reinterpret_cast<const uint4 *>(recs + (size_t)i * PART_RW);
+    const uint4 a = r4[0], b = r4[1];
+    e[0] = a.x; e[1] = a.y; e[2] = a.z; e[3] = a.w; e[4] = b.x; e[5] = b.y; e[6] = b.z; e[7] = b.w;
+}
+
+// ---- stage A: exact dedupe of one partition --------------------------------------------------------
+
+struct DedupeOut {
+    uint32_t *ukey, *ucount, *ufirst;
+    uint32_t *n_unique;     // dense output cursor
+    uint32_t *oversize;     // list of partitions that outgrew their region (handled by the spill path)
+    uint32_t *n_oversize;
+    int keep_zero;          // sharded jobs keep keys whose every record was filtered (weight 0)
+};
+
+template <int K, int PW>
+static __global__ void __launch_bounds__(TILE_THREADS) dedupe_tile_kernel(const __grid_constant__ PartParams Q,
+                                                                          const __grid_constant__ DedupeOut O)
+{
+    constexpr int KW = K * PW, RW = slot_words(KW);
+    static_assert(RW == PART_RW, "partitioned plan: 32-byte records");
+    __shared__ __align__(16) uint32_t recs[TILE_R * PART_RW];
+    __shared__ uint32_t tab[TILE_T];
+    __shared__ uint32_t warp_sums[32];
+    __shared__ uint32_t total, s_base;
+    const uint32_t p = blockIdx.x, tid = threadIdx.x;
+    const uint32_t cnt = Q.cursor[p];
+    if (cnt == 0) return;
+    if (cnt > (uint32_t)TILE_R) {
+        if (tid == 0) O.oversize[atomicAdd(O.n_oversize, 1u)] = p;
+        return;
+    }
+    stage_tile(recs, tab, Q.buf + (size_t)p * TILE_R * PART_RW, cnt);
+    __syncthreads();
+
+    // A record either wins an empty table entry (it becomes the representative of its key) or
+    // meets the representative and adds its weight / lowers the first index there.
+    uint32_t rep = 0;   // bit r: my record of round r is a representative
+#pragma unroll
+    for (int r = 0; r < TILE_R / TILE_THREADS; r++) {
+        const uint32_t i = r * TILE_THREADS + tid;
+        if (i >= cnt) break;
+        uint32_t e[PART_RW];
+        tile_load_rec(recs, i, e);
+        Key<K, PW> key;
+#pragma unroll
+        for (int j = 0; j < KW; j++) key.w[j] = e[j];
+        uint32_t s = (uint32_t)hash_key(key) & (TILE_T - 1);
+        for (;;) {
+            uint32_t cur = *reinterpret_cast<volatile uint32_t *>(tab + s);
+            if (cur == TILE_EMPTY) {
+                cur = atomicCAS(tab + s, TILE_EMPTY, i);
+                if (cur == TILE_EMPTY) { rep |= 1u << r; break; }
+            }
+            const uint32_t *o = recs + (size_t)cur * PART_RW;
+            uint32_t diff = 0;
+#pragma unroll
+            for (int j = 0; j < KW; j++) diff |= o[j] ^ e[j];
+            if (diff == 0) {
+                if (e[KW]) atomicAdd(recs + (size_t)cur * PART_RW + KW, e[KW]);
+                atomicMin(recs + (size_t)cur * PART_RW + KW + 1, e[KW + 1]);
+                break;
+            }
+            s = (s + 1) & (TILE_T - 1);
+        }
+    }
+    __syncthreads();
+
+    // representatives -> dense unique arrays (keys whose every record was filtered are dropped)
+    uint32_t nval = 0;
+#pragma unroll
+    for (int r = 0; r < TILE_R / TILE_THREADS; r++) {
+        if (!((rep >> r) & 1u)) continue;
+        const uint32_t i = r * TILE_THREADS + tid;
+        if (recs[(size_t)i * PART_RW + KW] != 0 || O.keep_zero) nval++;
+        else rep &= ~(1u << r);
+    }
+    const uint32_t off = block_exclusive_scan(nval, &total, warp_sums);
+    if (tid == 0) s_base = total ? atomicAdd(O.n_unique, total) : 0u;
+    __syncthreads();
+    uint32_t pos = s_base + off;
+#pragma unroll
+    for (int r = 0; r < TILE_R / TILE_THREADS; r++) {
+        if (!((rep >> r) & 1u)) continue;
+        const uint32_t i = r * TILE_THREADS + tid;
+        uint32_t e[PART_RW];
+        tile_load_rec(recs, i, e);
+#pragma unroll
+        for (int j = 0; j < KW; j++) O.ukey[(size_t)pos * KW + j] = e[j];
+        O.ucount[pos] = e[KW];
+        O.ufirst[pos] = e[KW + 1];
+        pos++;
+    }
+}
+
+// Spill path: the records of the oversize partitions (their full regions, blockIdx.y picks one)
+// or of the spill buffer (list == null) go through the single-table insert.
+template <int K, int PW>
+static __global__ void __launch_bounds__(256) spill_insert_kernel(const uint32_t *__restrict__ recs, const uint32_t *__restrict__ list,
+                                                                  uint32_t n, const __grid_constant__ TableRef tab,
+                                                                  uint32_t *n_claimed)
+{
+    constexpr int KW = K * PW, RW = slot_words(KW);
+    static_assert(RW == PART_RW, "partitioned plan: 32-byte records");
+    const uint32_t i = blockIdx.x * 256u + threadIdx.x;
+    const uint32_t *src = list ? recs + (size_t)list[blockIdx.y] * TILE_R * PART_RW : recs;
+    uint32_t claimed = NO_CLAIM;
+    if (i < n) {
+        uint32_t e[PART_RW];
+        load_rec_stream(src + (size_t)i * PART_RW, e);
+        Key<K, PW> key;
+#pragma unroll
+        for (int j = 0; j < KW; j++) key.w[j] = e[j];
+        claimed = table_insert<K, PW>(tab, key, hash_key(key), e[KW + 1], e[KW]);
+    }
+    const uint32_t pos = block_reserve(claimed != NO_CLAIM, n_claimed);
+    if (claimed != NO_CLAIM) tab.uslot[pos] = claimed;
+}
+
+// ---- stage B: one Hamming pigeonhole pass -------------------------------------------------------------
+
+template <int K, int PW>
+static __global__ void __launch_bounds__(256) bucket_partition_kernel(const __grid_constant__ PassParams P,
+                                                                      const __grid_constant__ PartParams Q)
+{
+    constexpr int KW = K * PW, RW = fat_words(KW);
+    static_assert(RW == PART_RW, "partitioned plan: 32-byte records");
+    const uint32_t u = blockIdx.x * 256u + threadIdx.x;
+    if (u >= P.U) return;
+    Key<K, PW> key;
+    load_key_stream<K, PW>(P.ukey, u, key);
+    const uint32_t count = __ldcs(P.ucount + u);
+    const uint32_t len = P.varlen ? key_length(key, P.pad_code, P.max_len) : P.max_len;
+    uint64_t sig;
+    bool build;
+    pass_variant<K, PW>(key, len, P, 0, sig, build);
+    if (P.world > 1 && (uint32_t)(sig >> 32) % (uint32_t)P.world != (uint32_t)P.my_rank) return;
+    uint32_t e[RW];
+#pragma unroll
+    for (int i = 0; i < RW; i++) e[i] = 0;
+#pragma unroll
+    for (int i = 0; i < KW; i++) e[i] = key.w[i];
+    e[KW] = count;
+    e[KW + 1] = u;
+    part_append(Q, part_of(sig, Q.nparts), e);
+}
+
+struct EdgeSink {
+    uint2 *edges;          // (ui, uj | EDGE_ONE) pairs of this pass
+    uint32_t *n_edges;
+    uint32_t cap;
+    uint32_t *overflow;    // set when a partition outgrew its tile: the pass is redone by the counting-sort plan
+};
+
+// Multimap insert with comparison on the way: the probe sequence of an entry starts at the hash
+// of its pigeonhole block, so all entries of one bucket share it.  Of two entries of a bucket
+// the one that claims its table entry later has walked over the other one (entries are never
+// released), so every in-bucket pair is tested exactly once; entries of other buckets that
+// happen to lie on the walk are tested too, which is harmless (a hit is a true edge).
+template <int K, int PW>
+static __global__ void __launch_bounds__(TILE_THREADS) bucket_tile_kernel(const __grid_constant__ PartParams Q,
+                                                                          const __grid_constant__ PassParams P,
+                                                                          const __grid_constant__ EdgeSink E)
+{
+    constexpr int KW = K * PW, RW = fat_words(KW);
+    static_assert(RW == PART_RW, "partitioned plan: 32-byte records");
+    __shared__ __align__(16) uint32_t recs[TILE_R * PART_RW];
+    __shared__ uint32_t tab[TILE_T];
+    __shared__ uint2 s_edges[TILE_E];
+    __shared__ uint32_t s_nedges, s_base;
+    const uint32_t p = blockIdx.x, tid = threadIdx.x;
+    const uint32_t cnt = Q.cursor[p];
+    if (cnt == 0) return;
+    if (cnt > (uint32_t)TILE_R) {
+        if (tid == 0) *E.overflow = 1u;
+        return;
+    }
+    if (tid == 0) s_nedges = 0;
+    stage_tile(recs, tab, Q.buf + (size_t)p * TILE_R * PART_RW, cnt);
+    __syncthreads();
+
+    uint32_t merges = 0, cand = 0;
+#pragma unroll 1
+    for (uint32_t i = tid; i < cnt; i += TILE_THREADS) {
+        uint32_t e[PART_RW];
+        tile_load_rec(recs, i, e);
+        Key<K, PW> ki;
+#pragma unroll
+        for (int j = 0; j < KW; j++) ki.w[j] = e[j];
+        const uint32_t ci = e[KW], ui = e[KW + 1];
+        const uint32_t len = P.varlen ? key_length(ki, P.pad_code, P.max_len) : P.max_len;
+        uint64_t sig;
+        bool build;
+        pass_variant<K, PW>(ki, len, P, 0, sig, build);
+        uint32_t s = (uint32_t)sig & (TILE_T - 1);
+        for (;;) {
+            uint32_t cur = *reinterpret_cast<volatile uint32_t *>(tab + s);
+            if (cur == TILE_EMPTY) {
+                cur = atomicCAS(tab + s, TILE_EMPTY, i);
+                if (cur == TILE_EMPTY) break;
+            }
+            uint32_t f[PART_RW];
+            tile_load_rec(recs, cur, f);
+            Key<K, PW> kj;
+#pragma unroll
+            for (int j = 0; j < KW; j++) kj.w[j] = f[j];
+            cand++;
+            if (hamming_within<K, PW>(ki, kj, P.d, P.varlen != 0, P.pad_code)) {
+                const uint32_t cj = f[KW], uj = f[KW + 1];
+                uint32_t flag = 0;
+                if (P.method == METHOD_DIRECTIONAL) {
+                    // closed form of reference __init__.py:60-91 (DESIGN.md "directional")
+                    if (ci >= 2 && (unsigned long long)cj >= 2ull * ci - 1ull) P.dominated[ui] = 1;
+                    if (cj >= 2 && (unsigned long long)ci >= 2ull * cj - 1ull) P.dominated[uj] = 1;
+                    if (ci == 1 && cj == 1) flag = EDGE_ONE;
+                    else if (ci == 1) P.dead[ui] = 1;
+                    else if (cj == 1) P.dead[uj] = 1;
+                } else if (P.method == METHOD_ADJACENCY) {
+                    const bool i_less = prio_less<K, PW>(ci, ki, cj, kj, P.rank_of_code);
+                    const unsigned long long pos = aggregated_inc64(&P.ctr->n_edges);
+                    if (pos < P.edge_cap) P.edges[pos] = i_less ? make_uint2(uj, ui) : make_uint2(ui, uj);
+                }
+                const uint32_t pos = atomicAdd(&s_nedges, 1u);
+                if (pos < (uint32_t)TILE_E) {
+                    s_edges[pos] = make_uint2(ui, uj | flag);
+                } else {   // dense tile: hook right here
+                    if (uf_union(P.parent_full, ui, uj)) merges++;
+                    if (flag) uf_union(P.parent_one, ui, uj);
+                }
+            }
+            s = (s + 1) & (TILE_T - 1);
+        }
+    }
+    __syncthreads();
+    const uint32_t ne = min(s_nedges, (uint32_t)TILE_E);
+    if (tid == 0) s_base = ne ? atomicAdd(E.n_edges, ne) : 0u;
+    __syncthreads();
+    for (uint32_t k = tid; k < ne; k += TILE_THREADS) {
+        const uint32_t pos = s_base + k;
+        const uint2 ed = s_edges[k];
+        if (pos < E.cap) {
+            E.edges[pos] = ed;
+        } else {
+            const uint32_t uj = ed.y & ~EDGE_ONE;
+            if (uf_union(P.parent_full, ed.x, uj)) merges++;
+            if (ed.y & EDGE_ONE) uf_union(P.parent_one, ed.x, uj);
+        }
+    }
+    for (int o = 16; o; o >>= 1) {
+        merges += __shfl_xor_sync(WARP_FULL, merges, o);
+        cand += __shfl_xor_sync(WARP_FULL, cand, o);
+    }
+    if ((tid & 31) == 0) {
+        if (merges) atomicAdd(&P.ctr->n_merges, merges);
+        if (cand) atomicAdd(&P.ctr->n_candidates, (unsigned long long)cand);
+    }
+}
+
+static __global__ void __launch_bounds__(256) apply_edges_kernel(const uint2 *__restrict__ edges, const uint32_t *__restrict__ n_edges,
+                                                                 uint32_t cap, uint32_t *parent_full, uint32_t *parent_one,
+                                                                 DevCounters *ctr)
+{
+    const uint32_t n = min(*n_edges, cap);
+    uint32_t merges = 0;
+    for (uint32_t i = blockIdx.x * 256u + threadIdx.x; i < n; i += gridDim.x * 256u) {
+        const uint2 ed = __ldcs(edges + i);
+        const uint32_t uj = ed.y & ~EDGE_ONE;
+        if (uf_union(parent_full, ed.x, uj)) merges++;
+        if (ed.y & EDGE_ONE) uf_union(parent_one, ed.x, uj);
+    }
+    for (int o = 16; o; o >>= 1) merges += __shfl_xor_sync(WARP_FULL, merges, o);
+    if ((threadIdx.x & 31) == 0 && merges) atomicAdd(&ctr->n_merges, merges);
+}
+
+}  // namespace fqd

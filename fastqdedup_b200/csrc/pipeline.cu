@@ -64,9 +64,9 @@ struct Forest {
 };
 
 struct StageTimes {
-    float table_clear = 0, ingest_kernel = 0, ingest = 0, compare = 0, h2d = 0;
+    float table_clear = 0, ingest_kernel = 0, dedupe_kernel = 0, ingest = 0, compare = 0, h2d = 0;
     uint32_t launches = 0;
-    bool streamed = false;
+    bool streamed = false, partitioned = false, passes_partitioned = false;
 };
 
 template <typename T>
@@ -79,8 +79,85 @@ int arena(fqd_context *ctx, size_t count, T **p)
 }
 
 // ---- stage 1: filter + pack + exact dedupe of this rank's records ----------------------------
-// Leaves the table in ctx->scratch_table / scratch_uslot for the gather and allocates the
-// dense arrays of `uq` (U entries).
+// Produces the dense unique arrays of `uq`.  Large jobs take the partitioned plan (streaming,
+// L2-resident tables); small ones, and jobs whose duplication is so skewed that a partition
+// overflows, take the single-table plan.
+
+// Launches `kernel(params)` over the records: in one go when they are in HBM, chunk by chunk
+// behind the H2D copies when they are still in host memory.
+template <typename Launch>
+int for_each_input_chunk(fqd_context *ctx, const DeviceJob &job, IngestParams ip, uint32_t index_base,
+                         uint32_t *keepmask, StageTimes &tt, Launch launch)
+{
+    cudaStream_t s = ctx->stream;
+    const uint64_t n = job.n;
+    if (!n) return FQD_OK;
+    if (!job.host_keys) {
+        launch(ip);
+        tt.launches++;
+        return FQD_OK;
+    }
+    // H2D of chunk i+1 overlaps the work on chunk i (PCIe is the e2e bottleneck)
+    const uint64_t chunk = 4u << 20;   // records; a multiple of every block tile and of 32
+    const size_t nchunks = (size_t)((n + chunk - 1) / chunk);
+    while (ctx->chunk_events.size() < nchunks) {
+        cudaEvent_t e;
+        FQD_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        ctx->chunk_events.push_back(e);
+    }
+    FQD_CUDA(cudaEventRecord(ctx->ev[9], s));
+    FQD_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev[9], 0));   // buffers are allocated / idle
+    FQD_CUDA(cudaEventRecord(ctx->ev[10], ctx->copy_stream));
+    for (size_t i = 0; i < nchunks; i++) {
+        const uint64_t c0 = i * chunk, cn = std::min<uint64_t>(chunk, n - c0);
+        FQD_CUDA(cudaMemcpyAsync(const_cast<uint8_t *>(job.keys) + c0 * job.key_stride,
+                                 job.host_keys + c0 * job.key_stride, cn * job.key_stride,
+                                 cudaMemcpyHostToDevice, ctx->copy_stream));
+        if (job.host_quals)
+            FQD_CUDA(cudaMemcpyAsync(const_cast<uint8_t *>(job.quals) + c0 * job.qual_stride,
+                                     job.host_quals + c0 * job.qual_stride, cn * job.qual_stride,
+                                     cudaMemcpyHostToDevice, ctx->copy_stream));
+        FQD_CUDA(cudaEventRecord(ctx->chunk_events[i], ctx->copy_stream));
+        FQD_CUDA(cudaStreamWaitEvent(s, ctx->chunk_events[i], 0));
+        IngestParams cp = ip;
+        cp.n = cn;
+        cp.keys = job.keys + c0 * job.key_stride;
+        cp.key_lens = job.key_lens ? job.key_lens + c0 : nullptr;
+        cp.quals = job.quals ? job.quals + c0 * job.qual_stride : nullptr;
+        cp.qual_lens = job.qual_lens ? job.qual_lens + c0 : nullptr;
+        cp.keepmask = keepmask ? keepmask + c0 / 32 : nullptr;
+        cp.weights = job.weights ? job.weights + c0 : nullptr;
+        cp.index_base = index_base + (uint32_t)c0;
+        launch(cp);
+        tt.launches++;
+    }
+    FQD_CUDA(cudaEventRecord(ctx->ev[11], ctx->copy_stream));
+    tt.streamed = true;
+    return FQD_OK;
+}
+
+// the ASCII-bits code of pack_key_acgtn (api.cu make_codec): the table-free packer applies
+bool codec_is_dna(const Codec &c)
+{
+    return c.bits == 3 && c.n_symbols == 5 && c.pad_code == SWAR_PAD_CODE && c.lut['A'] == 0 && c.lut['C'] == 1 &&
+           c.lut['T'] == 2 && c.lut['G'] == 3 && c.lut['N'] == 7;
+}
+
+uint32_t env_u32(const char *name, uint32_t fallback)
+{
+    const char *e = getenv(name);
+    return e && *e ? (uint32_t)strtoul(e, nullptr, 10) : fallback;
+}
+
+// partitions of the streaming plan: regions of TILE_R records filled to ~65 % on average
+uint32_t tile_partitions(uint64_t n)
+{
+    const uint32_t fill_pct = std::min(90u, std::max(20u, env_u32("FQD_TILE_FILL_PCT", 65)));
+    return (uint32_t)std::max<uint64_t>(1, (n * 100 + (uint64_t)TILE_R * fill_pct - 1) / ((uint64_t)TILE_R * fill_pct));
+}
+
+constexpr uint64_t PARTITION_MIN_RECORDS = 4u << 20;
+constexpr uint64_t PARTITION_MIN_UNIQUES = 1u << 20;
 
 template <int K, int PW>
 int stage_dedupe(fqd_context *ctx, const DeviceJob &job, const Codec &codec, uint32_t index_base,
@@ -90,21 +167,7 @@ int stage_dedupe(fqd_context *ctx, const DeviceJob &job, const Codec &codec, uin
     constexpr int KW = K * PW, RW = slot_words(KW);
     cudaStream_t s = ctx->stream;
     const uint64_t n = job.n;
-    FQD_TRY(reset_counters(ctx));
     cudaEvent_t *ev = ctx->ev;
-    FQD_CUDA(cudaEventRecord(ev[0], s));
-
-    const uint64_t capacity = std::max<uint64_t>(1024, n + (n >> 1) + 64);
-    if (capacity >= 0xFFFFFFF0ull) {
-        set_error("too many records for one job on one GPU (%llu)", (unsigned long long)n);
-        return FQD_ERR_UNSUPPORTED;
-    }
-    uint32_t *table, *uslot, *keepmask;
-    FQD_TRY(arena(ctx, capacity * RW, &table));
-    FQD_TRY(arena(ctx, std::max<uint64_t>(n, 1), &uslot));
-    FQD_TRY(arena(ctx, cdiv(std::max<uint64_t>(n, 1), 32), &keepmask));
-    FQD_CUDA(cudaMemsetAsync(table, 0xFF, capacity * RW * sizeof(uint32_t), s));
-    FQD_CUDA(cudaEventRecord(ev[1], s));
 
     IngestParams ip{};
     ip.n = n;
@@ -117,85 +180,171 @@ int stage_dedupe(fqd_context *ctx, const DeviceJob &job, const Codec &codec, uin
     ip.max_err = job.max_err;
     ip.phred_offset = job.phred_offset;
     ip.pad_code = codec.pad_code;
-    ip.tab.table = table; ip.tab.capacity = capacity; ip.tab.uslot = uslot; ip.tab.ctr = ctx->d_ctr;
-    ip.keepmask = keepmask;
     ip.weights = job.weights;
     ip.index_base = index_base;
     ip.sharded = sharded ? 1 : 0;
     ip.ctr = ctx->d_ctr;
     ip.codec = codec;
-    // shared-memory staging of fixed-stride rows
     uint32_t stride = 0;
     if (!job.key_off) stride = job.key_stride;
     if (job.filter_on && !job.qual_off) stride = std::max(stride, job.qual_stride);
     const bool fixed_any = !job.key_off || (job.filter_on && !job.qual_off);
-    size_t smem = 1280;
+
+    auto check_input_errors = [&](const DevCounters &c, bool &retry) -> int {
+        retry = false;
+        bool any_unknown = false;
+        for (int i = 0; i < 8; i++) { unknown_out[i] = c.unknown[i]; any_unknown |= c.unknown[i] != 0; }
+        st->bad_record = ~0ull;
+        if (c.phred_err != ~0ull) {
+            st->bad_record = c.phred_err >> 8;
+            st->bad_char = (uint32_t)(c.phred_err & 0xFF);
+            if (!sharded) {
+                set_error("Character %c outside of valid phred range ('%c' to '%c')",
+                          (int)st->bad_char, (int)job.phred_offset, 126);
+                return FQD_ERR_PHRED;
+            }
+        }
+        if (any_unknown && !sharded) retry = true;
+        return FQD_OK;
+    };
+    auto finish = [&](const DevCounters &c, uint32_t U) {
+        st->total_records = n;
+        st->discarded_records = c.n_discarded;
+        st->number_of_sequences = job.weights ? c.sum_weights : n - c.n_discarded;
+        uq.U = U;
+    };
+
+    // ================= streaming plan (partitioned.cuh) =================
+    const size_t plan_mark = arena_mark(ctx);
+    if constexpr (RW == PART_RW) {
+        uint64_t part_min = PARTITION_MIN_RECORDS;
+        if (const char *e = getenv("FQD_PARTITION_MIN")) part_min = strtoull(e, nullptr, 10);   // tests
+        if (n >= part_min && n > 0 && !getenv("FQD_NO_PARTITION")) {
+            FQD_TRY(reset_counters(ctx));
+            FQD_CUDA(cudaEventRecord(ev[0], s));
+            const uint32_t nparts = tile_partitions(n);
+            const uint32_t spill_cap = (uint32_t)(n / 8 + 4096);
+            uint32_t *buf, *cursor, *spill, *aux, *oversize;
+            FQD_TRY(arena(ctx, (size_t)nparts * TILE_R * RW, &buf));
+            FQD_TRY(arena(ctx, nparts, &cursor));
+            FQD_TRY(arena(ctx, (size_t)spill_cap * RW, &spill));
+            FQD_TRY(arena(ctx, 8, &aux));   // [0] spill count, [1] spill overflow, [2] dense uniques, [3] oversize partitions
+            FQD_TRY(arena(ctx, nparts, &oversize));
+            FQD_TRY(arena(ctx, n * KW, &uq.ukey));      // worst case: every record distinct
+            FQD_TRY(arena(ctx, n, &uq.ucount));
+            FQD_TRY(arena(ctx, n, &uq.ufirst));
+            FQD_CUDA(cudaMemsetAsync(cursor, 0, (size_t)nparts * 4, s));
+            FQD_CUDA(cudaMemsetAsync(aux, 0, 32, s));
+            FQD_CUDA(cudaEventRecord(ev[1], s));
+            constexpr uint32_t BR = 256u * INGEST_ROWS;   // records per block
+            IngestParams pp = ip;
+            pp.part = PartParams{buf, cursor, nparts, spill, aux, spill_cap};
+            pp.phase = 0;
+            pp.codec.swar = codec.swar || (K == 3 && codec_is_dna(codec) && !getenv("FQD_NO_SWAR"));
+            size_t smem = 1280;
+            if (fixed_any && (size_t)stride * BR + 1280 <= 200 * 1024) {
+                pp.stage_bytes = stride * BR;
+                smem += pp.stage_bytes;
+            }
+            FQD_CUDA(cudaFuncSetAttribute(ingest_kernel<K, PW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            FQD_TRY(for_each_input_chunk(ctx, job, pp, index_base, nullptr, tt, [&](const IngestParams &cp) {
+                ingest_kernel<K, PW><<<cdiv(cp.n, BR), 256, smem, s>>>(cp);
+            }));
+            FQD_CUDA(cudaGetLastError());
+            FQD_CUDA(cudaEventRecord(ev[2], s));
+            DedupeOut out{uq.ukey, uq.ucount, uq.ufirst, aux + 2, oversize, aux + 3, sharded ? 1 : 0};
+            dedupe_tile_kernel<K, PW><<<nparts, TILE_THREADS, 0, s>>>(pp.part, out);
+            tt.launches++;
+            FQD_CUDA(cudaGetLastError());
+            FQD_CUDA(cudaEventRecord(ev[3], s));
+            uint32_t h_aux[4] = {};
+            FQD_CUDA(cudaMemcpyAsync(h_aux, aux, sizeof h_aux, cudaMemcpyDeviceToHost, s));
+            FQD_TRY(fetch_counters(ctx));
+            const DevCounters c1 = *ctx->h_ctr;
+            bool retry = false;
+            FQD_TRY(check_input_errors(c1, retry));
+            if (retry) return RC_RETRY_ALPHABET;
+            if (!h_aux[1]) {
+                uint32_t U = h_aux[2];
+                if (h_aux[3]) {
+                    // oversize partitions + their spilled records: single-table dedupe, appended to the dense arrays
+                    const uint32_t n_over = h_aux[3], n_spill = h_aux[0];
+                    const uint64_t n_rec = (uint64_t)n_over * TILE_R + n_spill;
+                    const uint64_t capacity = n_rec + (n_rec >> 1) + 1024;
+                    uint32_t *table, *uslot;
+                    FQD_TRY(arena(ctx, capacity * RW, &table));
+                    FQD_TRY(arena(ctx, n_rec, &uslot));
+                    FQD_CUDA(cudaMemsetAsync(table, 0xFF, capacity * RW * 4, s));
+                    FQD_CUDA(cudaMemsetAsync(aux + 4, 0, 4, s));
+                    const TableRef tr{table, capacity, uslot, ctx->d_ctr};
+                    spill_insert_kernel<K, PW><<<dim3(TILE_R / 256, n_over), 256, 0, s>>>(buf, oversize, TILE_R, tr, aux + 4);
+                    if (n_spill) spill_insert_kernel<K, PW><<<cdiv(n_spill, 256), 256, 0, s>>>(spill, nullptr, n_spill, tr, aux + 4);
+                    uint32_t n_claimed = 0;
+                    FQD_CUDA(cudaMemcpyAsync(&n_claimed, aux + 4, 4, cudaMemcpyDeviceToHost, s));
+                    FQD_CUDA(cudaStreamSynchronize(s));
+                    if (n_claimed)
+                        gather_nonzero_kernel<K, PW><<<cdiv(n_claimed, 256), 256, 0, s>>>(n_claimed, table, uslot, uq.ukey, uq.ucount,
+                                                                                           uq.ufirst, aux + 2, sharded ? 1 : 0);
+                    FQD_CUDA(cudaGetLastError());
+                    FQD_CUDA(cudaEventRecord(ev[3], s));
+                    FQD_CUDA(cudaMemcpyAsync(&U, aux + 2, 4, cudaMemcpyDeviceToHost, s));
+                    FQD_TRY(fetch_counters(ctx));
+                    if (ctx->h_ctr->table_full) { set_error("internal: spill table overflow"); return FQD_ERR_NOMEM; }
+                    tt.launches += 3;
+                }
+                finish(c1, U);
+                cudaEventElapsedTime(&tt.table_clear, ev[0], ev[1]);
+                cudaEventElapsedTime(&tt.ingest_kernel, ev[1], ev[2]);
+                cudaEventElapsedTime(&tt.dedupe_kernel, ev[2], ev[3]);
+                cudaEventElapsedTime(&tt.ingest, ev[0], ev[3]);
+                if (tt.streamed) {
+                    FQD_CUDA(cudaEventSynchronize(ctx->ev[11]));
+                    cudaEventElapsedTime(&tt.h2d, ctx->ev[10], ctx->ev[11]);
+                }
+                st->ms_h2d = tt.h2d;
+                tt.partitioned = true;
+                return FQD_OK;
+            }
+            // the spill buffer overflowed (a few keys dominate the input): single-table plan instead
+            arena_release(ctx, plan_mark);
+            tt.launches = 0;
+        }
+    }
+
+    // ================= single-table plan =================
+    FQD_TRY(reset_counters(ctx));
+    FQD_CUDA(cudaEventRecord(ev[0], s));
+    const uint64_t capacity = std::max<uint64_t>(1024, n + (n >> 1) + 64);
+    if (capacity >= 0xFFFFFFF0ull) {
+        set_error("too many records for one job on one GPU (%llu)", (unsigned long long)n);
+        return FQD_ERR_UNSUPPORTED;
+    }
+    uint32_t *table, *uslot, *keepmask;
+    FQD_TRY(arena(ctx, capacity * RW, &table));
+    FQD_TRY(arena(ctx, std::max<uint64_t>(n, 1), &uslot));
+    FQD_TRY(arena(ctx, cdiv(std::max<uint64_t>(n, 1), 32), &keepmask));
+    FQD_CUDA(cudaMemsetAsync(table, 0xFF, capacity * RW * sizeof(uint32_t), s));
+    FQD_CUDA(cudaEventRecord(ev[1], s));
+    ip.tab.table = table; ip.tab.capacity = capacity; ip.tab.uslot = uslot; ip.tab.ctr = ctx->d_ctr;
+    ip.keepmask = keepmask;
     constexpr uint32_t BR = 256u * INGEST_ROWS;   // records per block
+    size_t smem = 1280;
     if (fixed_any && (size_t)stride * BR + 1280 <= 200 * 1024) {
         ip.stage_bytes = stride * BR;
         smem += ip.stage_bytes;
     }
-    FQD_CUDA(cudaFuncSetAttribute(ingest_kernel<K, PW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)smem));
+    FQD_CUDA(cudaFuncSetAttribute(ingest_kernel<K, PW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ip.phase = 0;
-    if (n && job.host_keys) {
-        // H2D of chunk i+1 overlaps the ingest of chunk i (PCIe is the e2e bottleneck)
-        const uint64_t chunk = 4u << 20;   // records; a multiple of 256 and of 32
-        const size_t nchunks = (size_t)((n + chunk - 1) / chunk);
-        while (ctx->chunk_events.size() < nchunks) {
-            cudaEvent_t e;
-            FQD_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-            ctx->chunk_events.push_back(e);
-        }
-        FQD_CUDA(cudaEventRecord(ctx->ev[9], s));
-        FQD_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev[9], 0));   // buffers are allocated / idle
-        FQD_CUDA(cudaEventRecord(ctx->ev[10], ctx->copy_stream));
-        IngestParams cp = ip;
-        for (size_t i = 0; i < nchunks; i++) {
-            const uint64_t c0 = i * chunk, cn = std::min<uint64_t>(chunk, n - c0);
-            FQD_CUDA(cudaMemcpyAsync(const_cast<uint8_t *>(job.keys) + c0 * job.key_stride,
-                                     job.host_keys + c0 * job.key_stride, cn * job.key_stride,
-                                     cudaMemcpyHostToDevice, ctx->copy_stream));
-            if (job.host_quals)
-                FQD_CUDA(cudaMemcpyAsync(const_cast<uint8_t *>(job.quals) + c0 * job.qual_stride,
-                                         job.host_quals + c0 * job.qual_stride, cn * job.qual_stride,
-                                         cudaMemcpyHostToDevice, ctx->copy_stream));
-            FQD_CUDA(cudaEventRecord(ctx->chunk_events[i], ctx->copy_stream));
-            FQD_CUDA(cudaStreamWaitEvent(s, ctx->chunk_events[i], 0));
-            cp.n = cn;
-            cp.keys = job.keys + c0 * job.key_stride;
-            cp.key_lens = job.key_lens ? job.key_lens + c0 : nullptr;
-            cp.quals = job.quals ? job.quals + c0 * job.qual_stride : nullptr;
-            cp.qual_lens = job.qual_lens ? job.qual_lens + c0 : nullptr;
-            cp.keepmask = keepmask + c0 / 32;
-            cp.weights = job.weights ? job.weights + c0 : nullptr;
-            cp.index_base = index_base + (uint32_t)c0;
-            ingest_kernel<K, PW><<<cdiv(cn, BR), 256, smem, s>>>(cp);
-            tt.launches++;
-        }
-        FQD_CUDA(cudaEventRecord(ctx->ev[11], ctx->copy_stream));
-        tt.streamed = true;
-    } else if (n) {
-        ingest_kernel<K, PW><<<cdiv(n, BR), 256, smem, s>>>(ip);
-        tt.launches++;
-    }
+    FQD_TRY(for_each_input_chunk(ctx, job, ip, index_base, keepmask, tt, [&](const IngestParams &cp) {
+        ingest_kernel<K, PW><<<cdiv(cp.n, BR), 256, smem, s>>>(cp);
+    }));
     FQD_CUDA(cudaEventRecord(ev[2], s));
     FQD_CUDA(cudaGetLastError());
     FQD_TRY(fetch_counters(ctx));
     const DevCounters c1 = *ctx->h_ctr;
-    bool any_unknown = false;
-    for (int i = 0; i < 8; i++) { unknown_out[i] = c1.unknown[i]; any_unknown |= c1.unknown[i] != 0; }
-    st->bad_record = ~0ull;
-    if (c1.phred_err != ~0ull) {
-        st->bad_record = c1.phred_err >> 8;
-        st->bad_char = (uint32_t)(c1.phred_err & 0xFF);
-        if (!sharded) {
-            set_error("Character %c outside of valid phred range ('%c' to '%c')",
-                      (int)st->bad_char, (int)job.phred_offset, 126);
-            return FQD_ERR_PHRED;
-        }
-    }
-    if (any_unknown && !sharded) return RC_RETRY_ALPHABET;
+    bool retry = false;
+    FQD_TRY(check_input_errors(c1, retry));
+    if (retry) return RC_RETRY_ALPHABET;
     if (c1.table_full) { set_error("internal: dedupe table overflow"); return FQD_ERR_NOMEM; }
     if (job.filter_on && c1.n_discarded && !sharded) {
         ip.phase = 1;
@@ -203,18 +352,18 @@ int stage_dedupe(fqd_context *ctx, const DeviceJob &job, const Codec &codec, uin
         tt.launches++;
         FQD_CUDA(cudaGetLastError());
     }
-    FQD_CUDA(cudaEventRecord(ev[3], s));
     const uint32_t U = c1.n_unique;
-    st->total_records = n;
-    st->discarded_records = c1.n_discarded;
-    st->number_of_sequences = job.weights ? c1.sum_weights : n - c1.n_discarded;
-
-    uq.U = U;
+    finish(c1, U);
     FQD_TRY(arena(ctx, (size_t)U * KW, &uq.ukey));
     FQD_TRY(arena(ctx, U, &uq.ucount));
     FQD_TRY(arena(ctx, U, &uq.ufirst));
-    ctx->scratch_table = table;
-    ctx->scratch_uslot = uslot;
+    if (U) {
+        gather_kernel<K, PW><<<cdiv(U, 256), 256, 0, s>>>(U, table, uslot, uq.ukey, uq.ucount, uq.ufirst,
+                                                          nullptr, nullptr, nullptr);
+        tt.launches++;
+    }
+    FQD_CUDA(cudaGetLastError());
+    FQD_CUDA(cudaEventRecord(ev[3], s));
     FQD_CUDA(cudaEventSynchronize(ev[3]));
     cudaEventElapsedTime(&tt.table_clear, ev[0], ev[1]);
     cudaEventElapsedTime(&tt.ingest_kernel, ev[1], ev[2]);
@@ -267,42 +416,100 @@ int stage_passes(fqd_context *ctx, const DeviceJob &job, const Codec &codec, con
     const int V = job.edit ? (job.varlen ? 2 * job.d + 1 : 1) * (job.d + 1) : 1;
     const uint64_t E = (uint64_t)U * V;
     if (E >= 0xFFFFFFF0ull) { set_error("too many pigeonhole entries (%llu)", (unsigned long long)E); return FQD_ERR_UNSUPPORTED; }
-    uint32_t NB = 1024;
-    while (NB < (1u << 24) && NB < E / 2) NB <<= 1;
     const bool fat = !job.edit;
-    uint32_t *cnt, *rank_arr, *entries, *block_sums, *grand;
-    FQD_TRY(arena(ctx, (size_t)NB + 1, &cnt));
-    FQD_TRY(arena(ctx, E, &rank_arr));
-    FQD_TRY(arena(ctx, fat ? E * FW : E * 2, &entries));
-    FQD_TRY(arena(ctx, (size_t)cdiv(NB, SCAN_TILE) + 16, &block_sums));
-    FQD_TRY(arena(ctx, 4, &grand));
     PassParams pp{};
     pp.U = U; pp.ukey = uq.ukey; pp.ucount = uq.ucount;
     pp.d = job.d; pp.edit = job.edit; pp.varlen = job.varlen ? 1 : 0; pp.method = job.method;
     pp.max_len = job.max_len; pp.pad_code = codec.pad_code;
-    pp.V = V; pp.nb_mask = NB - 1; pp.my_rank = rank; pp.world = world;
-    pp.cnt = cnt; pp.rank = rank_arr; pp.entries = reinterpret_cast<uint2 *>(entries); pp.fat = entries;
+    pp.V = V; pp.my_rank = rank; pp.world = world;
     pp.parent_full = f.parent_full; pp.parent_one = f.parent_one;
     pp.dominated = f.dominated; pp.dead = f.dead;
     pp.edges = f.edges; pp.edge_cap = f.edge_cap; pp.ctr = ctx->d_ctr;
     for (int i = 0; i < 256; i++) pp.rank_of_code[i] = codec.rank[i];
     std::vector<cudaEvent_t> cev(2 * npass);
     for (auto &e : cev) FQD_CUDA(cudaEventCreate(&e));
+
+    // Hamming passes of large jobs: partition by the block hash, multimap in L2 (partitioned.cuh)
+    bool use_part = false;
+    if constexpr (FW == PART_RW) {
+        uint64_t part_min = PARTITION_MIN_UNIQUES;
+        if (const char *e = getenv("FQD_PARTITION_MIN")) part_min = strtoull(e, nullptr, 10);   // tests
+        use_part = fat && U >= part_min && !getenv("FQD_NO_PARTITION") && !getenv("FQD_NO_PARTITION_PASSES");
+    }
+    const uint32_t own_avg = U / (uint32_t)std::max(world, 1);   // entries this rank's buckets receive
+    const uint32_t nparts = tile_partitions(own_avg);
+    uint32_t *pbuf = nullptr, *pcursor = nullptr, *paux = nullptr;   // paux per pass: [0] edge count, [1] overflow flag
+    EdgeSink sink{};
+    if (use_part) {
+        FQD_TRY(arena(ctx, (size_t)nparts * TILE_R * FW, &pbuf));
+        FQD_TRY(arena(ctx, (size_t)npass * nparts, &pcursor));
+        FQD_TRY(arena(ctx, (size_t)npass * 4, &paux));
+        sink.cap = (uint32_t)std::min<uint64_t>(0xFFFFFFF0ull, (uint64_t)U + (1u << 16));
+        FQD_TRY(arena(ctx, (size_t)sink.cap, &sink.edges));
+    }
+
+    // legacy plan (small jobs, Levenshtein, skewed buckets): counting sort by block hash + compare
+    uint32_t NB = 1024;
+    while (NB < (1u << 24) && NB < E / 2) NB <<= 1;
+    uint32_t *cnt = nullptr, *rank_arr = nullptr, *entries = nullptr, *block_sums = nullptr, *grand = nullptr;
+    auto legacy_alloc = [&]() -> int {
+        if (cnt) return FQD_OK;
+        FQD_TRY(arena(ctx, (size_t)NB + 1, &cnt));
+        FQD_TRY(arena(ctx, E, &rank_arr));
+        FQD_TRY(arena(ctx, fat ? E * FW : E * 2, &entries));
+        FQD_TRY(arena(ctx, (size_t)cdiv(NB, SCAN_TILE) + 16, &block_sums));
+        FQD_TRY(arena(ctx, 4, &grand));
+        pp.nb_mask = NB - 1;
+        pp.cnt = cnt; pp.rank = rank_arr; pp.entries = reinterpret_cast<uint2 *>(entries); pp.fat = entries;
+        return FQD_OK;
+    };
+    auto legacy_pass = [&](int j) -> int {
+        FQD_TRY(legacy_alloc());
+        pp.pass_j = j;
+        FQD_CUDA(cudaMemsetAsync(cnt, 0, ((size_t)NB + 1) * 4, s));
+        sig_count_kernel<K, PW><<<cdiv(U, 256), 256, 0, s>>>(pp);
+        FQD_TRY(exclusive_scan_inplace(ctx, cnt, NB, block_sums, grand));
+        if (fat) scatter_fat_kernel<K, PW><<<cdiv(U, 256), 256, 0, s>>>(pp);
+        else scatter_kernel<K, PW><<<cdiv(U, 256), 256, 0, s>>>(pp);
+        pp.n_entries = (uint32_t)E;   // upper bound; the kernel stops at cnt[NB]
+        tt.launches += 6;             // sig_count, 3 scan kernels, scatter, compare
+        FQD_CUDA(cudaEventRecord(cev[2 * j], s));
+        if (fat) compare_fat_kernel<K, PW><<<cdiv(E, 256), 256, 0, s>>>(pp);
+        else compare_kernel<K, PW><<<cdiv(E, 256), 256, 0, s>>>(pp);
+        FQD_CUDA(cudaEventRecord(cev[2 * j + 1], s));
+        FQD_CUDA(cudaGetLastError());
+        return FQD_OK;
+    };
+
     for (int attempt = 0; attempt < 2; attempt++) {
-        for (int j = 0; j < npass; j++) {
-            pp.pass_j = j;
-            FQD_CUDA(cudaMemsetAsync(cnt, 0, ((size_t)NB + 1) * 4, s));
-            sig_count_kernel<K, PW><<<cdiv(U, 256), 256, 0, s>>>(pp);
-            FQD_TRY(exclusive_scan_inplace(ctx, cnt, NB, block_sums, grand));
-            if (fat) scatter_fat_kernel<K, PW><<<cdiv(U, 256), 256, 0, s>>>(pp);
-            else scatter_kernel<K, PW><<<cdiv(U, 256), 256, 0, s>>>(pp);
-            pp.n_entries = (uint32_t)E;   // upper bound; the kernel stops at cnt[NB]
-            tt.launches += 6;             // sig_count, 3 scan kernels, scatter, compare
-            FQD_CUDA(cudaEventRecord(cev[2 * j], s));
-            if (fat) compare_fat_kernel<K, PW><<<cdiv(E, 256), 256, 0, s>>>(pp);
-            else compare_kernel<K, PW><<<cdiv(E, 256), 256, 0, s>>>(pp);
-            FQD_CUDA(cudaEventRecord(cev[2 * j + 1], s));
-            FQD_CUDA(cudaGetLastError());
+        if (use_part) {
+            if constexpr (FW == PART_RW) {
+                FQD_CUDA(cudaMemsetAsync(pcursor, 0, (size_t)npass * nparts * 4, s));
+                FQD_CUDA(cudaMemsetAsync(paux, 0, (size_t)npass * 16, s));
+                for (int j = 0; j < npass; j++) {
+                    pp.pass_j = j;
+                    PartParams qp{pbuf, pcursor + (size_t)j * nparts, nparts, nullptr, nullptr, 0};
+                    sink.n_edges = paux + 4 * j;
+                    sink.overflow = paux + 4 * j + 1;
+                    bucket_partition_kernel<K, PW><<<cdiv(U, 256), 256, 0, s>>>(pp, qp);
+                    FQD_CUDA(cudaEventRecord(cev[2 * j], s));
+                    bucket_tile_kernel<K, PW><<<nparts, TILE_THREADS, 0, s>>>(qp, pp, sink);
+                    apply_edges_kernel<<<ctx->sm_count * 8, 256, 0, s>>>(sink.edges, sink.n_edges, sink.cap, f.parent_full,
+                                                                        f.parent_one, ctx->d_ctr);
+                    FQD_CUDA(cudaEventRecord(cev[2 * j + 1], s));
+                    FQD_CUDA(cudaGetLastError());
+                    tt.launches += 3;
+                }
+                // passes whose partitions outgrew a tile (few distinct block values): counting-sort plan
+                std::vector<uint32_t> h_aux((size_t)npass * 4, 0);
+                FQD_CUDA(cudaMemcpyAsync(h_aux.data(), paux, h_aux.size() * 4, cudaMemcpyDeviceToHost, s));
+                FQD_CUDA(cudaStreamSynchronize(s));
+                tt.passes_partitioned = true;
+                for (int j = 0; j < npass; j++)
+                    if (h_aux[4 * j + 1]) { tt.passes_partitioned = false; FQD_TRY(legacy_pass(j)); }
+            }
+        } else {
+            for (int j = 0; j < npass; j++) FQD_TRY(legacy_pass(j));
         }
         if (job.method != METHOD_ADJACENCY) break;
         FQD_TRY(fetch_counters(ctx));
@@ -411,8 +618,7 @@ int run_typed(fqd_context *ctx, const DeviceJob &job, const Codec &codec, fqd_cl
     Forest f;
     FQD_TRY(stage_forest_alloc(ctx, job.method, U, f));
     if (U) {
-        gather_kernel<K, PW><<<cdiv(U, 256), 256, 0, s>>>(U, ctx->scratch_table, ctx->scratch_uslot, uq.ukey,
-                                                          uq.ucount, uq.ufirst, f.parent_full, f.parent_one, f.best);
+        init_forest_kernel<<<cdiv(U, 256), 256, 0, s>>>(U, f.parent_full, f.parent_one, f.best);
         tt.launches++;
     }
     FQD_CUDA(cudaGetLastError());
@@ -441,6 +647,9 @@ int run_typed(fqd_context *ctx, const DeviceJob &job, const Codec &codec, fqd_cl
     st->ms_ingest_kernel = tt.ingest_kernel;
     st->ms_bucket_build = st->ms_neighbour - tt.compare;
     st->launches = tt.launches;
+    st->plan_flags = (tt.partitioned ? FQD_PLAN_DEDUPE_PARTITIONED : 0u) | (tt.passes_partitioned ? FQD_PLAN_PASSES_PARTITIONED : 0u);
+    st->ms_partition_kernel = tt.partitioned ? tt.ingest_kernel : 0.f;
+    st->ms_dedupe_kernel = tt.dedupe_kernel;
     publish_result(ctx, uq, f, job.n, c2.n_selected);
     return FQD_OK;
 }
@@ -547,16 +756,7 @@ int run_sharded_typed(std::vector<Shard> &S, Exchange *ex, int world, const Code
         uint32_t unk[8] = {};
         FQD_TRY(stage_dedupe<K, PW>(sh.ctx, sh.job, codec, sh.index_base, true, sh.st, unk, sh.local, sh.tt));
         for (int k = 0; k < 8; k++) unknown_out[k] |= unk[k];
-        const uint32_t U = sh.local.U;
-        if (U) {
-            gather_kernel<K, PW><<<cdiv(U, 256), 256, 0, sh.ctx->stream>>>(
-                U, sh.ctx->scratch_table, sh.ctx->scratch_uslot, sh.local.ukey, sh.local.ucount,
-                sh.local.ufirst, nullptr, nullptr, nullptr);
-            sh.tt.launches++;
-        }
-        FQD_CUDA(cudaGetLastError());
     }
-    lap("local dedupe + gather");
     // error / alphabet agreement across ranks: [bad_record, bad_char, unknown x8]
     {
         std::vector<std::vector<uint64_t>> mine(L, std::vector<uint64_t>(10));
@@ -885,6 +1085,9 @@ int run_sharded_typed(std::vector<Shard> &S, Exchange *ex, int world, const Code
         st->ms_table_clear = sh.tt.table_clear;
         st->ms_compare = sh.tt.compare;
         st->launches = sh.tt.launches + 1;
+        st->plan_flags = (sh.tt.partitioned ? FQD_PLAN_DEDUPE_PARTITIONED : 0u) | (sh.tt.passes_partitioned ? FQD_PLAN_PASSES_PARTITIONED : 0u);
+        st->ms_partition_kernel = sh.tt.partitioned ? sh.tt.ingest_kernel : 0.f;
+        st->ms_dedupe_kernel = sh.tt.dedupe_kernel;
         cudaEventDestroy(e0[i]); cudaEventDestroy(e1[i]);
     }
     {

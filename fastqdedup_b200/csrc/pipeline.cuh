@@ -86,6 +86,53 @@ __device__ __forceinline__ unsigned long long aggregated_inc64(unsigned long lon
     return g.shfl(base, 0) + g.thread_rank();
 }
 
+// A single hot address takes ~0.5 ns per atomic on B200: 36 M appends through one counter cost
+// more than the whole table probe.  These helpers issue ONE atomic per 256-thread block.
+// Every thread of the block must call them (they contain __syncthreads).
+__device__ __forceinline__ uint32_t block_reserve(bool flag, uint32_t *counter)
+{
+    __shared__ uint32_t s_warp[8];
+    __shared__ uint32_t s_base;
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const uint32_t bal = __ballot_sync(0xFFFFFFFFu, flag);
+    if (lane == 0) s_warp[wid] = __popc(bal);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t total = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) { const uint32_t c = s_warp[i]; s_warp[i] = total; total += c; }
+        s_base = total ? atomicAdd(counter, total) : 0u;
+    }
+    __syncthreads();
+    const uint32_t pos = s_base + s_warp[wid] + __popc(bal & ((1u << lane) - 1u));
+    __syncthreads();   // s_warp / s_base may be reused by the next call
+    return pos;
+}
+
+__device__ __forceinline__ void block_add(uint32_t v, uint32_t *counter)
+{
+    __shared__ uint32_t s_sum;
+    if (threadIdx.x == 0) s_sum = 0;
+    __syncthreads();
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+    if ((threadIdx.x & 31) == 0 && v) atomicAdd(&s_sum, v);
+    __syncthreads();
+    if (threadIdx.x == 0 && s_sum) atomicAdd(counter, s_sum);
+    __syncthreads();
+}
+
+__device__ __forceinline__ void block_add64(uint32_t v, unsigned long long *counter)
+{
+    __shared__ uint32_t s_sum64;
+    if (threadIdx.x == 0) s_sum64 = 0;
+    __syncthreads();
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+    if ((threadIdx.x & 31) == 0 && v) atomicAdd(&s_sum64, v);
+    __syncthreads();
+    if (threadIdx.x == 0 && s_sum64) atomicAdd(counter, (unsigned long long)s_sum64);
+    __syncthreads();
+}
+
 template <int K, int PW>
 __device__ __forceinline__ void load_key(const uint32_t *__restrict__ ukey, uint32_t u,
                                          Key<K, PW> &k)
@@ -108,6 +155,53 @@ __device__ __forceinline__ void load_key_stream(const uint32_t *__restrict__ uke
     } else {
 #pragma unroll
         for (int i = 0; i < K * PW; i++) k.w[i] = __ldcs(p + i);
+    }
+}
+
+// ---- partition buffers of the streaming plan (partitioned.cuh) ---------------------------------
+
+constexpr int PART_RW = 8;                 // the plan handles 32-byte records (keys up to 6 words)
+constexpr int TILE_R = 1024;               // records per partition region = one shared-memory tile
+constexpr uint32_t WARP_FULL = 0xFFFFFFFFu;
+
+struct PartParams {
+    uint32_t *buf;         // nparts regions of TILE_R records of PART_RW words; null = not partitioning
+    uint32_t *cursor;      // nparts fill counters (a counter may exceed TILE_R: the partition is "oversize")
+    uint32_t nparts;
+    uint32_t *spill;       // records that did not fit their region (oversize partitions only)
+    uint32_t *spill_cnt;   // [0] records appended to spill, [1] set when spill itself overflowed
+    uint32_t spill_cap;
+};
+
+__device__ __forceinline__ uint32_t part_of(uint64_t h, uint32_t nparts)
+{
+    return __umulhi((uint32_t)(h >> 32), nparts);   // top hash bits; the tile's table uses the low ones
+}
+
+__device__ __forceinline__ void load_rec_stream(const uint32_t *p, uint32_t (&w)[PART_RW])
+{
+    asm volatile("ld.global.cs.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7])
+                 : "l"(p) : "memory");
+}
+__device__ __forceinline__ void store_rec_stream(uint32_t *p, const uint32_t (&w)[PART_RW])
+{
+    asm volatile("st.global.cs.v8.b32 [%8], {%0,%1,%2,%3,%4,%5,%6,%7};"
+                 :: "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]), "l"(p)
+                 : "memory");
+}
+
+// Append one 32-byte record to partition `part`: one atomic on the partition's cursor and one
+// 256-bit store; the L2 assembles the nparts write streams into full lines.
+__device__ __forceinline__ void part_append(const PartParams &Q, uint32_t part, const uint32_t (&e)[PART_RW])
+{
+    const uint32_t pos = atomicAdd(Q.cursor + part, 1u);
+    if (pos < (uint32_t)TILE_R) {
+        store_rec_stream(Q.buf + ((size_t)part * TILE_R + pos) * PART_RW, e);
+    } else if (Q.spill) {   // (without a spill buffer the tile kernel sees cursor > TILE_R and flags the overflow)
+        const uint32_t sp = atomicAdd(Q.spill_cnt, 1u);
+        if (sp < Q.spill_cap) store_rec_stream(Q.spill + (size_t)sp * PART_RW, e);
+        else Q.spill_cnt[1] = 1u;   // extreme skew: the caller falls back to the other plan
     }
 }
 
@@ -140,7 +234,9 @@ struct IngestParams {
     uint32_t phred_offset;
     uint32_t pad_code;
     TableRef tab;
-    uint32_t *keepmask;        // bit per record: passed the filter
+    PartParams part;           // part.buf != null: append {key, weight, index} to the partition of the
+                               // key hash instead of inserting into `tab` (streaming plan)
+    uint32_t *keepmask;        // bit per record: passed the filter (null in partition mode)
     const uint32_t *weights;   // optional multiplicity per record
     uint32_t index_base;       // global index of record 0 of this shard
     int sharded;               // 1: filtered records are inserted with weight 0 (their first
@@ -195,9 +291,13 @@ __device__ __forceinline__ void load_slot(const uint32_t *rec, uint32_t (&w)[RW]
 // slot with one sector read and adds to the count in that same (L2-hot) sector; the state
 // word keeps the smallest record index, which is rarely lowered because records arrive
 // roughly in index order.
+constexpr uint32_t NO_CLAIM = 0xFFFFFFFFu;
+
+// Returns the slot this call claimed (the record was the first of its key) or NO_CLAIM; the
+// caller appends claimed slots to the unique list with one atomic per block.
 template <int K, int PW>
-__device__ __forceinline__ void table_insert(const TableRef &P, const Key<K, PW> &key,
-                                             uint64_t h, uint32_t t, uint32_t weight)
+__device__ __forceinline__ uint32_t table_insert(const TableRef &P, const Key<K, PW> &key,
+                                                 uint64_t h, uint32_t t, uint32_t weight)
 {
     constexpr int KW = K * PW, RW = slot_words(KW);
     uint64_t s = __umul64hi(h, P.capacity);
@@ -220,9 +320,7 @@ __device__ __forceinline__ void table_insert(const TableRef &P, const Key<K, PW>
                 for (int i = 0; i < KW; i++) rec[i] = key.w[i];
                 rec[KW] = weight;
                 st_release_u32(rec + KW + 1, t);   // orders the stores above before the index
-                const uint32_t uid = aggregated_inc(&P.ctr->n_unique);
-                P.uslot[uid] = (uint32_t)s;
-                return;
+                return (uint32_t)s;
             }
             continue;   // somebody else claimed it first: look at the slot again
         }
@@ -234,12 +332,13 @@ __device__ __forceinline__ void table_insert(const TableRef &P, const Key<K, PW>
         if (diff == 0) {
             atomicAdd(rec + KW, weight);
             if (t < st) atomicMin(rec + KW + 1, t);
-            return;
+            return NO_CLAIM;
         }
         s = (s + 1 == P.capacity) ? 0 : s + 1;
         probes++;
     }
     P.ctr->table_full = 1u;
+    return NO_CLAIM;
 }
 
 // Records that failed the filter still define "first occurrence" (pass 2 of the reference
@@ -353,7 +452,7 @@ static __global__ void __launch_bounds__(256) ingest_kernel(const __grid_constan
         if (!active[r]) keep[r] = false;
         if (P.phase == 0) {
             const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, keep[r]);
-            if ((tid & 31) == 0 && t[r] < P.n) P.keepmask[t[r] >> 5] = ballot;
+            if ((tid & 31) == 0 && t[r] < P.n && P.keepmask) P.keepmask[t[r] >> 5] = ballot;
             if (P.filter_on && active[r] && !keep[r]) aggregated_inc(&P.ctr->n_discarded);
         }
     }
@@ -370,7 +469,7 @@ static __global__ void __launch_bounds__(256) ingest_kernel(const __grid_constan
 #pragma unroll
     for (int r = 0; r < ROWS; r++) {
         // phase 0: a filtered record stops here (unless sharded); phase 1: `keep` means "was filtered"
-        go[r] = active[r] && (keep[r] || (P.sharded && P.phase == 0));
+        go[r] = active[r] && (keep[r] || ((P.sharded || P.part.buf) && P.phase == 0));
         if (!go[r]) continue;
         const uint8_t *kb;
         uint32_t klen;
@@ -407,18 +506,46 @@ static __global__ void __launch_bounds__(256) ingest_kernel(const __grid_constan
         }
     }
 
+    // ---- streaming plan: hand the record to the partition of its hash ----
+    if (P.part.buf) {
+        if constexpr (RW == PART_RW) {
+#pragma unroll
+            for (int r = 0; r < ROWS; r++) {
+                if (!go[r]) continue;
+                // a filtered record travels with weight 0: it may hold its key's first index
+                const uint32_t weight = keep[r] ? (P.weights ? P.weights[t[r]] : 1u) : 0u;
+                if (P.weights && keep[r]) atomicAdd(&P.ctr->sum_weights, (unsigned long long)weight);
+                uint32_t e[RW];
+#pragma unroll
+                for (int i = 0; i < RW; i++) e[i] = 0;
+#pragma unroll
+                for (int i = 0; i < KW; i++) e[i] = key[r].w[i];
+                e[KW] = weight;
+                e[KW + 1] = P.index_base + (uint32_t)t[r];
+                part_append(P.part, part_of(hash[r], P.part.nparts), e);
+            }
+        }
+        return;
+    }
+
     // ---- exact dedupe ----
 #pragma unroll
     for (int r = 0; r < ROWS; r++) {
-        if (!go[r]) continue;
-        const uint32_t tg = P.index_base + (uint32_t)t[r];
-        if (P.phase == 0) {
-            // a filtered record only gets here in sharded mode: weight 0 carries its first index
-            const uint32_t weight = keep[r] ? (P.weights ? P.weights[t[r]] : 1u) : 0u;
-            if (P.weights && keep[r]) atomicAdd(&P.ctr->sum_weights, (unsigned long long)weight);
-            table_insert<K, PW>(P.tab, key[r], hash[r], tg, weight);
-        } else {
-            table_touch_first<K, PW>(P.tab, key[r], hash[r], tg);
+        uint32_t claimed = NO_CLAIM;
+        if (go[r]) {
+            const uint32_t tg = P.index_base + (uint32_t)t[r];
+            if (P.phase == 0) {
+                // a filtered record only gets here in sharded mode: weight 0 carries its first index
+                const uint32_t weight = keep[r] ? (P.weights ? P.weights[t[r]] : 1u) : 0u;
+                if (P.weights && keep[r]) atomicAdd(&P.ctr->sum_weights, (unsigned long long)weight);
+                claimed = table_insert<K, PW>(P.tab, key[r], hash[r], tg, weight);
+            } else {
+                table_touch_first<K, PW>(P.tab, key[r], hash[r], tg);
+            }
+        }
+        if (P.phase == 0) {   // uniform: the claimed slots of the block join the unique list
+            const uint32_t pos = block_reserve(claimed != NO_CLAIM, &P.ctr->n_unique);
+            if (claimed != NO_CLAIM) P.tab.uslot[pos] = claimed;
         }
     }
 }
@@ -1045,18 +1172,22 @@ static __global__ void __launch_bounds__(256) merge_insert_kernel(uint32_t n, co
 {
     constexpr int KW = K * PW, RW = slot_words(KW);
     const uint32_t i = blockIdx.x * 256u + threadIdx.x;
-    if (i >= n) return;
-    const uint4 *src = reinterpret_cast<const uint4 *>(recs + (size_t)i * RW);
-    uint32_t e[RW];
+    uint32_t claimed = NO_CLAIM;
+    if (i < n) {
+        const uint4 *src = reinterpret_cast<const uint4 *>(recs + (size_t)i * RW);
+        uint32_t e[RW];
 #pragma unroll
-    for (int c = 0; c < RW / 4; c++) {
-        const uint4 v = __ldg(src + c);
-        e[4 * c] = v.x; e[4 * c + 1] = v.y; e[4 * c + 2] = v.z; e[4 * c + 3] = v.w;
+        for (int c = 0; c < RW / 4; c++) {
+            const uint4 v = __ldg(src + c);
+            e[4 * c] = v.x; e[4 * c + 1] = v.y; e[4 * c + 2] = v.z; e[4 * c + 3] = v.w;
+        }
+        Key<K, PW> key;
+#pragma unroll
+        for (int j = 0; j < KW; j++) key.w[j] = e[j];
+        claimed = table_insert<K, PW>(tab, key, hash_key(key), e[KW + 1], e[KW]);
     }
-    Key<K, PW> key;
-#pragma unroll
-    for (int j = 0; j < KW; j++) key.w[j] = e[j];
-    table_insert<K, PW>(tab, key, hash_key(key), e[KW + 1], e[KW]);
+    const uint32_t pos = block_reserve(claimed != NO_CLAIM, &tab.ctr->n_unique);
+    if (claimed != NO_CLAIM) tab.uslot[pos] = claimed;
 }
 
 // gather that drops keys whose every record was filtered out (count 0)
@@ -1066,7 +1197,7 @@ static __global__ void __launch_bounds__(256) gather_nonzero_kernel(uint32_t U, 
                                                                     uint32_t *__restrict__ ukey,
                                                                     uint32_t *__restrict__ ucount,
                                                                     uint32_t *__restrict__ ufirst,
-                                                                    uint32_t *kept)
+                                                                    uint32_t *kept, int keep_zero = 0)
 {
     constexpr int KW = K * PW, RW = slot_words(KW);
     const uint32_t u = blockIdx.x * 256u + threadIdx.x;
@@ -1078,7 +1209,7 @@ static __global__ void __launch_bounds__(256) gather_nonzero_kernel(uint32_t U, 
         const uint4 v = __ldcs(rec + c);
         w[4 * c] = v.x; w[4 * c + 1] = v.y; w[4 * c + 2] = v.z; w[4 * c + 3] = v.w;
     }
-    if (w[KW] == 0) return;
+    if (w[KW] == 0 && !keep_zero) return;
     const uint32_t pos = aggregated_inc(kept);
 #pragma unroll
     for (int i = 0; i < KW; i++) ukey[(size_t)pos * KW + i] = w[i];
@@ -1200,3 +1331,5 @@ static __global__ void __launch_bounds__(128) within_distance_kernel(const uint8
 }
 
 }  // namespace fqd
+
+#include "partitioned.cuh"

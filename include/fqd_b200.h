@@ -127,8 +127,13 @@ typedef struct {
     float ms_table_clear;          /* clearing the dedupe table (inside ms_ingest) */
     float ms_bucket_build;         /* signature count + scan + scatter (inside ms_neighbour) */
     uint32_t launches;             /* kernels launched by this job */
-    uint32_t reserved_u;
+    uint32_t plan_flags;           /* FQD_PLAN_*: which launch plan the stages took */
+    float ms_partition_kernel;     /* partitioned dedupe: filter + pack + partition pass */
+    float ms_dedupe_kernel;        /* partitioned dedupe: the persistent L2-resident dedupe kernel */
 } fqd_cluster_stats;
+
+#define FQD_PLAN_DEDUPE_PARTITIONED 1u /* exact dedupe: partition by hash + L2-resident tables  */
+#define FQD_PLAN_PASSES_PARTITIONED 2u /* Hamming passes: partition by block hash + L2 multimap */
 
 /* Runs the job.  On success the per-unique result stays in the context until the next
  * job.  keep_bitmap (optional, in the job's memory space, (n_records+31)/32 uint32 words,

@@ -1,0 +1,130 @@
+"""The streaming plan of large jobs (csrc/partitioned.cuh: partition by hash into shared-memory
+sized tiles, one thread block per tile -- for the exact dedupe and for the Hamming passes) forced
+onto small inputs with FQD_PARTITION_MIN, so the oracle can check it -- and its spill path /
+fallback to the single-table / counting-sort plan when a partition outgrows its tile."""
+import os
+from dataclasses import replace
+
+import numpy as np
+import pytest
+
+from fastqdedup_b200 import synth
+from fastqdedup_b200.clustering import cluster_keys
+from fastqdedup_b200.multigpu import cluster_keys_sharded_local
+from test_gpu_cluster import METHODS, assert_same
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True)
+def force_partitioned():
+    old = os.environ.get("FQD_PARTITION_MIN")
+    os.environ["FQD_PARTITION_MIN"] = "1"
+    yield
+    if old is None:
+        del os.environ["FQD_PARTITION_MIN"]
+    else:
+        os.environ["FQD_PARTITION_MIN"] = old
+
+
+@pytest.mark.parametrize("name,n,d", [("cfg1", 40000, 1), ("cfg5", 60000, 1), ("cfg3", 30000, 2),
+                                      ("cfg4", 8000, 2), ("cfg2", 30000, 1)])
+def test_partitioned_plan_vs_oracle(gpu_ctx, oracle, name, n, d):
+    cfg = synth.CONFIGS[name].scaled(n)
+    keys, lens, quals = synth.SynthSource(cfg).reads()
+    for method in METHODS:
+        want = oracle.cluster(keys, quals, d, cfg.use_edit_distance, method, cfg.max_average_error_rate)
+        got = cluster_keys(keys, quals, d, cfg.use_edit_distance, method, cfg.max_average_error_rate,
+                           context=gpu_ctx)
+        assert_same(got, want, f"{name}/{method}")
+        assert got.stats["plan_flags"] & 1          # partitioned dedupe
+        if not cfg.use_edit_distance and name != "cfg1":
+            assert got.stats["plan_flags"] & 2      # partitioned Hamming passes
+
+
+def test_partitioned_plan_vs_reference_midsize(gpu_ctx, oracle, reference):
+    cfg = synth.CONFIGS["cfg5"].scaled(600_000)
+    keys, lens, quals = synth.SynthSource(cfg).reads()
+    want = oracle.ref_cluster(keys, None, 1, False, "directional", 1.0)
+    got = cluster_keys(keys, None, 1, False, "directional", 1.0, context=gpu_ctx)
+    assert_same(got, want, "cfg5 600k")
+
+
+def test_partitioned_filter_ragged_pad_and_alphabet(gpu_ctx, oracle):
+    cfg = replace(synth.CONFIGS["cfg3"].scaled(9000), truncate_frac=0.05, key_length=24, max_distance=1)
+    keys, lens, quals = synth.SynthSource(cfg).reads()
+    kin, qin = synth.to_ragged(keys, lens), synth.to_ragged(quals, lens)
+    for edit in (False, True):
+        want = oracle.cluster(kin, qin, 1, edit, "directional", 0.001)
+        assert want["discarded_records"] > 0
+        assert_same(cluster_keys(kin, qin, 1, edit, "directional", 0.001, context=gpu_ctx), want, "ragged")
+        assert_same(cluster_keys(keys, quals, 1, edit, "directional", 0.001, lengths=lens, context=gpu_ctx), want, "rows")
+    rng = np.random.default_rng(4)
+    reads = [bytes(rng.choice(list(b"ACGTNacgtRY"), size=8).astype(np.uint8)) for _ in range(5000)]
+    assert_same(cluster_keys(reads, None, 1, False, "adjacency", 1.0, context=gpu_ctx),
+                oracle.cluster(reads, None, 1, False, "adjacency", 1.0), "alphabet growth")
+    # first occurrence filtered, kept copy later; a key that only ever appears filtered
+    k = [b"ACGTACGTACGT", b"ACGTACGTACGT", b"ACGTACGTACGA", b"TTTTTTTTTTTT", b"CCCCCCCCCCCC"]
+    q = [b"?" * 12, b"I" * 12, b"I" * 12, b"?" * 12, b"I" * 12]
+    want = oracle.cluster(k, q, 1, False, "directional", 0.001)
+    assert_same(cluster_keys(k, q, 1, False, "directional", 0.001, context=gpu_ctx), want, "filtered first")
+    assert 0 in want["selected_first"].tolist() and want["number_of_uniques"] == 3
+
+
+def test_partition_overflow_falls_back(gpu_ctx, oracle):
+    """One key dominating the input overflows its partition: the single-table plan takes over."""
+    rng = np.random.default_rng(9)
+    reads = [b"GGGGGGGGGGGG"] * 600000 + [bytes(rng.choice(list(b"ACGT"), size=12).astype(np.uint8)) for _ in range(3000)]
+    perm = rng.permutation(len(reads))
+    reads = [reads[i] for i in perm[:200000]]
+    want = oracle.cluster(reads, None, 1, False, "directional", 1.0)
+    got = cluster_keys(reads, None, 1, False, "directional", 1.0, context=gpu_ctx)
+    assert_same(got, want, "skewed")
+    assert not (got.stats["plan_flags"] & 1)     # not the partitioned dedupe
+
+
+def test_partitioned_plan_in_sharded_jobs(gpu_ctx, oracle):
+    from fastqdedup_b200 import _native
+    ctxs = [_native.Context(0) for _ in range(3)]
+    try:
+        cfg = synth.CONFIGS["cfg3"].scaled(12000)
+        keys, lens, quals = synth.SynthSource(cfg).reads()
+        for method in METHODS:
+            want = oracle.cluster(keys, quals, 2, False, method, 0.001)
+            got = cluster_keys_sharded_local(keys, quals, 2, False, method, 0.001, world=3, contexts=ctxs)
+            assert_same(got, want, method)
+    finally:
+        for c in ctxs:
+            c.close()
+
+
+def test_bucket_partition_overflow_falls_back(gpu_ctx, oracle):
+    """Most keys share their first pigeonhole block: that pass's partition overflows and is redone
+    by the counting-sort plan; the other pass stays partitioned."""
+    rng = np.random.default_rng(11)
+    tails = rng.choice(list(b"ACGT"), size=(6000, 8)).astype(np.uint8)
+    reads = [b"ACGTACGT" + bytes(t) for t in tails] + \
+            [bytes(rng.choice(list(b"ACGT"), size=16).astype(np.uint8)) for _ in range(3000)]
+    reads = [reads[i] for i in rng.integers(0, len(reads), size=30000)]
+    for method in METHODS:
+        want = oracle.cluster(reads, None, 1, False, method, 1.0)
+        got = cluster_keys(reads, None, 1, False, method, 1.0, context=gpu_ctx)
+        assert_same(got, want, f"skewed block/{method}")
+        assert got.stats["plan_flags"] & 1 and not (got.stats["plan_flags"] & 2)
+
+
+def test_oversize_partitions_take_the_spill_path(gpu_ctx, oracle):
+    """A few keys with thousands of copies outgrow their tiles: those partitions and the spilled
+    records are deduplicated by the single-table kernels, everything else stays in tiles."""
+    cfg = synth.CONFIGS["cfg5"].scaled(50000)
+    keys, lens, quals = synth.SynthSource(cfg).reads()
+    rng = np.random.default_rng(5)
+    heavy = np.concatenate([np.repeat(keys[7:8], 5000, axis=0), np.repeat(keys[11:12], 2500, axis=0),
+                            np.repeat(keys[500:501], 1500, axis=0)])
+    allk = np.concatenate([keys, heavy])
+    allk = allk[rng.permutation(len(allk))]
+    for method in METHODS:
+        want = oracle.cluster(allk, None, 1, False, method, 1.0)
+        got = cluster_keys(allk, None, 1, False, method, 1.0, context=gpu_ctx)
+        assert_same(got, want, f"oversize/{method}")
+        assert got.stats["plan_flags"] & 1
