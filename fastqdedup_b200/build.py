@@ -25,7 +25,7 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC", "-Xptxas", "-v",
 ]
 CU_SOURCES = ["api.cu", "pipeline.cu", "trie_shim.cu", "nccl_exchange.cu"]
-HEADERS = ["key.cuh", "pipeline.cuh", "common.h", "exchange.h", "phred_lut.h",
+HEADERS = ["key.cuh", "pipeline.cuh", "partitioned.cuh", "common.h", "exchange.h", "phred_lut.h",
            os.path.join("..", "..", "include", "fqd_b200.h")]
 PY_MODULES = {"_trie": "py_trie.c", "_distance": "py_distance.c", "_fastq": "py_fastq.c"}
 

@@ -65,16 +65,34 @@ FQD_HD uint64_t mix64(uint64_t h)
     return h;
 }
 
+FQD_HD uint32_t fmix32(uint32_t h)
+{
+    h ^= h >> 16; h *= 0x85EBCA6Bu;
+    h ^= h >> 13; h *= 0xC2B2AE35u;
+    h ^= h >> 16;
+    return h;
+}
+FQD_HD uint32_t rotl32(uint32_t x, int r) { r &= 31; return r ? (x << r) | (x >> (32 - r)) : x; }
+
+// Two independent 32-bit lanes; every word goes through its own odd multiplier (a bijection of
+// the word) and the products are combined by rotate-xor, so the 2*NW multiplies are independent
+// of each other (the 64-bit multiply chain this replaces was a quarter of the ingest kernel's
+// instructions).  High word: partition / owner / table slot of the HBM table; low word: slot in
+// a shared-memory tile.
+FQD_HD void hash_lanes(uint32_t v, int i, uint32_t &a, uint32_t &b)
+{
+    const uint32_t ca = 0x9E3779B1u * (2u * (uint32_t)i + 1u), cb = 0x85EBCA77u * (2u * (uint32_t)i + 3u);
+    a ^= rotl32((v ^ (0x7F4A7C15u + 0x01000193u * (uint32_t)i)) * (ca | 1u), 7 * i + 3);
+    b ^= rotl32((v + (0x2545F491u ^ (0x9E3779B9u * (uint32_t)i))) * (cb | 1u), 11 * i + 5);
+}
+
 template <int K, int PW>
 FQD_HD uint64_t hash_key(const Key<K, PW> &k)
 {
-    uint64_t h = 0x243f6a8885a308d3ULL;
+    uint32_t a = 0x243F6A88u, b = 0x85A308D3u;
 #pragma unroll
-    for (int i = 0; i < K * PW; i++) {
-        h = (h ^ k.w[i]) * 0x9E3779B97F4A7C15ULL;
-        h ^= h >> 29;
-    }
-    return mix64(h);
+    for (int i = 0; i < K * PW; i++) hash_lanes(k.w[i], i, a, b);
+    return ((uint64_t)fmix32(a ^ rotl32(b, 16)) << 32) | fmix32(b + 0x9E3779B9u * a);
 }
 
 template <int K, int PW>
@@ -116,21 +134,53 @@ FQD_HD bool pack_key(const uint8_t *bytes, uint32_t len, uint32_t padded_len,
     return ok;
 }
 
+#if defined(__CUDA_ARCH__)
+FQD_HD uint32_t funnel_l(uint32_t lo, uint32_t hi, uint32_t s) { return __funnelshift_l(lo, hi, s); }
+#else
+FQD_HD uint32_t funnel_l(uint32_t lo, uint32_t hi, uint32_t s) { return s ? (hi << s) | (lo >> (32u - s)) : hi; }
+#endif
+
 // SWAR packing for the ACGTN alphabet: four ASCII bytes per 32-bit word, no table.  The code
 // of a letter is bits 1..3 of its byte; the remaining bits are a function of those three for
 // exactly the five letters, which is how a foreign byte is detected (returns false; the caller
 // then reports the bytes one by one through the table path).  `words` must be 4-byte aligned.
+//
+// Per word and plane: mask the four code bits where they sit (bit 8k+1+p), one multiply moves
+// them to the top nibble (bits 28..31; the cross terms land on distinct lower bits or overflow,
+// so no carry reaches the nibble) and one funnel shift appends that nibble to the plane word --
+// three instructions.  Words are visited from the last to the first so nibble j ends at bit 4j.
+struct SwarCheck {
+    uint32_t bad = 0, any = 0, all = 0xFFFFFFFFu;
+    // bits 7..5 of every byte must read 010; `bad` is evaluated at bit 1 of every byte
+    FQD_HD bool ok() const { return ((bad & 0x02020202u) | (any & 0xA0A0A0A0u) | (~all & 0x40404040u)) == 0; }
+};
+
+// four symbols: validity + the three plane nibbles appended to p0/p1/p2
+FQD_HD void swar_step(uint32_t w, SwarCheck &c, uint32_t &p0, uint32_t &p1, uint32_t &p2)
+{
+    // validity at bit 1 of every byte: c0 = bit 1, c1 = bit 2, c2 = bit 3
+    const uint32_t s1 = w >> 1, s2 = w >> 2, s3 = w >> 3, sl = w << 1;
+    const uint32_t is_t = ~w & s1 & ~s2;            // code 2
+    const uint32_t t_or_n = s1 & ~(w ^ s2);         // code 2 or 7
+    const uint32_t inval = s2 & ~(w & s1);          // codes 4, 5, 6
+    c.bad |= inval | (is_t ^ s3) | ~(sl ^ t_or_n);  // bit 4 == is_t, bit 0 == !(T or N)
+    c.any |= w;
+    c.all &= w;
+    p0 = funnel_l((w & 0x02020202u) * 0x08102040u, p0, 4);
+    p1 = funnel_l((w & 0x04040404u) * 0x04081020u, p1, 4);
+    p2 = funnel_l((w & 0x08080808u) * 0x02040810u, p2, 4);
+}
+
 template <int PW>
 FQD_HD bool pack_key_acgtn(const uint32_t *words, uint32_t len, uint32_t padded_len, Key<3, PW> &out)
 {
-    const uint32_t M = 0x01010101u;
-    uint32_t bad = 0;
+    SwarCheck chk;
 #pragma unroll
     for (int wi = 0; wi < PW; wi++) {
         uint32_t p0 = 0, p1 = 0, p2 = 0;
         const uint32_t base = 32u * wi;
 #pragma unroll
-        for (int j = 0; j < 8; j++) {
+        for (int j = 7; j >= 0; j--) {
             const uint32_t pos = base + 4u * j;
             if (pos < len) {
                 uint32_t w = words[pos >> 2];
@@ -139,15 +189,7 @@ FQD_HD bool pack_key_acgtn(const uint32_t *words, uint32_t len, uint32_t padded_
                     const uint32_t keep = (1u << (8u * rem)) - 1u;
                     w = (w & keep) | (0x41414141u & ~keep);     // the rest reads as 'A' (code 0)
                 }
-                const uint32_t x0 = w & M, x1 = (w >> 1) & M, x2 = (w >> 2) & M, x3 = (w >> 3) & M,
-                               x4 = (w >> 4) & M;
-                const uint32_t is_t = x2 & (x1 ^ M) & (x3 ^ M);
-                bad |= ((w & 0xE0E0E0E0u) ^ 0x40404040u) | (x3 & ~(x1 & x2)) | (x4 ^ is_t) |
-                       (x0 ^ ((x3 ^ M) & (is_t ^ M)));
-                // gather the four byte-LSBs into a nibble (byte 0 -> bit 0)
-                p0 |= ((x1 * 0x01020408u) >> 24 & 0xFu) << (4 * j);
-                p1 |= ((x2 * 0x01020408u) >> 24 & 0xFu) << (4 * j);
-                p2 |= ((x3 * 0x01020408u) >> 24 & 0xFu) << (4 * j);
+                swar_step(w, chk, p0, p1, p2);
             }
         }
         // PAD (code 4 = plane 2 only) on [len, padded_len)
@@ -162,7 +204,26 @@ FQD_HD bool pack_key_acgtn(const uint32_t *words, uint32_t len, uint32_t padded_
         out.w[1 * PW + wi] = p1;
         out.w[2 * PW + wi] = p2;
     }
-    return bad == 0;
+    return chk.ok() || len == 0;
+}
+
+// The same for keys of exactly 4*NW symbols (no padding): straight-line code, no length tests.
+template <int PW, int NW>
+FQD_HD bool pack_key_acgtn_fixed(const uint32_t *words, Key<3, PW> &out)
+{
+    static_assert(4 * NW <= 32 * PW, "key does not fit");
+    SwarCheck chk;
+#pragma unroll
+    for (int wi = 0; wi < PW; wi++) {
+        uint32_t p0 = 0, p1 = 0, p2 = 0;
+#pragma unroll
+        for (int j = 7; j >= 0; j--)
+            if (wi * 8 + j < NW) swar_step(words[wi * 8 + j], chk, p0, p1, p2);
+        out.w[0 * PW + wi] = p0;
+        out.w[1 * PW + wi] = p1;
+        out.w[2 * PW + wi] = p2;
+    }
+    return chk.ok();
 }
 
 // Bit mask (per plane word i) of the positions holding PAD.
@@ -279,27 +340,23 @@ FQD_HD uint32_t plane_bits32(const Key<K, PW> &a, int p, uint32_t pos)
 template <int K, int PW>
 FQD_HD uint64_t block_hash(const Key<K, PW> &a, uint32_t start, uint32_t len, uint64_t salt)
 {
-    uint64_t h = salt * 0xD6E8FEB86659FD93ULL + 0x9E3779B97F4A7C15ULL;
+    uint32_t ha = 0x243F6A88u ^ (uint32_t)salt, hb = 0x85A308D3u + (uint32_t)(salt >> 32) * 0x9E3779B1u;
 #pragma unroll
     for (int c = 0; c < PW; c++) {
         if ((uint32_t)(32 * c) < len) {
             const uint32_t rem = len - 32u * c;
             const uint32_t mask = rem >= 32u ? 0xFFFFFFFFu : ((1u << rem) - 1u);
 #pragma unroll
-            for (int p = 0; p < K; p++) {
-                uint32_t v = plane_bits32(a, p, start + 32u * c) & mask;
-                h = (h ^ v) * 0x9E3779B97F4A7C15ULL;
-                h ^= h >> 29;
-            }
+            for (int p = 0; p < K; p++) hash_lanes(plane_bits32(a, p, start + 32u * c) & mask, c * K + p, ha, hb);
         }
     }
-    return mix64(h);
+    return ((uint64_t)fmix32(ha ^ rotl32(hb, 16)) << 32) | fmix32(hb + 0x9E3779B9u * ha);
 }
 
 // Pigeonhole block j of d+1 over a key of `len` symbols: [len*j/(d+1), len*(j+1)/(d+1)).
 FQD_HD uint32_t block_start(uint32_t len, uint32_t j, uint32_t nblocks)
 {
-    return (uint32_t)(((uint64_t)len * j) / nblocks);
+    return (len * j) / nblocks;   // len <= 320 symbols, j <= nblocks <= len: 32-bit arithmetic (a 64-bit divide costs ~100 instructions)
 }
 
 // ---------------------------------------------------------------------------------------

@@ -41,6 +41,7 @@ namespace fqd {
 constexpr int TILE_T = 2 * TILE_R;         // table entries per tile (load <= 0.5)
 constexpr int TILE_THREADS = 256;
 constexpr int TILE_E = 512;                // edges a tile buffers in shared memory before hooking inline
+static_assert(TILE_R <= 1024, "tile-local indices are packed into 10 bits");
 constexpr uint32_t TILE_EMPTY = 0xFFFFFFFFu;
 constexpr uint32_t EDGE_ONE = 0x80000000u; // edge flag: both ends have count 1 (also joins the count-1 forest)
 
@@ -59,6 +60,35 @@ __device__ __forceinline__ void tile_load_rec(const uint32_t *recs, uint32_t i, 
     e[0] = a.x; e[1] = a.y; e[2] = a.z; e[3] = a.w; e[4] = b.x; e[5] = b.y; e[6] = b.z; e[7] = b.w;
 }
 
+// pass edges: (ui, uj | EDGE_ONE) pairs waiting for apply_edges_kernel
+struct EdgeSink {
+    uint2 *edges;          // (ui, uj | EDGE_ONE) pairs of this pass
+    uint32_t *n_edges;
+    uint32_t cap;
+    uint32_t *overflow;    // set when a partition outgrew its tile: the pass is redone by the counting-sort plan
+};
+
+// What a tile does with two entries within the distance (closed forms: DESIGN.md "dissection").
+template <int K, int PW>
+__device__ __forceinline__ uint32_t tile_edge_flags(const PassParams &P, uint32_t ui, uint32_t uj, uint32_t ci, uint32_t cj,
+                                                    const Key<K, PW> &ki, const Key<K, PW> &kj)
+{
+    uint32_t flag = 0;
+    if (P.method == METHOD_DIRECTIONAL) {
+        // closed form of reference __init__.py:60-91
+        if (ci >= 2 && (unsigned long long)cj >= 2ull * ci - 1ull) P.dominated[ui] = 1;
+        if (cj >= 2 && (unsigned long long)ci >= 2ull * cj - 1ull) P.dominated[uj] = 1;
+        if (ci == 1 && cj == 1) flag = EDGE_ONE;
+        else if (ci == 1) P.dead[ui] = 1;
+        else if (cj == 1) P.dead[uj] = 1;
+    } else if (P.method == METHOD_ADJACENCY) {
+        const bool i_less = prio_less<K, PW>(ci, ki, cj, kj, P.rank_of_code);
+        const unsigned long long pos = aggregated_inc64(&P.ctr->n_edges);
+        if (pos < P.edge_cap) P.edges[pos] = i_less ? make_uint2(uj, ui) : make_uint2(ui, uj);
+    }
+    return flag;
+}
+
 // ---- stage A: exact dedupe of one partition --------------------------------------------------------
 
 struct DedupeOut {
@@ -69,9 +99,16 @@ struct DedupeOut {
     int keep_zero;          // sharded jobs keep keys whose every record was filtered (weight 0)
 };
 
-template <int K, int PW>
+// FUSED: the records were partitioned by the hash of pigeonhole block 0, so a tile holds whole
+// pass-0 buckets: once the uniques of the tile have their dense ids, the same table is reused
+// as the block multimap (see bucket_tile_kernel) and pass 0 never touches HBM again.  The
+// forest does not exist yet (U is unknown), so hits can only be deferred: when a buffer is
+// too small the overflow flag makes the caller run pass 0 the ordinary way as well.
+template <int K, int PW, bool FUSED>
 static __global__ void __launch_bounds__(TILE_THREADS) dedupe_tile_kernel(const __grid_constant__ PartParams Q,
-                                                                          const __grid_constant__ DedupeOut O)
+                                                                          const __grid_constant__ DedupeOut O,
+                                                                          const __grid_constant__ PassParams P,
+                                                                          const __grid_constant__ EdgeSink E)
 {
     constexpr int KW = K * PW, RW = slot_words(KW);
     static_assert(RW == PART_RW, "partitioned plan: 32-byte records");
@@ -122,7 +159,10 @@ static __global__ void __launch_bounds__(TILE_THREADS) dedupe_tile_kernel(const 
     }
     __syncthreads();
 
-    // representatives -> dense unique arrays (keys whose every record was filtered are dropped)
+    // representatives -> dense unique arrays (keys whose every record was filtered are dropped).
+    // Their tile-local indices are compacted first so that the copy-out (and the fused pass 0)
+    // run with full warps and neighbouring threads write neighbouring unique ids.
+    __shared__ uint16_t replist[TILE_R];
     uint32_t nval = 0;
 #pragma unroll
     for (int r = 0; r < TILE_R / TILE_THREADS; r++) {
@@ -131,21 +171,80 @@ static __global__ void __launch_bounds__(TILE_THREADS) dedupe_tile_kernel(const 
         if (recs[(size_t)i * PART_RW + KW] != 0 || O.keep_zero) nval++;
         else rep &= ~(1u << r);
     }
-    const uint32_t off = block_exclusive_scan(nval, &total, warp_sums);
+    uint32_t off = block_exclusive_scan(nval, &total, warp_sums);
     if (tid == 0) s_base = total ? atomicAdd(O.n_unique, total) : 0u;
-    __syncthreads();
-    uint32_t pos = s_base + off;
 #pragma unroll
-    for (int r = 0; r < TILE_R / TILE_THREADS; r++) {
-        if (!((rep >> r) & 1u)) continue;
-        const uint32_t i = r * TILE_THREADS + tid;
+    for (int r = 0; r < TILE_R / TILE_THREADS; r++)
+        if ((rep >> r) & 1u) replist[off++] = (uint16_t)(r * TILE_THREADS + tid);
+    __syncthreads();
+    const uint32_t nrep = total, base = s_base;
+    for (uint32_t k = tid; k < nrep; k += TILE_THREADS) {
+        const uint32_t i = replist[k], pos = base + k;
         uint32_t e[PART_RW];
         tile_load_rec(recs, i, e);
 #pragma unroll
         for (int j = 0; j < KW; j++) O.ukey[(size_t)pos * KW + j] = e[j];
         O.ucount[pos] = e[KW];
         O.ufirst[pos] = e[KW + 1];
-        pos++;
+        if constexpr (FUSED) recs[(size_t)i * PART_RW + KW + 1] = pos;   // the record now carries its unique id
+    }
+
+    if constexpr (FUSED) {
+        // edges as (i | j << 10 | one << 31), tile-local record indices; the buffer reuses the upper half
+        // of the table (the multimap only needs TILE_T / 2 entries: it holds uniques, not records)
+        uint32_t *s_edges = tab + TILE_T / 2;
+        __shared__ uint32_t s_nedges;
+        for (uint32_t i = tid; i < (uint32_t)TILE_T / 2; i += TILE_THREADS) tab[i] = TILE_EMPTY;   // (the dedupe probes ended at the last barrier)
+        if (tid == 0) s_nedges = 0;
+        __syncthreads();
+        uint32_t cand = 0;
+#pragma unroll 1
+        for (uint32_t k = tid; k < nrep; k += TILE_THREADS) {
+            const uint32_t i = replist[k];
+            uint32_t e[PART_RW];
+            tile_load_rec(recs, i, e);
+            Key<K, PW> ki;
+#pragma unroll
+            for (int j = 0; j < KW; j++) ki.w[j] = e[j];
+            const uint32_t ci = e[KW], ui = e[KW + 1];
+            const uint32_t len = P.varlen ? key_length(ki, P.pad_code, P.max_len) : P.max_len;
+            uint64_t sig;
+            bool build;
+            pass_variant<K, PW>(ki, len, P, 0, sig, build);
+            uint32_t s = (uint32_t)sig & (TILE_T / 2 - 1);
+            for (;;) {
+                uint32_t cur = *reinterpret_cast<volatile uint32_t *>(tab + s);
+                if (cur == TILE_EMPTY) {
+                    cur = atomicCAS(tab + s, TILE_EMPTY, i);
+                    if (cur == TILE_EMPTY) break;
+                }
+                uint32_t f[PART_RW];
+                tile_load_rec(recs, cur, f);
+                Key<K, PW> kj;
+#pragma unroll
+                for (int j = 0; j < KW; j++) kj.w[j] = f[j];
+                cand++;
+                if (hamming_within<K, PW>(ki, kj, P.d, P.varlen != 0, P.pad_code)) {
+                    const uint32_t flag = tile_edge_flags<K, PW>(P, ui, f[KW + 1], ci, f[KW], ki, kj);
+                    const uint32_t epos = atomicAdd(&s_nedges, 1u);
+                    if (epos < (uint32_t)TILE_T / 2) s_edges[epos] = i | (cur << 10) | flag;
+                    else *E.overflow = 1u;
+                }
+                s = (s + 1) & (TILE_T / 2 - 1);
+            }
+        }
+        __syncthreads();
+        const uint32_t ne = min(s_nedges, (uint32_t)TILE_T / 2);
+        if (tid == 0) s_base = ne ? atomicAdd(E.n_edges, ne) : 0u;
+        __syncthreads();
+        for (uint32_t k = tid; k < ne; k += TILE_THREADS) {
+            const uint32_t ed = s_edges[k];
+            const uint32_t ui = recs[(size_t)(ed & 1023u) * PART_RW + KW + 1], uj = recs[(size_t)((ed >> 10) & 1023u) * PART_RW + KW + 1];
+            if (s_base + k < E.cap) E.edges[s_base + k] = make_uint2(ui, uj | (ed & EDGE_ONE));
+            else *E.overflow = 1u;
+        }
+        for (int o = 16; o; o >>= 1) cand += __shfl_xor_sync(WARP_FULL, cand, o);
+        if ((tid & 31) == 0 && cand) atomicAdd(&P.ctr->n_candidates, (unsigned long long)cand);
     }
 }
 
@@ -175,38 +274,48 @@ static __global__ void __launch_bounds__(256) spill_insert_kernel(const uint32_t
 
 // ---- stage B: one Hamming pigeonhole pass -------------------------------------------------------------
 
+constexpr int BP_ROWS = 2;   // uniques per thread: the loads and the cursor atomics of both are in flight together
+
 template <int K, int PW>
 static __global__ void __launch_bounds__(256) bucket_partition_kernel(const __grid_constant__ PassParams P,
                                                                       const __grid_constant__ PartParams Q)
 {
     constexpr int KW = K * PW, RW = fat_words(KW);
     static_assert(RW == PART_RW, "partitioned plan: 32-byte records");
-    const uint32_t u = blockIdx.x * 256u + threadIdx.x;
-    if (u >= P.U) return;
-    Key<K, PW> key;
-    load_key_stream<K, PW>(P.ukey, u, key);
-    const uint32_t count = __ldcs(P.ucount + u);
-    const uint32_t len = P.varlen ? key_length(key, P.pad_code, P.max_len) : P.max_len;
-    uint64_t sig;
-    bool build;
-    pass_variant<K, PW>(key, len, P, 0, sig, build);
-    if (P.world > 1 && (uint32_t)(sig >> 32) % (uint32_t)P.world != (uint32_t)P.my_rank) return;
-    uint32_t e[RW];
+    uint32_t e[BP_ROWS][RW], part[BP_ROWS], pos[BP_ROWS];
+    bool go[BP_ROWS];
 #pragma unroll
-    for (int i = 0; i < RW; i++) e[i] = 0;
+    for (int r = 0; r < BP_ROWS; r++) {
+        const uint64_t u = ((uint64_t)blockIdx.x * BP_ROWS + r) * 256u + threadIdx.x;
+        go[r] = u < P.U;
+        if (!go[r]) continue;
+        Key<K, PW> key;
+        load_key_stream<K, PW>(P.ukey, (uint32_t)u, key);
 #pragma unroll
-    for (int i = 0; i < KW; i++) e[i] = key.w[i];
-    e[KW] = count;
-    e[KW + 1] = u;
-    part_append(Q, part_of(sig, Q.nparts), e);
+        for (int i = 0; i < RW; i++) e[r][i] = 0;
+#pragma unroll
+        for (int i = 0; i < KW; i++) e[r][i] = key.w[i];
+        e[r][KW] = __ldcs(P.ucount + u);
+        e[r][KW + 1] = (uint32_t)u;
+    }
+#pragma unroll
+    for (int r = 0; r < BP_ROWS; r++) {
+        if (!go[r]) continue;
+        Key<K, PW> key;
+#pragma unroll
+        for (int i = 0; i < KW; i++) key.w[i] = e[r][i];
+        const uint32_t len = P.varlen ? key_length(key, P.pad_code, P.max_len) : P.max_len;
+        uint64_t sig;
+        bool build;
+        pass_variant<K, PW>(key, len, P, 0, sig, build);
+        go[r] = !(P.world > 1 && (uint32_t)(sig >> 32) % (uint32_t)P.world != (uint32_t)P.my_rank);
+        part[r] = part_of(sig, Q.nparts);
+        if (go[r]) pos[r] = atomicAdd(Q.cursor + part[r], 1u);
+    }
+#pragma unroll
+    for (int r = 0; r < BP_ROWS; r++)
+        if (go[r] && pos[r] < (uint32_t)TILE_R) store_rec_stream(Q.buf + ((size_t)part[r] * TILE_R + pos[r]) * PART_RW, e[r]);
 }
-
-struct EdgeSink {
-    uint2 *edges;          // (ui, uj | EDGE_ONE) pairs of this pass
-    uint32_t *n_edges;
-    uint32_t cap;
-    uint32_t *overflow;    // set when a partition outgrew its tile: the pass is redone by the counting-sort plan
-};
 
 // Multimap insert with comparison on the way: the probe sequence of an entry starts at the hash
 // of its pigeonhole block, so all entries of one bucket share it.  Of two entries of a bucket
@@ -222,7 +331,7 @@ static __global__ void __launch_bounds__(TILE_THREADS) bucket_tile_kernel(const 
     static_assert(RW == PART_RW, "partitioned plan: 32-byte records");
     __shared__ __align__(16) uint32_t recs[TILE_R * PART_RW];
     __shared__ uint32_t tab[TILE_T];
-    __shared__ uint2 s_edges[TILE_E];
+    __shared__ uint32_t s_edges[TILE_E];   // (i | j << 10 | one << 31), tile-local record indices
     __shared__ uint32_t s_nedges, s_base;
     const uint32_t p = blockIdx.x, tid = threadIdx.x;
     const uint32_t cnt = Q.cursor[p];
@@ -263,22 +372,10 @@ static __global__ void __launch_bounds__(TILE_THREADS) bucket_tile_kernel(const 
             cand++;
             if (hamming_within<K, PW>(ki, kj, P.d, P.varlen != 0, P.pad_code)) {
                 const uint32_t cj = f[KW], uj = f[KW + 1];
-                uint32_t flag = 0;
-                if (P.method == METHOD_DIRECTIONAL) {
-                    // closed form of reference __init__.py:60-91 (DESIGN.md "directional")
-                    if (ci >= 2 && (unsigned long long)cj >= 2ull * ci - 1ull) P.dominated[ui] = 1;
-                    if (cj >= 2 && (unsigned long long)ci >= 2ull * cj - 1ull) P.dominated[uj] = 1;
-                    if (ci == 1 && cj == 1) flag = EDGE_ONE;
-                    else if (ci == 1) P.dead[ui] = 1;
-                    else if (cj == 1) P.dead[uj] = 1;
-                } else if (P.method == METHOD_ADJACENCY) {
-                    const bool i_less = prio_less<K, PW>(ci, ki, cj, kj, P.rank_of_code);
-                    const unsigned long long pos = aggregated_inc64(&P.ctr->n_edges);
-                    if (pos < P.edge_cap) P.edges[pos] = i_less ? make_uint2(uj, ui) : make_uint2(ui, uj);
-                }
+                const uint32_t flag = tile_edge_flags<K, PW>(P, ui, uj, ci, cj, ki, kj);
                 const uint32_t pos = atomicAdd(&s_nedges, 1u);
                 if (pos < (uint32_t)TILE_E) {
-                    s_edges[pos] = make_uint2(ui, uj | flag);
+                    s_edges[pos] = i | (cur << 10) | flag;
                 } else {   // dense tile: hook right here
                     if (uf_union(P.parent_full, ui, uj)) merges++;
                     if (flag) uf_union(P.parent_one, ui, uj);
@@ -293,13 +390,13 @@ static __global__ void __launch_bounds__(TILE_THREADS) bucket_tile_kernel(const 
     __syncthreads();
     for (uint32_t k = tid; k < ne; k += TILE_THREADS) {
         const uint32_t pos = s_base + k;
-        const uint2 ed = s_edges[k];
+        const uint32_t ed = s_edges[k];
+        const uint32_t ui = recs[(size_t)(ed & 1023u) * PART_RW + KW + 1], uj = recs[(size_t)((ed >> 10) & 1023u) * PART_RW + KW + 1];
         if (pos < E.cap) {
-            E.edges[pos] = ed;
+            E.edges[pos] = make_uint2(ui, uj | (ed & EDGE_ONE));
         } else {
-            const uint32_t uj = ed.y & ~EDGE_ONE;
-            if (uf_union(P.parent_full, ed.x, uj)) merges++;
-            if (ed.y & EDGE_ONE) uf_union(P.parent_one, ed.x, uj);
+            if (uf_union(P.parent_full, ui, uj)) merges++;
+            if (ed & EDGE_ONE) uf_union(P.parent_one, ui, uj);
         }
     }
     for (int o = 16; o; o >>= 1) {
@@ -307,6 +404,36 @@ static __global__ void __launch_bounds__(TILE_THREADS) bucket_tile_kernel(const 
         cand += __shfl_xor_sync(WARP_FULL, cand, o);
     }
     if ((tid & 31) == 0) {
+        if (merges) atomicAdd(&P.ctr->n_merges, merges);
+        if (cand) atomicAdd(&P.ctr->n_candidates, (unsigned long long)cand);
+    }
+}
+
+// All pairs among the uniques [lo, hi) (the handful that left the dedupe stage through the spill
+// path and so were not compared inside a tile by the fused pass 0).
+template <int K, int PW>
+static __global__ void __launch_bounds__(256) range_pairs_kernel(const __grid_constant__ PassParams P, uint32_t lo, uint32_t hi)
+{
+    const uint32_t i = lo + blockIdx.x * 256u + threadIdx.x;
+    const uint32_t j0 = lo + blockIdx.y * 256u, j1 = min(hi, j0 + 256u);   // this block's slice of partners
+    uint32_t merges = 0, cand = 0;
+    if (i < hi && j1 > i + 1) {
+        Key<K, PW> ki;
+        load_key<K, PW>(P.ukey, i, ki);
+        const uint32_t ci = P.ucount[i];
+        for (uint32_t j = max(i + 1, j0); j < j1; j++) {
+            Key<K, PW> kj;
+            load_key<K, PW>(P.ukey, j, kj);
+            cand++;
+            if (hamming_within<K, PW>(ki, kj, P.d, P.varlen != 0, P.pad_code))
+                process_edge<K, PW>(P, i, j, ci, P.ucount[j], ki, kj, merges);
+        }
+    }
+    for (int o = 16; o; o >>= 1) {
+        merges += __shfl_xor_sync(WARP_FULL, merges, o);
+        cand += __shfl_xor_sync(WARP_FULL, cand, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
         if (merges) atomicAdd(&P.ctr->n_merges, merges);
         if (cand) atomicAdd(&P.ctr->n_candidates, (unsigned long long)cand);
     }

@@ -66,8 +66,21 @@ struct Forest {
 struct StageTimes {
     float table_clear = 0, ingest_kernel = 0, dedupe_kernel = 0, ingest = 0, compare = 0, h2d = 0;
     uint32_t launches = 0;
-    bool streamed = false, partitioned = false, passes_partitioned = false;
+    bool streamed = false, partitioned = false, passes_partitioned = false, pass0_fused = false;
 };
+
+// Pass 0 of the Hamming search done inside the dedupe tiles (partitioned.cuh, FUSED).  The flag
+// bytes and the edge list are allocated before the unique count is known (record-sized).
+struct FusedPass0 {
+    bool want = false;      // the job qualifies (single GPU, Hamming, d >= 1, not adjacency)
+    bool done = false;      // the dedupe stage did it: pass 0 is complete, its edges wait in `edges`
+    uint8_t *dominated = nullptr, *dead = nullptr;
+    uint2 *edges = nullptr;
+    uint32_t edge_cap = 0;
+    uint32_t *aux = nullptr;   // [0] edge count, [1] overflow flag
+    uint32_t spill_lo = 0, spill_hi = 0;   // unique ids that came out of the spill path (compared by brute force)
+};
+constexpr uint32_t FUSED_SPILL_MAX = 8192;
 
 template <typename T>
 int arena(fqd_context *ctx, size_t count, T **p)
@@ -152,7 +165,7 @@ uint32_t env_u32(const char *name, uint32_t fallback)
 // partitions of the streaming plan: regions of TILE_R records filled to ~65 % on average
 uint32_t tile_partitions(uint64_t n)
 {
-    const uint32_t fill_pct = std::min(90u, std::max(20u, env_u32("FQD_TILE_FILL_PCT", 65)));
+    const uint32_t fill_pct = std::min(90u, std::max(20u, env_u32("FQD_TILE_FILL_PCT", 50)));
     return (uint32_t)std::max<uint64_t>(1, (n * 100 + (uint64_t)TILE_R * fill_pct - 1) / ((uint64_t)TILE_R * fill_pct));
 }
 
@@ -162,7 +175,7 @@ constexpr uint64_t PARTITION_MIN_UNIQUES = 1u << 20;
 template <int K, int PW>
 int stage_dedupe(fqd_context *ctx, const DeviceJob &job, const Codec &codec, uint32_t index_base,
                  bool sharded, fqd_cluster_stats *st, uint32_t unknown_out[8], Uniques &uq,
-                 StageTimes &tt)
+                 StageTimes &tt, FusedPass0 *fp = nullptr)
 {
     constexpr int KW = K * PW, RW = slot_words(KW);
     cudaStream_t s = ctx->stream;
@@ -219,7 +232,11 @@ int stage_dedupe(fqd_context *ctx, const DeviceJob &job, const Codec &codec, uin
     if constexpr (RW == PART_RW) {
         uint64_t part_min = PARTITION_MIN_RECORDS;
         if (const char *e = getenv("FQD_PARTITION_MIN")) part_min = strtoull(e, nullptr, 10);   // tests
-        if (n >= part_min && n > 0 && !getenv("FQD_NO_PARTITION")) {
+        // attempt 0: records partitioned by pigeonhole block 0, pass 0 fused into the dedupe tiles;
+        // attempt 1 (or the only one): partitioned by the whole key
+        const int first_attempt = (fp && fp->want && !getenv("FQD_NO_FUSED_PASS0")) ? 0 : 1;
+        for (int attempt = first_attempt; attempt < 2 && n >= part_min && n > 0 && !getenv("FQD_NO_PARTITION"); attempt++) {
+            const bool fused = attempt == 0;
             FQD_TRY(reset_counters(ctx));
             FQD_CUDA(cudaEventRecord(ev[0], s));
             const uint32_t nparts = tile_partitions(n);
@@ -240,6 +257,7 @@ int stage_dedupe(fqd_context *ctx, const DeviceJob &job, const Codec &codec, uin
             IngestParams pp = ip;
             pp.part = PartParams{buf, cursor, nparts, spill, aux, spill_cap};
             pp.phase = 0;
+            pp.part_blocks = fused ? (uint32_t)job.d + 1u : 0u;
             pp.codec.swar = codec.swar || (K == 3 && codec_is_dna(codec) && !getenv("FQD_NO_SWAR"));
             size_t smem = 1280;
             if (fixed_any && (size_t)stride * BR + 1280 <= 200 * 1024) {
@@ -253,7 +271,20 @@ int stage_dedupe(fqd_context *ctx, const DeviceJob &job, const Codec &codec, uin
             FQD_CUDA(cudaGetLastError());
             FQD_CUDA(cudaEventRecord(ev[2], s));
             DedupeOut out{uq.ukey, uq.ucount, uq.ufirst, aux + 2, oversize, aux + 3, sharded ? 1 : 0};
-            dedupe_tile_kernel<K, PW><<<nparts, TILE_THREADS, 0, s>>>(pp.part, out);
+            PassParams p0{};
+            EdgeSink sink0{};
+            if (fused) {
+                p0.d = job.d; p0.edit = 0; p0.varlen = job.varlen ? 1 : 0; p0.method = job.method;
+                p0.max_len = job.max_len; p0.pad_code = codec.pad_code; p0.V = 1; p0.world = 1;
+                p0.pass_j = 0;
+                p0.fix_st = 0;
+                p0.fix_bl = block_start(job.max_len, 1u, (uint32_t)job.d + 1u);
+                p0.dominated = fp->dominated; p0.dead = fp->dead; p0.ctr = ctx->d_ctr;
+                sink0 = EdgeSink{fp->edges, fp->aux, fp->edge_cap, fp->aux + 1};
+                dedupe_tile_kernel<K, PW, true><<<nparts, TILE_THREADS, 0, s>>>(pp.part, out, p0, sink0);
+            } else {
+                dedupe_tile_kernel<K, PW, false><<<nparts, TILE_THREADS, 0, s>>>(pp.part, out, p0, sink0);
+            }
             tt.launches++;
             FQD_CUDA(cudaGetLastError());
             FQD_CUDA(cudaEventRecord(ev[3], s));
@@ -293,6 +324,20 @@ int stage_dedupe(fqd_context *ctx, const DeviceJob &job, const Codec &codec, uin
                     tt.launches += 3;
                 }
                 finish(c1, U);
+                if (fused) {
+                    // complete only if no tile buffer overflowed and no partition took the spill path
+                    uint32_t h_f[2] = {};
+                    FQD_CUDA(cudaMemcpyAsync(h_f, fp->aux, sizeof h_f, cudaMemcpyDeviceToHost, s));
+                    FQD_CUDA(cudaStreamSynchronize(s));
+                    // the uniques of oversize partitions (ids [h_aux[2], U)) were not compared inside a tile:
+                    // a few of them are finished by brute force, many mean pass 0 is redone the ordinary way
+                    fp->spill_lo = h_aux[2];
+                    fp->spill_hi = U;
+                    fp->done = !h_f[1] && U - h_aux[2] <= FUSED_SPILL_MAX;
+                    if (getenv("FQD_TRACE"))
+                        fprintf(stderr, "[fqd trace] fused pass 0: edges %u overflow %u oversize partitions %u spill %u (%u uniques) -> %s\n",
+                                h_f[0], h_f[1], h_aux[3], h_aux[0], U - h_aux[2], fp->done ? "done" : "redo");
+                }
                 cudaEventElapsedTime(&tt.table_clear, ev[0], ev[1]);
                 cudaEventElapsedTime(&tt.ingest_kernel, ev[1], ev[2]);
                 cudaEventElapsedTime(&tt.dedupe_kernel, ev[2], ev[3]);
@@ -308,6 +353,13 @@ int stage_dedupe(fqd_context *ctx, const DeviceJob &job, const Codec &codec, uin
             // the spill buffer overflowed (a few keys dominate the input): single-table plan instead
             arena_release(ctx, plan_mark);
             tt.launches = 0;
+            if (fused) {   // the tiles numbered the uniques differently: forget what they flagged
+                FQD_CUDA(cudaMemsetAsync(fp->aux, 0, 16, s));
+                if (fp->dominated) {
+                    FQD_CUDA(cudaMemsetAsync(fp->dominated, 0, n, s));
+                    FQD_CUDA(cudaMemsetAsync(fp->dead, 0, n, s));
+                }
+            }
         }
     }
 
@@ -378,7 +430,7 @@ int stage_dedupe(fqd_context *ctx, const DeviceJob &job, const Codec &codec, uin
 
 // ---- stage 2: forest / flag arrays over U uniques ----------------------------------------------
 
-int stage_forest_alloc(fqd_context *ctx, int method, uint32_t U, Forest &f)
+int stage_forest_alloc(fqd_context *ctx, int method, uint32_t U, Forest &f, const FusedPass0 *fp = nullptr)
 {
     cudaStream_t s = ctx->stream;
     FQD_TRY(arena(ctx, U, &f.parent_full));
@@ -386,11 +438,16 @@ int stage_forest_alloc(fqd_context *ctx, int method, uint32_t U, Forest &f)
     FQD_TRY(arena(ctx, U, &f.selected));
     if (method == METHOD_DIRECTIONAL) {
         FQD_TRY(arena(ctx, U, &f.parent_one));
-        FQD_TRY(arena(ctx, U, &f.dominated));
-        FQD_TRY(arena(ctx, U, &f.dead));
         FQD_TRY(arena(ctx, U, &f.deadroot));
-        FQD_CUDA(cudaMemsetAsync(f.dominated, 0, std::max<size_t>(U, 1), s));
-        FQD_CUDA(cudaMemsetAsync(f.dead, 0, std::max<size_t>(U, 1), s));
+        if (fp && fp->dominated) {   // allocated and zeroed before the dedupe stage, maybe already written by its tiles
+            f.dominated = fp->dominated;
+            f.dead = fp->dead;
+        } else {
+            FQD_TRY(arena(ctx, U, &f.dominated));
+            FQD_TRY(arena(ctx, U, &f.dead));
+            FQD_CUDA(cudaMemsetAsync(f.dominated, 0, std::max<size_t>(U, 1), s));
+            FQD_CUDA(cudaMemsetAsync(f.dead, 0, std::max<size_t>(U, 1), s));
+        }
         FQD_CUDA(cudaMemsetAsync(f.deadroot, 0, std::max<size_t>(U, 1), s));
     }
     if (method != METHOD_ADJACENCY) FQD_TRY(arena(ctx, U, &f.best));
@@ -405,7 +462,7 @@ int stage_forest_alloc(fqd_context *ctx, int method, uint32_t U, Forest &f)
 
 template <int K, int PW>
 int stage_passes(fqd_context *ctx, const DeviceJob &job, const Codec &codec, const Uniques &uq,
-                 Forest &f, int rank, int world, fqd_cluster_stats *st, StageTimes &tt)
+                 Forest &f, int rank, int world, fqd_cluster_stats *st, StageTimes &tt, int first_pass = 0)
 {
     constexpr int KW = K * PW, FW = fat_words(KW);
     cudaStream_t s = ctx->stream;
@@ -466,6 +523,8 @@ int stage_passes(fqd_context *ctx, const DeviceJob &job, const Codec &codec, con
     auto legacy_pass = [&](int j) -> int {
         FQD_TRY(legacy_alloc());
         pp.pass_j = j;
+        pp.fix_st = block_start(job.max_len, (uint32_t)j, (uint32_t)job.d + 1u);
+        pp.fix_bl = block_start(job.max_len, (uint32_t)j + 1u, (uint32_t)job.d + 1u) - pp.fix_st;
         FQD_CUDA(cudaMemsetAsync(cnt, 0, ((size_t)NB + 1) * 4, s));
         sig_count_kernel<K, PW><<<cdiv(U, 256), 256, 0, s>>>(pp);
         FQD_TRY(exclusive_scan_inplace(ctx, cnt, NB, block_sums, grand));
@@ -486,12 +545,14 @@ int stage_passes(fqd_context *ctx, const DeviceJob &job, const Codec &codec, con
             if constexpr (FW == PART_RW) {
                 FQD_CUDA(cudaMemsetAsync(pcursor, 0, (size_t)npass * nparts * 4, s));
                 FQD_CUDA(cudaMemsetAsync(paux, 0, (size_t)npass * 16, s));
-                for (int j = 0; j < npass; j++) {
+                for (int j = first_pass; j < npass; j++) {
                     pp.pass_j = j;
+                    pp.fix_st = block_start(job.max_len, (uint32_t)j, (uint32_t)job.d + 1u);
+                    pp.fix_bl = block_start(job.max_len, (uint32_t)j + 1u, (uint32_t)job.d + 1u) - pp.fix_st;
                     PartParams qp{pbuf, pcursor + (size_t)j * nparts, nparts, nullptr, nullptr, 0};
                     sink.n_edges = paux + 4 * j;
                     sink.overflow = paux + 4 * j + 1;
-                    bucket_partition_kernel<K, PW><<<cdiv(U, 256), 256, 0, s>>>(pp, qp);
+                    bucket_partition_kernel<K, PW><<<cdiv(U, 256 * BP_ROWS), 256, 0, s>>>(pp, qp);
                     FQD_CUDA(cudaEventRecord(cev[2 * j], s));
                     bucket_tile_kernel<K, PW><<<nparts, TILE_THREADS, 0, s>>>(qp, pp, sink);
                     apply_edges_kernel<<<ctx->sm_count * 8, 256, 0, s>>>(sink.edges, sink.n_edges, sink.cap, f.parent_full,
@@ -505,11 +566,11 @@ int stage_passes(fqd_context *ctx, const DeviceJob &job, const Codec &codec, con
                 FQD_CUDA(cudaMemcpyAsync(h_aux.data(), paux, h_aux.size() * 4, cudaMemcpyDeviceToHost, s));
                 FQD_CUDA(cudaStreamSynchronize(s));
                 tt.passes_partitioned = true;
-                for (int j = 0; j < npass; j++)
+                for (int j = first_pass; j < npass; j++)
                     if (h_aux[4 * j + 1]) { tt.passes_partitioned = false; FQD_TRY(legacy_pass(j)); }
             }
         } else {
-            for (int j = 0; j < npass; j++) FQD_TRY(legacy_pass(j));
+            for (int j = first_pass; j < npass; j++) FQD_TRY(legacy_pass(j));
         }
         if (job.method != METHOD_ADJACENCY) break;
         FQD_TRY(fetch_counters(ctx));
@@ -525,7 +586,7 @@ int stage_passes(fqd_context *ctx, const DeviceJob &job, const Codec &codec, con
         tt.launches++;
     }
     FQD_CUDA(cudaStreamSynchronize(s));
-    for (int j = 0; j < npass; j++) {
+    for (int j = first_pass; j < npass; j++) {
         float t = 0.f;
         cudaEventElapsedTime(&t, cev[2 * j], cev[2 * j + 1]);
         tt.compare += t;
@@ -610,20 +671,60 @@ int run_typed(fqd_context *ctx, const DeviceJob &job, const Codec &codec, fqd_cl
     FQD_CUDA(cudaEventRecord(ev[4], s));
     StageTimes tt;
     Uniques uq;
-    FQD_TRY(stage_dedupe<K, PW>(ctx, job, codec, 0, false, st, unknown_out, uq, tt));
+    // Hamming jobs: pass 0 can run inside the dedupe tiles (its flag bytes and edge list are
+    // needed before the unique count is known, so they are sized by the record count)
+    FusedPass0 fp;
+    uint64_t part_min = PARTITION_MIN_RECORDS;
+    if (const char *e = getenv("FQD_PARTITION_MIN")) part_min = strtoull(e, nullptr, 10);   // tests
+    fp.want = !job.edit && job.d >= 1 && job.method != METHOD_ADJACENCY && job.n >= part_min && job.n > 1 &&
+              slot_words(K * PW) == PART_RW;
+    if (fp.want) {
+        fp.edge_cap = (uint32_t)std::min<uint64_t>(0x7FFFFFF0ull, job.n / 4 + (1u << 16));
+        FQD_TRY(arena(ctx, (size_t)fp.edge_cap, &fp.edges));
+        FQD_TRY(arena(ctx, 4, &fp.aux));
+        FQD_CUDA(cudaMemsetAsync(fp.aux, 0, 16, s));
+        if (job.method == METHOD_DIRECTIONAL) {
+            FQD_TRY(arena(ctx, job.n, &fp.dominated));
+            FQD_TRY(arena(ctx, job.n, &fp.dead));
+            FQD_CUDA(cudaMemsetAsync(fp.dominated, 0, job.n, s));
+            FQD_CUDA(cudaMemsetAsync(fp.dead, 0, job.n, s));
+        }
+    }
+    FQD_TRY(stage_dedupe<K, PW>(ctx, job, codec, 0, false, st, unknown_out, uq, tt, &fp));
     const uint32_t U = uq.U;
     st->number_of_uniques = U;
     if (U > ENT_UID) { set_error("too many unique keys for one GPU (%u)", U); return FQD_ERR_UNSUPPORTED; }
     FQD_CUDA(cudaEventRecord(ev[5], s));
     Forest f;
-    FQD_TRY(stage_forest_alloc(ctx, job.method, U, f));
+    FQD_TRY(stage_forest_alloc(ctx, job.method, U, f, &fp));
     if (U) {
         init_forest_kernel<<<cdiv(U, 256), 256, 0, s>>>(U, f.parent_full, f.parent_one, f.best);
         tt.launches++;
     }
     FQD_CUDA(cudaGetLastError());
     FQD_CUDA(cudaEventRecord(ev[6], s));
-    FQD_TRY(stage_passes<K, PW>(ctx, job, codec, uq, f, 0, 1, st, tt));
+    int first_pass = 0;
+    if (fp.done && U > 1) {
+        apply_edges_kernel<<<ctx->sm_count * 8, 256, 0, s>>>(fp.edges, fp.aux, fp.edge_cap, f.parent_full, f.parent_one, ctx->d_ctr);
+        tt.launches++;
+        tt.pass0_fused = true;
+        first_pass = 1;
+        if (fp.spill_hi > fp.spill_lo + 1) {
+            PassParams bp{};
+            bp.U = U; bp.ukey = uq.ukey; bp.ucount = uq.ucount;
+            bp.d = job.d; bp.varlen = job.varlen ? 1 : 0; bp.method = job.method;
+            bp.max_len = job.max_len; bp.pad_code = codec.pad_code;
+            bp.parent_full = f.parent_full; bp.parent_one = f.parent_one;
+            bp.dominated = f.dominated; bp.dead = f.dead; bp.ctr = ctx->d_ctr;
+            for (int i = 0; i < 256; i++) bp.rank_of_code[i] = codec.rank[i];
+            {
+                const uint32_t nb = cdiv(fp.spill_hi - fp.spill_lo, 256);
+                range_pairs_kernel<K, PW><<<dim3(nb, nb), 256, 0, s>>>(bp, fp.spill_lo, fp.spill_hi);
+            }
+            tt.launches++;
+        }
+    }
+    FQD_TRY(stage_passes<K, PW>(ctx, job, codec, uq, f, 0, 1, st, tt, first_pass));
     if (job.method == METHOD_ADJACENCY) {
         FQD_TRY(fetch_counters(ctx));
         f.n_edges = ctx->h_ctr->n_edges;
@@ -647,7 +748,8 @@ int run_typed(fqd_context *ctx, const DeviceJob &job, const Codec &codec, fqd_cl
     st->ms_ingest_kernel = tt.ingest_kernel;
     st->ms_bucket_build = st->ms_neighbour - tt.compare;
     st->launches = tt.launches;
-    st->plan_flags = (tt.partitioned ? FQD_PLAN_DEDUPE_PARTITIONED : 0u) | (tt.passes_partitioned ? FQD_PLAN_PASSES_PARTITIONED : 0u);
+    st->plan_flags = (tt.partitioned ? FQD_PLAN_DEDUPE_PARTITIONED : 0u) | (tt.passes_partitioned ? FQD_PLAN_PASSES_PARTITIONED : 0u) |
+                     (tt.pass0_fused ? FQD_PLAN_PASS0_FUSED : 0u);
     st->ms_partition_kernel = tt.partitioned ? tt.ingest_kernel : 0.f;
     st->ms_dedupe_kernel = tt.dedupe_kernel;
     publish_result(ctx, uq, f, job.n, c2.n_selected);

@@ -236,6 +236,8 @@ struct IngestParams {
     TableRef tab;
     PartParams part;           // part.buf != null: append {key, weight, index} to the partition of the
                                // key hash instead of inserting into `tab` (streaming plan)
+    uint32_t part_blocks;      // > 0: partition by the hash of pigeonhole block 0 of part_blocks instead
+                               // (keys sharing that block share a tile: pass 0 runs inside the dedupe tiles)
     uint32_t *keepmask;        // bit per record: passed the filter (null in partition mode)
     const uint32_t *weights;   // optional multiplicity per record
     uint32_t index_base;       // global index of record 0 of this shard
@@ -465,9 +467,11 @@ static __global__ void __launch_bounds__(256) ingest_kernel(const __grid_constan
     }
     Key<K, PW> key[ROWS];
     uint64_t hash[ROWS];
+    uint32_t klens[ROWS];
     bool go[ROWS];
 #pragma unroll
     for (int r = 0; r < ROWS; r++) {
+        klens[r] = 0;
         // phase 0: a filtered record stops here (unless sharded); phase 1: `keep` means "was filtered"
         go[r] = active[r] && (keep[r] || ((P.sharded || P.part.buf) && P.phase == 0));
         if (!go[r]) continue;
@@ -481,13 +485,20 @@ static __global__ void __launch_bounds__(256) ingest_kernel(const __grid_constan
             klen = P.key_lens ? P.key_lens[t[r]] : P.key_len;
         }
         if (klen > P.max_len) klen = P.max_len;
+        klens[r] = klen;
         uint32_t badbyte = 0;
         bool packed = false;
         if constexpr (K == 3) {
-            // table-free DNA packing from the 4-byte aligned staged row (opt-in, see api.cu)
-            if (P.codec.swar && kstaged && (P.key_stride & 3u) == 0)
-                packed = pack_key_acgtn<PW>(reinterpret_cast<const uint32_t *>(kb), klen,
-                                            P.codec.varlen ? P.max_len : klen, key[r]);
+            // table-free DNA packing from the 4-byte aligned staged row (shared-memory loads)
+            if (P.codec.swar && kstaged && (P.key_stride & 3u) == 0) {
+                const uint32_t *row = reinterpret_cast<const uint32_t *>(stage) + (size_t)(r * 256u + tid) * (P.key_stride >> 2);
+                const uint32_t nw = (!P.key_lens && !P.codec.varlen && (klen & 3u) == 0) ? klen >> 2 : 0u;   // uniform
+                if (nw == 9 && PW >= 2) { if constexpr (PW >= 2) packed = pack_key_acgtn_fixed<PW, 9>(row, key[r]); }
+                else if (nw == 12 && PW >= 2) { if constexpr (PW >= 2) packed = pack_key_acgtn_fixed<PW, 12>(row, key[r]); }
+                else if (nw == 6) packed = pack_key_acgtn_fixed<PW, 6>(row, key[r]);
+                else if (nw == 3) packed = pack_key_acgtn_fixed<PW, 3>(row, key[r]);
+                else packed = pack_key_acgtn<PW>(row, klen, P.codec.varlen ? P.max_len : klen, key[r]);
+            }
         }
         if (!packed &&
             !pack_key<K, PW>(kb, klen, P.codec.varlen ? P.max_len : klen, lut, P.pad_code, key[r], &badbyte)) {
@@ -522,7 +533,10 @@ static __global__ void __launch_bounds__(256) ingest_kernel(const __grid_constan
                 for (int i = 0; i < KW; i++) e[i] = key[r].w[i];
                 e[KW] = weight;
                 e[KW + 1] = P.index_base + (uint32_t)t[r];
-                part_append(P.part, part_of(hash[r], P.part.nparts), e);
+                uint64_t hp = hash[r];
+                if (P.part_blocks)
+                    hp = block_hash(key[r], 0, block_start(klens[r], 1, P.part_blocks), (uint64_t)klens[r]);
+                part_append(P.part, part_of(hp, P.part.nparts), e);
             }
         }
         return;
@@ -653,6 +667,7 @@ struct PassParams {
     int d, edit, varlen, method;
     uint32_t max_len, pad_code;
     int pass_j, V;
+    uint32_t fix_st, fix_bl;   // Hamming block of pass_j for keys of max_len symbols (set with pass_j)
     int my_rank, world;     // buckets are owned by rank (sig >> 32) % world
     uint32_t nb_mask;
     uint32_t *cnt;          // NB+1 counters -> exclusive offsets after the scan
@@ -682,8 +697,13 @@ __device__ __forceinline__ bool pass_variant(const Key<K, PW> &key, uint32_t len
     const uint32_t nb = (uint32_t)P.d + 1u;
     const uint32_t j = (uint32_t)P.pass_j;
     if (!P.edit) {
-        const uint32_t st = block_start(len, j, nb);
-        const uint32_t bl = block_start(len, j + 1, nb) - st;
+        uint32_t st, bl;
+        if (!P.varlen) {   // one length: the block bounds were computed on the host
+            st = P.fix_st; bl = P.fix_bl;
+        } else {
+            st = block_start(len, j, nb);
+            bl = block_start(len, j + 1, nb) - st;
+        }
         sig = block_hash(key, st, bl, ((uint64_t)j << 32) | len);
         build = true;
         return true;

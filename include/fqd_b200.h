@@ -132,8 +132,9 @@ typedef struct {
     float ms_dedupe_kernel;        /* partitioned dedupe: the persistent L2-resident dedupe kernel */
 } fqd_cluster_stats;
 
-#define FQD_PLAN_DEDUPE_PARTITIONED 1u /* exact dedupe: partition by hash + L2-resident tables  */
-#define FQD_PLAN_PASSES_PARTITIONED 2u /* Hamming passes: partition by block hash + L2 multimap */
+#define FQD_PLAN_DEDUPE_PARTITIONED 1u /* exact dedupe: partition by hash, tables in shared-memory tiles */
+#define FQD_PLAN_PASSES_PARTITIONED 2u /* Hamming passes: partition by block hash, multimap in shared-memory tiles */
+#define FQD_PLAN_PASS0_FUSED 4u        /* pass 0 ran inside the dedupe tiles (records partitioned by block 0) */
 
 /* Runs the job.  On success the per-unique result stays in the context until the next
  * job.  keep_bitmap (optional, in the job's memory space, (n_records+31)/32 uint32 words,
