@@ -89,6 +89,87 @@ __device__ __forceinline__ uint32_t tile_edge_flags(const PassParams &P, uint32_
     return flag;
 }
 
+// One pigeonhole pass over `n` entries of a staged tile (entry k is record index_of(k); its
+// record carries {key, count, unique id}).  The table (`tsize` entries, a power of two) is used
+// as a MULTIMAP keyed by the block hash: the probe sequence of an entry starts at the hash of
+// its pigeonhole block, so all entries of one bucket share it.  Of two entries of a bucket the
+// one that claims its table entry later has walked over the other one (entries are never
+// released), so every in-bucket pair is tested exactly once, with XOR+POPC Hamming; entries of
+// other buckets that happen to lie on the walk are tested too, which is harmless (a hit is a
+// true edge).  Hits set the directional flags at once; their union-find hooks are buffered in
+// `s_edge` (as tile-local index pairs) and leave the tile as one contiguous run of the edge list.
+// (Recording the met pairs and verifying them in a second, dense loop was measured slower.)
+template <int K, int PW, bool CAN_UNION, typename IndexOf>
+__device__ __forceinline__ void tile_bucket_pass(const uint32_t *recs, uint32_t *tab, uint32_t tsize, uint32_t *s_edge,
+                                                 uint32_t cap_e, uint32_t n, IndexOf index_of, const PassParams &P,
+                                                 const EdgeSink &E, uint32_t &merges, uint32_t &cand)
+{
+    constexpr int KW = K * PW;
+    __shared__ uint32_t sc[2];   // [0] edges recorded, [1] base of the edges in the global list
+    const uint32_t tid = threadIdx.x, tmask = tsize - 1;
+    for (uint32_t i = tid; i < tsize; i += TILE_THREADS) tab[i] = TILE_EMPTY;
+    if (tid == 0) sc[0] = 0;
+    __syncthreads();
+#pragma unroll 1
+    for (uint32_t k = tid; k < n; k += TILE_THREADS) {
+        const uint32_t i = index_of(k);
+        uint32_t e[PART_RW];
+        tile_load_rec(recs, i, e);
+        Key<K, PW> ki;
+#pragma unroll
+        for (int w = 0; w < KW; w++) ki.w[w] = e[w];
+        const uint32_t ci = e[KW], ui = e[KW + 1];
+        const uint32_t len = P.varlen ? key_length(ki, P.pad_code, P.max_len) : P.max_len;
+        uint64_t sig;
+        bool build;
+        pass_variant<K, PW>(ki, len, P, 0, sig, build);
+        uint32_t s = (uint32_t)sig & tmask;
+        for (;;) {
+            uint32_t cur = *reinterpret_cast<volatile uint32_t *>(tab + s);
+            if (cur == TILE_EMPTY) {
+                cur = atomicCAS(tab + s, TILE_EMPTY, i);
+                if (cur == TILE_EMPTY) break;
+            }
+            uint32_t f[PART_RW];
+            tile_load_rec(recs, cur, f);
+            Key<K, PW> kj;
+#pragma unroll
+            for (int w = 0; w < KW; w++) kj.w[w] = f[w];
+            cand++;
+            if (hamming_within<K, PW>(ki, kj, P.d, P.varlen != 0, P.pad_code)) {
+                const uint32_t flag = tile_edge_flags<K, PW>(P, ui, f[KW + 1], ci, f[KW], ki, kj);
+                const uint32_t epos = atomicAdd(&sc[0], 1u);
+                if (epos < cap_e) {
+                    s_edge[epos] = i | (cur << 10) | flag;
+                } else if constexpr (CAN_UNION) {   // dense tile: hook right here
+                    if (uf_union(P.parent_full, ui, f[KW + 1])) merges++;
+                    if (flag) uf_union(P.parent_one, ui, f[KW + 1]);
+                } else {
+                    *E.overflow = 1u;               // the forest does not exist yet: the caller redoes the pass
+                }
+            }
+            s = (s + 1) & tmask;
+        }
+    }
+    __syncthreads();
+    const uint32_t ne = min(sc[0], cap_e);
+    if (tid == 0) sc[1] = ne ? atomicAdd(E.n_edges, ne) : 0u;
+    __syncthreads();
+    for (uint32_t k = tid; k < ne; k += TILE_THREADS) {
+        const uint32_t pos = sc[1] + k;
+        const uint32_t ed = s_edge[k];
+        const uint32_t ui = recs[(size_t)(ed & 1023u) * PART_RW + KW + 1], uj = recs[(size_t)((ed >> 10) & 1023u) * PART_RW + KW + 1];
+        if (pos < E.cap) {
+            E.edges[pos] = make_uint2(ui, uj | (ed & EDGE_ONE));
+        } else if constexpr (CAN_UNION) {
+            if (uf_union(P.parent_full, ui, uj)) merges++;
+            if (ed & EDGE_ONE) uf_union(P.parent_one, ui, uj);
+        } else {
+            *E.overflow = 1u;
+        }
+    }
+}
+
 // ---- stage A: exact dedupe of one partition --------------------------------------------------------
 
 struct DedupeOut {
@@ -190,61 +271,12 @@ static __global__ void __launch_bounds__(TILE_THREADS) dedupe_tile_kernel(const 
     }
 
     if constexpr (FUSED) {
-        // edges as (i | j << 10 | one << 31), tile-local record indices; the buffer reuses the upper half
-        // of the table (the multimap only needs TILE_T / 2 entries: it holds uniques, not records)
-        uint32_t *s_edges = tab + TILE_T / 2;
-        __shared__ uint32_t s_nedges;
-        for (uint32_t i = tid; i < (uint32_t)TILE_T / 2; i += TILE_THREADS) tab[i] = TILE_EMPTY;   // (the dedupe probes ended at the last barrier)
-        if (tid == 0) s_nedges = 0;
-        __syncthreads();
-        uint32_t cand = 0;
-#pragma unroll 1
-        for (uint32_t k = tid; k < nrep; k += TILE_THREADS) {
-            const uint32_t i = replist[k];
-            uint32_t e[PART_RW];
-            tile_load_rec(recs, i, e);
-            Key<K, PW> ki;
-#pragma unroll
-            for (int j = 0; j < KW; j++) ki.w[j] = e[j];
-            const uint32_t ci = e[KW], ui = e[KW + 1];
-            const uint32_t len = P.varlen ? key_length(ki, P.pad_code, P.max_len) : P.max_len;
-            uint64_t sig;
-            bool build;
-            pass_variant<K, PW>(ki, len, P, 0, sig, build);
-            uint32_t s = (uint32_t)sig & (TILE_T / 2 - 1);
-            for (;;) {
-                uint32_t cur = *reinterpret_cast<volatile uint32_t *>(tab + s);
-                if (cur == TILE_EMPTY) {
-                    cur = atomicCAS(tab + s, TILE_EMPTY, i);
-                    if (cur == TILE_EMPTY) break;
-                }
-                uint32_t f[PART_RW];
-                tile_load_rec(recs, cur, f);
-                Key<K, PW> kj;
-#pragma unroll
-                for (int j = 0; j < KW; j++) kj.w[j] = f[j];
-                cand++;
-                if (hamming_within<K, PW>(ki, kj, P.d, P.varlen != 0, P.pad_code)) {
-                    const uint32_t flag = tile_edge_flags<K, PW>(P, ui, f[KW + 1], ci, f[KW], ki, kj);
-                    const uint32_t epos = atomicAdd(&s_nedges, 1u);
-                    if (epos < (uint32_t)TILE_T / 2) s_edges[epos] = i | (cur << 10) | flag;
-                    else *E.overflow = 1u;
-                }
-                s = (s + 1) & (TILE_T / 2 - 1);
-            }
-        }
-        __syncthreads();
-        const uint32_t ne = min(s_nedges, (uint32_t)TILE_T / 2);
-        if (tid == 0) s_base = ne ? atomicAdd(E.n_edges, ne) : 0u;
-        __syncthreads();
-        for (uint32_t k = tid; k < ne; k += TILE_THREADS) {
-            const uint32_t ed = s_edges[k];
-            const uint32_t ui = recs[(size_t)(ed & 1023u) * PART_RW + KW + 1], uj = recs[(size_t)((ed >> 10) & 1023u) * PART_RW + KW + 1];
-            if (s_base + k < E.cap) E.edges[s_base + k] = make_uint2(ui, uj | (ed & EDGE_ONE));
-            else *E.overflow = 1u;
-        }
-        for (int o = 16; o; o >>= 1) cand += __shfl_xor_sync(WARP_FULL, cand, o);
-        if ((tid & 31) == 0 && cand) atomicAdd(&P.ctr->n_candidates, (unsigned long long)cand);
+        __syncthreads();   // ids are in place, the dedupe probes are over: the table is free for pass 0
+        uint32_t merges = 0, cand = 0;
+        // the uniques of a tile need half the table; its other half buffers the edges
+        tile_bucket_pass<K, PW, false>(recs, tab, TILE_T / 2, tab + TILE_T / 2, TILE_T / 2, nrep,
+                                       [&](uint32_t k) { return (uint32_t)replist[k]; }, P, E, merges, cand);
+        block_add64(cand, &P.ctr->n_candidates);   // one atomic per tile (per-warp atomics on one address serialise)
     }
 }
 
@@ -317,11 +349,6 @@ static __global__ void __launch_bounds__(256) bucket_partition_kernel(const __gr
         if (go[r] && pos[r] < (uint32_t)TILE_R) store_rec_stream(Q.buf + ((size_t)part[r] * TILE_R + pos[r]) * PART_RW, e[r]);
 }
 
-// Multimap insert with comparison on the way: the probe sequence of an entry starts at the hash
-// of its pigeonhole block, so all entries of one bucket share it.  Of two entries of a bucket
-// the one that claims its table entry later has walked over the other one (entries are never
-// released), so every in-bucket pair is tested exactly once; entries of other buckets that
-// happen to lie on the walk are tested too, which is harmless (a hit is a true edge).
 template <int K, int PW>
 static __global__ void __launch_bounds__(TILE_THREADS) bucket_tile_kernel(const __grid_constant__ PartParams Q,
                                                                           const __grid_constant__ PassParams P,
@@ -331,8 +358,7 @@ static __global__ void __launch_bounds__(TILE_THREADS) bucket_tile_kernel(const 
     static_assert(RW == PART_RW, "partitioned plan: 32-byte records");
     __shared__ __align__(16) uint32_t recs[TILE_R * PART_RW];
     __shared__ uint32_t tab[TILE_T];
-    __shared__ uint32_t s_edges[TILE_E];   // (i | j << 10 | one << 31), tile-local record indices
-    __shared__ uint32_t s_nedges, s_base;
+    __shared__ uint32_t s_edges[TILE_E];
     const uint32_t p = blockIdx.x, tid = threadIdx.x;
     const uint32_t cnt = Q.cursor[p];
     if (cnt == 0) return;
@@ -340,73 +366,13 @@ static __global__ void __launch_bounds__(TILE_THREADS) bucket_tile_kernel(const 
         if (tid == 0) *E.overflow = 1u;
         return;
     }
-    if (tid == 0) s_nedges = 0;
-    stage_tile(recs, tab, Q.buf + (size_t)p * TILE_R * PART_RW, cnt);
-    __syncthreads();
-
+    const uint4 *s4 = reinterpret_cast<const uint4 *>(Q.buf + (size_t)p * TILE_R * PART_RW);
+    uint4 *d4 = reinterpret_cast<uint4 *>(recs);
+    for (uint32_t i = tid; i < cnt * (PART_RW / 4); i += TILE_THREADS) d4[i] = __ldcs(s4 + i);
     uint32_t merges = 0, cand = 0;
-#pragma unroll 1
-    for (uint32_t i = tid; i < cnt; i += TILE_THREADS) {
-        uint32_t e[PART_RW];
-        tile_load_rec(recs, i, e);
-        Key<K, PW> ki;
-#pragma unroll
-        for (int j = 0; j < KW; j++) ki.w[j] = e[j];
-        const uint32_t ci = e[KW], ui = e[KW + 1];
-        const uint32_t len = P.varlen ? key_length(ki, P.pad_code, P.max_len) : P.max_len;
-        uint64_t sig;
-        bool build;
-        pass_variant<K, PW>(ki, len, P, 0, sig, build);
-        uint32_t s = (uint32_t)sig & (TILE_T - 1);
-        for (;;) {
-            uint32_t cur = *reinterpret_cast<volatile uint32_t *>(tab + s);
-            if (cur == TILE_EMPTY) {
-                cur = atomicCAS(tab + s, TILE_EMPTY, i);
-                if (cur == TILE_EMPTY) break;
-            }
-            uint32_t f[PART_RW];
-            tile_load_rec(recs, cur, f);
-            Key<K, PW> kj;
-#pragma unroll
-            for (int j = 0; j < KW; j++) kj.w[j] = f[j];
-            cand++;
-            if (hamming_within<K, PW>(ki, kj, P.d, P.varlen != 0, P.pad_code)) {
-                const uint32_t cj = f[KW], uj = f[KW + 1];
-                const uint32_t flag = tile_edge_flags<K, PW>(P, ui, uj, ci, cj, ki, kj);
-                const uint32_t pos = atomicAdd(&s_nedges, 1u);
-                if (pos < (uint32_t)TILE_E) {
-                    s_edges[pos] = i | (cur << 10) | flag;
-                } else {   // dense tile: hook right here
-                    if (uf_union(P.parent_full, ui, uj)) merges++;
-                    if (flag) uf_union(P.parent_one, ui, uj);
-                }
-            }
-            s = (s + 1) & (TILE_T - 1);
-        }
-    }
-    __syncthreads();
-    const uint32_t ne = min(s_nedges, (uint32_t)TILE_E);
-    if (tid == 0) s_base = ne ? atomicAdd(E.n_edges, ne) : 0u;
-    __syncthreads();
-    for (uint32_t k = tid; k < ne; k += TILE_THREADS) {
-        const uint32_t pos = s_base + k;
-        const uint32_t ed = s_edges[k];
-        const uint32_t ui = recs[(size_t)(ed & 1023u) * PART_RW + KW + 1], uj = recs[(size_t)((ed >> 10) & 1023u) * PART_RW + KW + 1];
-        if (pos < E.cap) {
-            E.edges[pos] = make_uint2(ui, uj | (ed & EDGE_ONE));
-        } else {
-            if (uf_union(P.parent_full, ui, uj)) merges++;
-            if (ed & EDGE_ONE) uf_union(P.parent_one, ui, uj);
-        }
-    }
-    for (int o = 16; o; o >>= 1) {
-        merges += __shfl_xor_sync(WARP_FULL, merges, o);
-        cand += __shfl_xor_sync(WARP_FULL, cand, o);
-    }
-    if ((tid & 31) == 0) {
-        if (merges) atomicAdd(&P.ctr->n_merges, merges);
-        if (cand) atomicAdd(&P.ctr->n_candidates, (unsigned long long)cand);
-    }
+    tile_bucket_pass<K, PW, true>(recs, tab, TILE_T, s_edges, TILE_E, cnt, [](uint32_t k) { return k; }, P, E, merges, cand);   // (starts with a barrier)
+    block_add(merges, &P.ctr->n_merges);
+    block_add64(cand, &P.ctr->n_candidates);
 }
 
 // All pairs among the uniques [lo, hi) (the handful that left the dedupe stage through the spill

@@ -1080,8 +1080,7 @@ static __global__ void __launch_bounds__(256) select_kernel(const __grid_constan
         P.selected[u] = sel ? 1 : 0;
         if (sel && P.bitmap && f < P.bitmap_n) atomicOr(P.bitmap + (f >> 5), 1u << (f & 31));
     }
-    const uint32_t b = __ballot_sync(0xFFFFFFFFu, sel);
-    if ((threadIdx.x & 31) == 0 && b) atomicAdd(&P.ctr->n_selected, (uint32_t)__popc(b));
+    block_add(sel ? 1u : 0u, &P.ctr->n_selected);   // one atomic per block: a per-warp atomic on one address serialises the kernel
 }
 
 // adjacency (__init__.py:105-122) == greedy maximal independent set in descending
