@@ -95,6 +95,17 @@ FQD_HD uint64_t hash_key(const Key<K, PW> &k)
     return ((uint64_t)fmix32(a ^ rotl32(b, 16)) << 32) | fmix32(b + 0x9E3779B9u * a);
 }
 
+// One 32-bit lane of the same construction: the slot of a key inside a shared-memory tile (the
+// tile's keys already share the partition bits, any well-mixed function of the key will do).
+template <int K, int PW>
+FQD_HD uint32_t hash_key32(const Key<K, PW> &k)
+{
+    uint32_t a = 0x243F6A88u;
+#pragma unroll
+    for (int i = 0; i < K * PW; i++) a ^= rotl32((k.w[i] ^ (0x7F4A7C15u + 0x01000193u * (uint32_t)i)) * ((0x9E3779B1u * (2u * (uint32_t)i + 1u)) | 1u), 7 * i + 3);
+    return fmix32(a);
+}
+
 template <int K, int PW>
 FQD_HD bool key_equal(const Key<K, PW> &a, const Key<K, PW> &b)
 {
@@ -348,6 +359,23 @@ FQD_HD uint64_t block_hash(const Key<K, PW> &a, uint32_t start, uint32_t len, ui
             const uint32_t mask = rem >= 32u ? 0xFFFFFFFFu : ((1u << rem) - 1u);
 #pragma unroll
             for (int p = 0; p < K; p++) hash_lanes(plane_bits32(a, p, start + 32u * c) & mask, c * K + p, ha, hb);
+        }
+    }
+    return ((uint64_t)fmix32(ha ^ rotl32(hb, 16)) << 32) | fmix32(hb + 0x9E3779B9u * ha);
+}
+
+// block_hash of the leading `len` symbols (start = 0: no shifting or word selection needed).
+template <int K, int PW>
+FQD_HD uint64_t block0_hash(const Key<K, PW> &a, uint32_t len, uint64_t salt)
+{
+    uint32_t ha = 0x243F6A88u ^ (uint32_t)salt, hb = 0x85A308D3u + (uint32_t)(salt >> 32) * 0x9E3779B1u;
+#pragma unroll
+    for (int c = 0; c < PW; c++) {
+        if ((uint32_t)(32 * c) < len) {
+            const uint32_t rem = len - 32u * c;
+            const uint32_t mask = rem >= 32u ? 0xFFFFFFFFu : ((1u << rem) - 1u);
+#pragma unroll
+            for (int p = 0; p < K; p++) hash_lanes(a.w[p * PW + c] & mask, c * K + p, ha, hb);
         }
     }
     return ((uint64_t)fmix32(ha ^ rotl32(hb, 16)) << 32) | fmix32(hb + 0x9E3779B9u * ha);

@@ -60,6 +60,55 @@ __device__ __forceinline__ void tile_load_rec(const uint32_t *recs, uint32_t i, 
     e[0] = a.x; e[1] = a.y; e[2] = a.z; e[3] = a.w; e[4] = b.x; e[5] = b.y; e[6] = b.z; e[7] = b.w;
 }
 
+// ---- the partition pass of the common large job -----------------------------------------------------
+//
+// Fixed-stride ACGTN keys of exactly 4*NW symbols, rows back to back, no quality filter, no
+// multiplicities: everything the general ingest_kernel decides at run time is known here, which
+// removes a third of its instructions (the pass is instruction-bound: ~1.7 G warp instructions
+// for 100 M records).  Same record format, same partition function.
+template <int PW, int NW>
+static __global__ void __launch_bounds__(256) partition_dna_kernel(const __grid_constant__ IngestParams P)
+{
+    constexpr int K = 3, KW = K * PW;
+    static_assert(slot_words(KW) == PART_RW, "partitioned plan: 32-byte records");
+    __shared__ __align__(16) uint32_t stage[256 * NW];
+    const uint32_t tid = threadIdx.x;
+    const uint64_t t0 = (uint64_t)blockIdx.x * 256u;
+    const uint32_t nblk = (uint32_t)min((uint64_t)256u, P.n - t0);
+    const uint32_t nwords = nblk * NW;
+    const uint32_t *src = reinterpret_cast<const uint32_t *>(P.keys + t0 * (4u * NW));
+    if ((reinterpret_cast<uintptr_t>(src) & 15u) == 0) {
+        const uint4 *s4 = reinterpret_cast<const uint4 *>(src);
+        uint4 *d4 = reinterpret_cast<uint4 *>(stage);
+        for (uint32_t i = tid; i < nwords / 4; i += 256) d4[i] = __ldcs(s4 + i);
+        for (uint32_t i = (nwords & ~3u) + tid; i < nwords; i += 256) stage[i] = __ldcs(src + i);
+    } else {
+        for (uint32_t i = tid; i < nwords; i += 256) stage[i] = __ldcs(src + i);
+    }
+    __syncthreads();
+    if (tid >= nblk) return;
+    Key<K, PW> key;
+    if (!pack_key_acgtn_fixed<PW, NW>(stage + tid * NW, key)) {
+        // report every unknown byte of this key so one retry with a grown alphabet suffices
+        const uint8_t *kb = reinterpret_cast<const uint8_t *>(stage + tid * NW);
+        for (uint32_t i = 0; i < 4u * NW; i++) {
+            const uint32_t c = kb[i];
+            if (P.codec.lut[c] == 0xFF) atomicOr(&P.ctr->unknown[c >> 5], 1u << (c & 31));
+        }
+        return;
+    }
+    // (records partitioned by their pigeonhole block 0 never need the hash of the whole key)
+    const uint64_t h = P.part_blocks ? block0_hash(key, block_start(4u * NW, 1, P.part_blocks), (uint64_t)(4u * NW)) : hash_key(key);
+    uint32_t e[PART_RW];
+#pragma unroll
+    for (int i = 0; i < PART_RW; i++) e[i] = 0;
+#pragma unroll
+    for (int i = 0; i < KW; i++) e[i] = key.w[i];
+    e[KW] = 1u;
+    e[KW + 1] = P.index_base + (uint32_t)(t0 + tid);
+    part_append(P.part, part_of(h, P.part.nparts), e);
+}
+
 // pass edges: (ui, uj | EDGE_ONE) pairs waiting for apply_edges_kernel
 struct EdgeSink {
     uint2 *edges;          // (ui, uj | EDGE_ONE) pairs of this pass
@@ -89,6 +138,22 @@ __device__ __forceinline__ uint32_t tile_edge_flags(const PassParams &P, uint32_
     return flag;
 }
 
+// Job statistics of a tile kernel: one atomic per warp, spread over STAT_SPREAD counters by block
+// (per-warp atomics on ONE address serialise at ~0.5 ns each and end up bounding the kernel; a
+// block-wide reduction costs three barriers per tile).  The host folds the counters.
+__device__ __forceinline__ void tile_stats(DevCounters *ctr, uint32_t merges, uint32_t cand)
+{
+    for (int o = 16; o; o >>= 1) {
+        merges += __shfl_xor_sync(WARP_FULL, merges, o);
+        cand += __shfl_xor_sync(WARP_FULL, cand, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        const uint32_t k = (blockIdx.x * 8u + (threadIdx.x >> 5)) % STAT_SPREAD;
+        if (merges) atomicAdd(&ctr->merge_spread[k], merges);
+        if (cand) atomicAdd(&ctr->cand_spread[k], (unsigned long long)cand);
+    }
+}
+
 // One pigeonhole pass over `n` entries of a staged tile (entry k is record index_of(k); its
 // record carries {key, count, unique id}).  The table (`tsize` entries, a power of two) is used
 // as a MULTIMAP keyed by the block hash: the probe sequence of an entry starts at the hash of
@@ -99,9 +164,9 @@ __device__ __forceinline__ uint32_t tile_edge_flags(const PassParams &P, uint32_
 // true edge).  Hits set the directional flags at once; their union-find hooks are buffered in
 // `s_edge` (as tile-local index pairs) and leave the tile as one contiguous run of the edge list.
 // (Recording the met pairs and verifying them in a second, dense loop was measured slower.)
-template <int K, int PW, bool CAN_UNION, typename IndexOf>
+template <int K, int PW, bool CAN_UNION, typename IndexOf, typename SlotOf>
 __device__ __forceinline__ void tile_bucket_pass(const uint32_t *recs, uint32_t *tab, uint32_t tsize, uint32_t *s_edge,
-                                                 uint32_t cap_e, uint32_t n, IndexOf index_of, const PassParams &P,
+                                                 uint32_t cap_e, uint32_t n, IndexOf index_of, SlotOf slot_of, const PassParams &P,
                                                  const EdgeSink &E, uint32_t &merges, uint32_t &cand)
 {
     constexpr int KW = K * PW;
@@ -119,11 +184,7 @@ __device__ __forceinline__ void tile_bucket_pass(const uint32_t *recs, uint32_t 
 #pragma unroll
         for (int w = 0; w < KW; w++) ki.w[w] = e[w];
         const uint32_t ci = e[KW], ui = e[KW + 1];
-        const uint32_t len = P.varlen ? key_length(ki, P.pad_code, P.max_len) : P.max_len;
-        uint64_t sig;
-        bool build;
-        pass_variant<K, PW>(ki, len, P, 0, sig, build);
-        uint32_t s = (uint32_t)sig & tmask;
+        uint32_t s = slot_of(ki) & tmask;   // a function of the entry's pigeonhole block only
         for (;;) {
             uint32_t cur = *reinterpret_cast<volatile uint32_t *>(tab + s);
             if (cur == TILE_EMPTY) {
@@ -141,11 +202,16 @@ __device__ __forceinline__ void tile_bucket_pass(const uint32_t *recs, uint32_t 
                 const uint32_t epos = atomicAdd(&sc[0], 1u);
                 if (epos < cap_e) {
                     s_edge[epos] = i | (cur << 10) | flag;
-                } else if constexpr (CAN_UNION) {   // dense tile: hook right here
-                    if (uf_union(P.parent_full, ui, f[KW + 1])) merges++;
-                    if (flag) uf_union(P.parent_one, ui, f[KW + 1]);
-                } else {
-                    *E.overflow = 1u;               // the forest does not exist yet: the caller redoes the pass
+                } else {   // dense tile (a big family): this edge goes to the global list on its own
+                    const uint32_t gpos = atomicAdd(E.n_edges, 1u);
+                    if (gpos < E.cap) {
+                        E.edges[gpos] = make_uint2(ui, f[KW + 1] | flag);
+                    } else if constexpr (CAN_UNION) {
+                        if (uf_union(P.parent_full, ui, f[KW + 1])) merges++;
+                        if (flag) uf_union(P.parent_one, ui, f[KW + 1]);
+                    } else {
+                        *E.overflow = 1u;           // the forest does not exist yet: the caller redoes the pass
+                    }
                 }
             }
             s = (s + 1) & tmask;
@@ -219,7 +285,7 @@ static __global__ void __launch_bounds__(TILE_THREADS) dedupe_tile_kernel(const 
         Key<K, PW> key;
 #pragma unroll
         for (int j = 0; j < KW; j++) key.w[j] = e[j];
-        uint32_t s = (uint32_t)hash_key(key) & (TILE_T - 1);
+        uint32_t s = hash_key32(key) & (TILE_T - 1);
         for (;;) {
             uint32_t cur = *reinterpret_cast<volatile uint32_t *>(tab + s);
             if (cur == TILE_EMPTY) {
@@ -274,9 +340,14 @@ static __global__ void __launch_bounds__(TILE_THREADS) dedupe_tile_kernel(const 
         __syncthreads();   // ids are in place, the dedupe probes are over: the table is free for pass 0
         uint32_t merges = 0, cand = 0;
         // the uniques of a tile need half the table; its other half buffers the edges
-        tile_bucket_pass<K, PW, false>(recs, tab, TILE_T / 2, tab + TILE_T / 2, TILE_T / 2, nrep,
-                                       [&](uint32_t k) { return (uint32_t)replist[k]; }, P, E, merges, cand);
-        block_add64(cand, &P.ctr->n_candidates);   // one atomic per tile (per-warp atomics on one address serialise)
+        tile_bucket_pass<K, PW, false>(
+            recs, tab, TILE_T / 2, tab + TILE_T / 2, TILE_T / 2, nrep, [&](uint32_t k) { return (uint32_t)replist[k]; },
+            [&](const Key<K, PW> &ki) {   // pass 0: the leading block
+                const uint32_t len = P.varlen ? key_length(ki, P.pad_code, P.max_len) : P.max_len;
+                return (uint32_t)block0_hash(ki, block_start(len, 1, (uint32_t)P.d + 1u), (uint64_t)len);
+            },
+            P, E, merges, cand);
+        tile_stats(P.ctr, 0, cand);
     }
 }
 
@@ -370,9 +441,17 @@ static __global__ void __launch_bounds__(TILE_THREADS) bucket_tile_kernel(const 
     uint4 *d4 = reinterpret_cast<uint4 *>(recs);
     for (uint32_t i = tid; i < cnt * (PART_RW / 4); i += TILE_THREADS) d4[i] = __ldcs(s4 + i);
     uint32_t merges = 0, cand = 0;
-    tile_bucket_pass<K, PW, true>(recs, tab, TILE_T, s_edges, TILE_E, cnt, [](uint32_t k) { return k; }, P, E, merges, cand);   // (starts with a barrier)
-    block_add(merges, &P.ctr->n_merges);
-    block_add64(cand, &P.ctr->n_candidates);
+    tile_bucket_pass<K, PW, true>(   // (starts with a barrier)
+        recs, tab, TILE_T, s_edges, TILE_E, cnt, [](uint32_t k) { return k; },
+        [&](const Key<K, PW> &ki) {
+            const uint32_t len = P.varlen ? key_length(ki, P.pad_code, P.max_len) : P.max_len;
+            uint64_t sig;
+            bool build;
+            pass_variant<K, PW>(ki, len, P, 0, sig, build);
+            return (uint32_t)sig;
+        },
+        P, E, merges, cand);
+    tile_stats(P.ctr, merges, cand);
 }
 
 // All pairs among the uniques [lo, hi) (the handful that left the dedupe stage through the spill
@@ -411,6 +490,7 @@ static __global__ void __launch_bounds__(256) apply_edges_kernel(const uint2 *__
 {
     const uint32_t n = min(*n_edges, cap);
     uint32_t merges = 0;
+    // (prefetching the next edge's parents into the L2 while hooking the current one was measured slower)
     for (uint32_t i = blockIdx.x * 256u + threadIdx.x; i < n; i += gridDim.x * 256u) {
         const uint2 ed = __ldcs(edges + i);
         const uint32_t uj = ed.y & ~EDGE_ONE;

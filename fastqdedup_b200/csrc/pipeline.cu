@@ -21,6 +21,23 @@ int fetch_counters(fqd_context *ctx)
     FQD_CUDA(cudaMemcpyAsync(ctx->h_ctr, ctx->d_ctr, sizeof(DevCounters), cudaMemcpyDeviceToHost,
                              ctx->stream));
     FQD_CUDA(cudaStreamSynchronize(ctx->stream));
+    // fold the spread statistics of the tile kernels (the host copy then holds plain totals, which is
+    // also what goes back to the device when a plan rewrites the counters)
+    DevCounters *h = ctx->h_ctr;
+    bool any = false;
+    for (uint32_t k = 0; k < STAT_SPREAD; k++) {
+        any |= h->cand_spread[k] != 0 || h->merge_spread[k] != 0;
+        h->n_candidates += h->cand_spread[k];
+        h->n_merges += h->merge_spread[k];
+        h->cand_spread[k] = 0;
+        h->merge_spread[k] = 0;
+    }
+    if (any) {   // keep the device copy consistent with the folded host copy
+        FQD_CUDA(cudaMemcpyAsync(&ctx->d_ctr->n_candidates, &h->n_candidates, sizeof h->n_candidates, cudaMemcpyHostToDevice, ctx->stream));
+        FQD_CUDA(cudaMemcpyAsync(&ctx->d_ctr->n_merges, &h->n_merges, sizeof h->n_merges, cudaMemcpyHostToDevice, ctx->stream));
+        FQD_CUDA(cudaMemsetAsync(ctx->d_ctr->cand_spread, 0, sizeof h->cand_spread, ctx->stream));
+        FQD_CUDA(cudaMemsetAsync(ctx->d_ctr->merge_spread, 0, sizeof h->merge_spread, ctx->stream));
+    }
     return FQD_OK;
 }
 
@@ -265,7 +282,23 @@ int stage_dedupe(fqd_context *ctx, const DeviceJob &job, const Codec &codec, uin
                 smem += pp.stage_bytes;
             }
             FQD_CUDA(cudaFuncSetAttribute(ingest_kernel<K, PW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            // the common large job has its own lean partition kernel (partitioned.cuh)
+            int lean_nw = 0;
+            if constexpr (K == 3) {
+                if (codec_is_dna(codec) && !job.filter_on && !job.key_off && !job.key_lens && !job.weights && !job.varlen &&
+                    job.key_stride == job.key_len && job.key_len == job.max_len && (job.key_len & 3u) == 0 &&
+                    !getenv("FQD_NO_SWAR") && !getenv("FQD_NO_LEAN"))
+                    lean_nw = (int)(job.key_len >> 2);
+            }
             FQD_TRY(for_each_input_chunk(ctx, job, pp, index_base, nullptr, tt, [&](const IngestParams &cp) {
+                if constexpr (K == 3) {
+                    if (lean_nw == 3) { partition_dna_kernel<PW, 3><<<cdiv(cp.n, 256), 256, 0, s>>>(cp); return; }
+                    if (lean_nw == 6) { partition_dna_kernel<PW, 6><<<cdiv(cp.n, 256), 256, 0, s>>>(cp); return; }
+                    if constexpr (PW >= 2) {
+                        if (lean_nw == 9) { partition_dna_kernel<PW, 9><<<cdiv(cp.n, 256), 256, 0, s>>>(cp); return; }
+                        if (lean_nw == 12) { partition_dna_kernel<PW, 12><<<cdiv(cp.n, 256), 256, 0, s>>>(cp); return; }
+                    }
+                }
                 ingest_kernel<K, PW><<<cdiv(cp.n, BR), 256, smem, s>>>(cp);
             }));
             FQD_CUDA(cudaGetLastError());
@@ -679,7 +712,7 @@ int run_typed(fqd_context *ctx, const DeviceJob &job, const Codec &codec, fqd_cl
     fp.want = !job.edit && job.d >= 1 && job.method != METHOD_ADJACENCY && job.n >= part_min && job.n > 1 &&
               slot_words(K * PW) == PART_RW;
     if (fp.want) {
-        fp.edge_cap = (uint32_t)std::min<uint64_t>(0x7FFFFFF0ull, job.n / 4 + (1u << 16));
+        fp.edge_cap = (uint32_t)std::min<uint64_t>(0x7FFFFFF0ull, job.n / 2 + (1u << 16));
         FQD_TRY(arena(ctx, (size_t)fp.edge_cap, &fp.edges));
         FQD_TRY(arena(ctx, 4, &fp.aux));
         FQD_CUDA(cudaMemsetAsync(fp.aux, 0, 16, s));

@@ -49,7 +49,12 @@ struct DevCounters {
     uint32_t undecided;
     uint32_t unknown[8];              // bitmap of key bytes outside the alphabet
     uint32_t len_min, len_max;
+    // n_candidates / n_merges contributions of the tile kernels, spread to avoid one hot address;
+    // fetch_counters folds them into the two totals
+    unsigned long long cand_spread[64];
+    uint32_t merge_spread[64];
 };
+constexpr uint32_t STAT_SPREAD = 64;
 
 // ---- small device helpers -----------------------------------------------------------
 
@@ -510,7 +515,9 @@ static __global__ void __launch_bounds__(256) ingest_kernel(const __grid_constan
             go[r] = false;
             continue;
         }
-        hash[r] = hash_key(key[r]);
+        // (records partitioned by their pigeonhole block 0 never need the hash of the whole key)
+        hash[r] = (P.part.buf && P.part_blocks) ? block0_hash(key[r], block_start(klen, 1, P.part_blocks), (uint64_t)klen)
+                                                : hash_key(key[r]);
         if constexpr (ROWS > 1) {
             const uint32_t *home = P.tab.table + __umul64hi(hash[r], P.tab.capacity) * RW;
             asm volatile("prefetch.global.L2 [%0];" :: "l"(home));
@@ -533,10 +540,7 @@ static __global__ void __launch_bounds__(256) ingest_kernel(const __grid_constan
                 for (int i = 0; i < KW; i++) e[i] = key[r].w[i];
                 e[KW] = weight;
                 e[KW + 1] = P.index_base + (uint32_t)t[r];
-                uint64_t hp = hash[r];
-                if (P.part_blocks)
-                    hp = block_hash(key[r], 0, block_start(klens[r], 1, P.part_blocks), (uint64_t)klens[r]);
-                part_append(P.part, part_of(hp, P.part.nparts), e);
+                part_append(P.part, part_of(hash[r], P.part.nparts), e);
             }
         }
         return;
