@@ -378,7 +378,8 @@ def run_ours(args, rank, world, local_rank):
     read_b = (n * L if filter_on else 0) + st.number_of_sequences * W
     if streaming:
         groups = [
-            ("ingest_kernel<3,2> partition mode (filter + pack + hash + partition)", mean("ms_partition_kernel"), read_b),
+            (("partition_dna_kernel<2,9>" if not filter_on else "ingest_kernel<3,2> partition mode") + " (pack + hash + partition into tiles)",
+             mean("ms_partition_kernel"), read_b),
             ("dedupe_tile_kernel<3,2>" + (" fused with pass 0" if fused else "") + " (exact dedupe in shared-memory tiles)",
              mean("ms_dedupe_kernel"), U * (R + 4) + (3 * U * R if fused else 0)),
             (f"{passes_left} pass(es): bucket_partition_kernel + bucket_tile_kernel + apply_edges_kernel",
@@ -399,7 +400,7 @@ def run_ours(args, rank, world, local_rank):
     if os.path.exists(tpath):
         try:
             for name, val in json.load(open(tpath)).items():
-                if dom["kernel"].startswith(name):
+                if not name.startswith("_") and dom["kernel"].startswith(name):
                     traffic = val
         except Exception:
             traffic = None
