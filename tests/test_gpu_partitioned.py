@@ -128,3 +128,24 @@ def test_oversize_partitions_take_the_spill_path(gpu_ctx, oracle):
         got = cluster_keys(allk, None, 1, False, method, 1.0, context=gpu_ctx)
         assert_same(got, want, f"oversize/{method}")
         assert got.stats["plan_flags"] & 1
+
+
+@pytest.mark.parametrize("L", [12, 24, 36, 48])
+def test_lean_partition_kernel_rows_and_foreign_bytes(gpu_ctx, oracle, L):
+    """Fixed-stride ACGTN rows of 12/24/36/48 nt take the lean partition kernel; a foreign byte anywhere
+    makes the job re-run with the grown alphabet (through the general kernel) and still match."""
+    rng = np.random.default_rng(L)
+    mol = rng.choice(list(b"ACGT"), size=(400, L)).astype(np.uint8)
+    rows = mol[rng.integers(0, len(mol), size=6000)].copy()
+    err = rng.random(rows.shape) < 0.01
+    rows[err] = rng.choice(list(b"ACGTN"), size=int(err.sum())).astype(np.uint8)
+    for method in METHODS:
+        want = oracle.cluster(rows, None, 1, False, method, 1.0)
+        got = cluster_keys(rows, None, 1, False, method, 1.0, context=gpu_ctx)
+        assert_same(got, want, f"lean/{L}/{method}")
+        assert got.stats["plan_flags"] & 1
+    dirty = rows.copy()
+    dirty[17, L - 1] = ord("a")
+    dirty[4000, 0] = ord("R")
+    want = oracle.cluster(dirty, None, 1, False, "directional", 1.0)
+    assert_same(cluster_keys(dirty, None, 1, False, "directional", 1.0, context=gpu_ctx), want, f"lean/{L}/foreign bytes")
