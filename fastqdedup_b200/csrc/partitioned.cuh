@@ -66,15 +66,17 @@ __device__ __forceinline__ void tile_load_rec(const uint32_t *recs, uint32_t i, 
 // multiplicities: everything the general ingest_kernel decides at run time is known here, which
 // removes a third of its instructions (the pass is instruction-bound: ~1.7 G warp instructions
 // for 100 M records).  Same record format, same partition function.
+constexpr int LEAN_ROWS = 2;   // records per thread: both cursor atomics are in flight before the first store needs its position
+
 template <int PW, int NW>
 static __global__ void __launch_bounds__(256) partition_dna_kernel(const __grid_constant__ IngestParams P)
 {
-    constexpr int K = 3, KW = K * PW;
+    constexpr int K = 3, KW = K * PW, ROWS = LEAN_ROWS;
     static_assert(slot_words(KW) == PART_RW, "partitioned plan: 32-byte records");
-    __shared__ __align__(16) uint32_t stage[256 * NW];
+    __shared__ __align__(16) uint32_t stage[256 * ROWS * NW];
     const uint32_t tid = threadIdx.x;
-    const uint64_t t0 = (uint64_t)blockIdx.x * 256u;
-    const uint32_t nblk = (uint32_t)min((uint64_t)256u, P.n - t0);
+    const uint64_t t0 = (uint64_t)blockIdx.x * (256u * ROWS);
+    const uint32_t nblk = (uint32_t)min((uint64_t)(256u * ROWS), P.n - t0);
     const uint32_t nwords = nblk * NW;
     const uint32_t *src = reinterpret_cast<const uint32_t *>(P.keys + t0 * (4u * NW));
     if ((reinterpret_cast<uintptr_t>(src) & 15u) == 0) {
@@ -86,27 +88,38 @@ static __global__ void __launch_bounds__(256) partition_dna_kernel(const __grid_
         for (uint32_t i = tid; i < nwords; i += 256) stage[i] = __ldcs(src + i);
     }
     __syncthreads();
-    if (tid >= nblk) return;
-    Key<K, PW> key;
-    if (!pack_key_acgtn_fixed<PW, NW>(stage + tid * NW, key)) {
-        // report every unknown byte of this key so one retry with a grown alphabet suffices
-        const uint8_t *kb = reinterpret_cast<const uint8_t *>(stage + tid * NW);
-        for (uint32_t i = 0; i < 4u * NW; i++) {
-            const uint32_t c = kb[i];
-            if (P.codec.lut[c] == 0xFF) atomicOr(&P.ctr->unknown[c >> 5], 1u << (c & 31));
+    uint32_t e[ROWS][PART_RW], part[ROWS], pos[ROWS];
+    bool go[ROWS];
+#pragma unroll
+    for (int r = 0; r < ROWS; r++) {
+        const uint32_t row = r * 256u + tid;
+        go[r] = row < nblk;
+        if (!go[r]) continue;
+        Key<K, PW> key;
+        if (!pack_key_acgtn_fixed<PW, NW>(stage + row * NW, key)) {
+            // report every unknown byte of this key so one retry with a grown alphabet suffices
+            const uint8_t *kb = reinterpret_cast<const uint8_t *>(stage + row * NW);
+            for (uint32_t i = 0; i < 4u * NW; i++) {
+                const uint32_t c = kb[i];
+                if (P.codec.lut[c] == 0xFF) atomicOr(&P.ctr->unknown[c >> 5], 1u << (c & 31));
+            }
+            go[r] = false;
+            continue;
         }
-        return;
+        // (records partitioned by their pigeonhole block 0 never need the hash of the whole key)
+        const uint64_t h = P.part_blocks ? block0_hash(key, block_start(4u * NW, 1, P.part_blocks), PART_SALT | (4u * NW)) : hash_key(key);
+#pragma unroll
+        for (int i = 0; i < PART_RW; i++) e[r][i] = 0;
+#pragma unroll
+        for (int i = 0; i < KW; i++) e[r][i] = key.w[i];
+        e[r][KW] = 1u;
+        e[r][KW + 1] = P.index_base + (uint32_t)(t0 + row);
+        part[r] = part_of(h, P.part.nparts);
+        pos[r] = atomicAdd(P.part.cursor + part[r], 1u);
     }
-    // (records partitioned by their pigeonhole block 0 never need the hash of the whole key)
-    const uint64_t h = P.part_blocks ? block0_hash(key, block_start(4u * NW, 1, P.part_blocks), (uint64_t)(4u * NW)) : hash_key(key);
-    uint32_t e[PART_RW];
 #pragma unroll
-    for (int i = 0; i < PART_RW; i++) e[i] = 0;
-#pragma unroll
-    for (int i = 0; i < KW; i++) e[i] = key.w[i];
-    e[KW] = 1u;
-    e[KW + 1] = P.index_base + (uint32_t)(t0 + tid);
-    part_append(P.part, part_of(h, P.part.nparts), e);
+    for (int r = 0; r < ROWS; r++)
+        if (go[r]) part_place(P.part, part[r], pos[r], e[r]);
 }
 
 // pass edges: (ui, uj | EDGE_ONE) pairs waiting for apply_edges_kernel
@@ -389,7 +402,7 @@ static __global__ void __launch_bounds__(256) bucket_partition_kernel(const __gr
     bool go[BP_ROWS];
 #pragma unroll
     for (int r = 0; r < BP_ROWS; r++) {
-        const uint64_t u = ((uint64_t)blockIdx.x * BP_ROWS + r) * 256u + threadIdx.x;
+        const uint64_t u = (uint64_t)P.u_lo + ((uint64_t)blockIdx.x * BP_ROWS + r) * 256u + threadIdx.x;
         go[r] = u < P.U;
         if (!go[r]) continue;
         Key<K, PW> key;

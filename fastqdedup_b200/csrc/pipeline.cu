@@ -97,7 +97,7 @@ struct FusedPass0 {
     uint32_t *aux = nullptr;   // [0] edge count, [1] overflow flag
     uint32_t spill_lo = 0, spill_hi = 0;   // unique ids that came out of the spill path (compared by brute force)
 };
-constexpr uint32_t FUSED_SPILL_MAX = 8192;
+constexpr uint32_t FUSED_SPILL_BRUTE = 4096;   // at most this many spilled uniques are compared by brute force
 
 template <typename T>
 int arena(fqd_context *ctx, size_t count, T **p)
@@ -182,7 +182,7 @@ uint32_t env_u32(const char *name, uint32_t fallback)
 // partitions of the streaming plan: regions of TILE_R records filled to ~65 % on average
 uint32_t tile_partitions(uint64_t n)
 {
-    const uint32_t fill_pct = std::min(90u, std::max(20u, env_u32("FQD_TILE_FILL_PCT", 50)));
+    const uint32_t fill_pct = std::min(90u, std::max(20u, env_u32("FQD_TILE_FILL_PCT", 60)));
     return (uint32_t)std::max<uint64_t>(1, (n * 100 + (uint64_t)TILE_R * fill_pct - 1) / ((uint64_t)TILE_R * fill_pct));
 }
 
@@ -257,7 +257,7 @@ int stage_dedupe(fqd_context *ctx, const DeviceJob &job, const Codec &codec, uin
             FQD_TRY(reset_counters(ctx));
             FQD_CUDA(cudaEventRecord(ev[0], s));
             const uint32_t nparts = tile_partitions(n);
-            const uint32_t spill_cap = (uint32_t)(n / 8 + 4096);
+            const uint32_t spill_cap = (uint32_t)(n / 4 + 4096);
             uint32_t *buf, *cursor, *spill, *aux, *oversize;
             FQD_TRY(arena(ctx, (size_t)nparts * TILE_R * RW, &buf));
             FQD_TRY(arena(ctx, nparts, &cursor));
@@ -292,11 +292,11 @@ int stage_dedupe(fqd_context *ctx, const DeviceJob &job, const Codec &codec, uin
             }
             FQD_TRY(for_each_input_chunk(ctx, job, pp, index_base, nullptr, tt, [&](const IngestParams &cp) {
                 if constexpr (K == 3) {
-                    if (lean_nw == 3) { partition_dna_kernel<PW, 3><<<cdiv(cp.n, 256), 256, 0, s>>>(cp); return; }
-                    if (lean_nw == 6) { partition_dna_kernel<PW, 6><<<cdiv(cp.n, 256), 256, 0, s>>>(cp); return; }
+                    if (lean_nw == 3) { partition_dna_kernel<PW, 3><<<cdiv(cp.n, 256 * LEAN_ROWS), 256, 0, s>>>(cp); return; }
+                    if (lean_nw == 6) { partition_dna_kernel<PW, 6><<<cdiv(cp.n, 256 * LEAN_ROWS), 256, 0, s>>>(cp); return; }
                     if constexpr (PW >= 2) {
-                        if (lean_nw == 9) { partition_dna_kernel<PW, 9><<<cdiv(cp.n, 256), 256, 0, s>>>(cp); return; }
-                        if (lean_nw == 12) { partition_dna_kernel<PW, 12><<<cdiv(cp.n, 256), 256, 0, s>>>(cp); return; }
+                        if (lean_nw == 9) { partition_dna_kernel<PW, 9><<<cdiv(cp.n, 256 * LEAN_ROWS), 256, 0, s>>>(cp); return; }
+                        if (lean_nw == 12) { partition_dna_kernel<PW, 12><<<cdiv(cp.n, 256 * LEAN_ROWS), 256, 0, s>>>(cp); return; }
                     }
                 }
                 ingest_kernel<K, PW><<<cdiv(cp.n, BR), 256, smem, s>>>(cp);
@@ -366,7 +366,7 @@ int stage_dedupe(fqd_context *ctx, const DeviceJob &job, const Codec &codec, uin
                     // a few of them are finished by brute force, many mean pass 0 is redone the ordinary way
                     fp->spill_lo = h_aux[2];
                     fp->spill_hi = U;
-                    fp->done = !h_f[1] && U - h_aux[2] <= FUSED_SPILL_MAX;
+                    fp->done = !h_f[1];
                     if (getenv("FQD_TRACE"))
                         fprintf(stderr, "[fqd trace] fused pass 0: edges %u overflow %u oversize partitions %u spill %u (%u uniques) -> %s\n",
                                 h_f[0], h_f[1], h_aux[3], h_aux[0], U - h_aux[2], fp->done ? "done" : "redo");
@@ -495,20 +495,24 @@ int stage_forest_alloc(fqd_context *ctx, int method, uint32_t U, Forest &f, cons
 
 template <int K, int PW>
 int stage_passes(fqd_context *ctx, const DeviceJob &job, const Codec &codec, const Uniques &uq,
-                 Forest &f, int rank, int world, fqd_cluster_stats *st, StageTimes &tt, int first_pass = 0)
+                 Forest &f, int rank, int world, fqd_cluster_stats *st, StageTimes &tt, int first_pass = 0,
+                 int end_pass = -1, uint32_t u_lo = 0)
 {
     constexpr int KW = K * PW, FW = fat_words(KW);
     cudaStream_t s = ctx->stream;
     const uint32_t U = uq.U;
-    const int npass = (job.d > 0 && U > 1) ? job.d + 1 : 0;
-    st->n_passes = npass;
-    if (!npass) return FQD_OK;
+    // passes [first_pass, npass) over the uniques [u_lo, U) (a sub-range only for the streaming plan:
+    // the uniques that left the dedupe stage through the spill path redo pass 0 among themselves)
+    const int npass_all = (job.d > 0 && U > 1) ? job.d + 1 : 0;
+    const int npass = end_pass < 0 ? npass_all : std::min(end_pass, npass_all);
+    if (end_pass < 0) st->n_passes = npass_all;
+    if (npass <= first_pass) return FQD_OK;
     const int V = job.edit ? (job.varlen ? 2 * job.d + 1 : 1) * (job.d + 1) : 1;
     const uint64_t E = (uint64_t)U * V;
     if (E >= 0xFFFFFFF0ull) { set_error("too many pigeonhole entries (%llu)", (unsigned long long)E); return FQD_ERR_UNSUPPORTED; }
     const bool fat = !job.edit;
     PassParams pp{};
-    pp.U = U; pp.ukey = uq.ukey; pp.ucount = uq.ucount;
+    pp.U = U; pp.u_lo = u_lo; pp.ukey = uq.ukey; pp.ucount = uq.ucount;
     pp.d = job.d; pp.edit = job.edit; pp.varlen = job.varlen ? 1 : 0; pp.method = job.method;
     pp.max_len = job.max_len; pp.pad_code = codec.pad_code;
     pp.V = V; pp.my_rank = rank; pp.world = world;
@@ -524,9 +528,9 @@ int stage_passes(fqd_context *ctx, const DeviceJob &job, const Codec &codec, con
     if constexpr (FW == PART_RW) {
         uint64_t part_min = PARTITION_MIN_UNIQUES;
         if (const char *e = getenv("FQD_PARTITION_MIN")) part_min = strtoull(e, nullptr, 10);   // tests
-        use_part = fat && U >= part_min && !getenv("FQD_NO_PARTITION") && !getenv("FQD_NO_PARTITION_PASSES");
+        use_part = fat && (U >= part_min || u_lo) && !getenv("FQD_NO_PARTITION") && !getenv("FQD_NO_PARTITION_PASSES");
     }
-    const uint32_t own_avg = U / (uint32_t)std::max(world, 1);   // entries this rank's buckets receive
+    const uint32_t own_avg = (U - u_lo) / (uint32_t)std::max(world, 1);   // entries this rank's buckets receive
     const uint32_t nparts = tile_partitions(own_avg);
     uint32_t *pbuf = nullptr, *pcursor = nullptr, *paux = nullptr;   // paux per pass: [0] edge count, [1] overflow flag
     EdgeSink sink{};
@@ -585,7 +589,7 @@ int stage_passes(fqd_context *ctx, const DeviceJob &job, const Codec &codec, con
                     PartParams qp{pbuf, pcursor + (size_t)j * nparts, nparts, nullptr, nullptr, 0};
                     sink.n_edges = paux + 4 * j;
                     sink.overflow = paux + 4 * j + 1;
-                    bucket_partition_kernel<K, PW><<<cdiv(U, 256 * BP_ROWS), 256, 0, s>>>(pp, qp);
+                    bucket_partition_kernel<K, PW><<<cdiv(U - u_lo, 256 * BP_ROWS), 256, 0, s>>>(pp, qp);
                     FQD_CUDA(cudaEventRecord(cev[2 * j], s));
                     bucket_tile_kernel<K, PW><<<nparts, TILE_THREADS, 0, s>>>(qp, pp, sink);
                     apply_edges_kernel<<<ctx->sm_count * 8, 256, 0, s>>>(sink.edges, sink.n_edges, sink.cap, f.parent_full,
@@ -599,8 +603,12 @@ int stage_passes(fqd_context *ctx, const DeviceJob &job, const Codec &codec, con
                 FQD_CUDA(cudaMemcpyAsync(h_aux.data(), paux, h_aux.size() * 4, cudaMemcpyDeviceToHost, s));
                 FQD_CUDA(cudaStreamSynchronize(s));
                 tt.passes_partitioned = true;
-                for (int j = first_pass; j < npass; j++)
+                for (int j = first_pass; j < npass; j++) {
+                    if (getenv("FQD_TRACE"))
+                        fprintf(stderr, "[fqd trace] pass %d over uniques [%u, %u): %u tiles, %u edges%s\n", j, u_lo, U, nparts,
+                                h_aux[4 * j], h_aux[4 * j + 1] ? ", a tile overflowed -> counting-sort plan" : "");
                     if (h_aux[4 * j + 1]) { tt.passes_partitioned = false; FQD_TRY(legacy_pass(j)); }
+                }
             }
         } else {
             for (int j = first_pass; j < npass; j++) FQD_TRY(legacy_pass(j));
@@ -742,7 +750,7 @@ int run_typed(fqd_context *ctx, const DeviceJob &job, const Codec &codec, fqd_cl
         tt.launches++;
         tt.pass0_fused = true;
         first_pass = 1;
-        if (fp.spill_hi > fp.spill_lo + 1) {
+        if (fp.spill_hi > fp.spill_lo + 1 && fp.spill_hi - fp.spill_lo <= FUSED_SPILL_BRUTE) {
             PassParams bp{};
             bp.U = U; bp.ukey = uq.ukey; bp.ucount = uq.ucount;
             bp.d = job.d; bp.varlen = job.varlen ? 1 : 0; bp.method = job.method;
@@ -750,11 +758,12 @@ int run_typed(fqd_context *ctx, const DeviceJob &job, const Codec &codec, fqd_cl
             bp.parent_full = f.parent_full; bp.parent_one = f.parent_one;
             bp.dominated = f.dominated; bp.dead = f.dead; bp.ctr = ctx->d_ctr;
             for (int i = 0; i < 256; i++) bp.rank_of_code[i] = codec.rank[i];
-            {
-                const uint32_t nb = cdiv(fp.spill_hi - fp.spill_lo, 256);
-                range_pairs_kernel<K, PW><<<dim3(nb, nb), 256, 0, s>>>(bp, fp.spill_lo, fp.spill_hi);
-            }
+            const uint32_t nb = cdiv(fp.spill_hi - fp.spill_lo, 256);
+            range_pairs_kernel<K, PW><<<dim3(nb, nb), 256, 0, s>>>(bp, fp.spill_lo, fp.spill_hi);
             tt.launches++;
+        } else if (fp.spill_hi > fp.spill_lo + 1) {
+            // many spilled uniques: pass 0 among themselves the ordinary way (their bucket mates spilled too)
+            FQD_TRY(stage_passes<K, PW>(ctx, job, codec, uq, f, 0, 1, st, tt, 0, 1, fp.spill_lo));
         }
     }
     FQD_TRY(stage_passes<K, PW>(ctx, job, codec, uq, f, 0, 1, st, tt, first_pass));

@@ -168,6 +168,10 @@ __device__ __forceinline__ void load_key_stream(const uint32_t *__restrict__ uke
 constexpr int PART_RW = 8;                 // the plan handles 32-byte records (keys up to 6 words)
 constexpr int TILE_R = 1024;               // records per partition region = one shared-memory tile
 constexpr uint32_t WARP_FULL = 0xFFFFFFFFu;
+// salt of the hash that spreads records over the tiles by their pigeonhole block 0: it must not be the
+// pass-0 signature itself, or the uniques of a few tiles would land in a few tiles again when a pass
+// re-partitions just them (the spill path)
+constexpr uint64_t PART_SALT = 0x5bd1e995ull << 32;
 
 struct PartParams {
     uint32_t *buf;         // nparts regions of TILE_R records of PART_RW words; null = not partitioning
@@ -198,9 +202,14 @@ __device__ __forceinline__ void store_rec_stream(uint32_t *p, const uint32_t (&w
 
 // Append one 32-byte record to partition `part`: one atomic on the partition's cursor and one
 // 256-bit store; the L2 assembles the nparts write streams into full lines.
+__device__ __forceinline__ void part_place(const PartParams &Q, uint32_t part, uint32_t pos, const uint32_t (&e)[PART_RW]);
 __device__ __forceinline__ void part_append(const PartParams &Q, uint32_t part, const uint32_t (&e)[PART_RW])
 {
-    const uint32_t pos = atomicAdd(Q.cursor + part, 1u);
+    part_place(Q, part, atomicAdd(Q.cursor + part, 1u), e);
+}
+// the store half: `pos` is what the cursor atomic returned
+__device__ __forceinline__ void part_place(const PartParams &Q, uint32_t part, uint32_t pos, const uint32_t (&e)[PART_RW])
+{
     if (pos < (uint32_t)TILE_R) {
         store_rec_stream(Q.buf + ((size_t)part * TILE_R + pos) * PART_RW, e);
     } else if (Q.spill) {   // (without a spill buffer the tile kernel sees cursor > TILE_R and flags the overflow)
@@ -516,7 +525,7 @@ static __global__ void __launch_bounds__(256) ingest_kernel(const __grid_constan
             continue;
         }
         // (records partitioned by their pigeonhole block 0 never need the hash of the whole key)
-        hash[r] = (P.part.buf && P.part_blocks) ? block0_hash(key[r], block_start(klen, 1, P.part_blocks), (uint64_t)klen)
+        hash[r] = (P.part.buf && P.part_blocks) ? block0_hash(key[r], block_start(klen, 1, P.part_blocks), PART_SALT | klen)
                                                 : hash_key(key[r]);
         if constexpr (ROWS > 1) {
             const uint32_t *home = P.tab.table + __umul64hi(hash[r], P.tab.capacity) * RW;
@@ -666,6 +675,7 @@ __device__ __forceinline__ bool uf_union(uint32_t *parent, uint32_t a, uint32_t 
 
 struct PassParams {
     uint32_t U;
+    uint32_t u_lo;          // streaming plan: the pass covers the uniques [u_lo, U) only
     const uint32_t *ukey;
     const uint32_t *ucount;
     int d, edit, varlen, method;

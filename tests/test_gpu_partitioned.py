@@ -149,3 +149,19 @@ def test_lean_partition_kernel_rows_and_foreign_bytes(gpu_ctx, oracle, L):
     dirty[4000, 0] = ord("R")
     want = oracle.cluster(dirty, None, 1, False, "directional", 1.0)
     assert_same(cluster_keys(dirty, None, 1, False, "directional", 1.0, context=gpu_ctx), want, f"lean/{L}/foreign bytes")
+
+
+def test_many_spilled_uniques_redo_pass0_as_a_ranged_pass(gpu_ctx, oracle):
+    """Dozens of heavy keys: thousands of uniques leave the dedupe stage through the spill path; the
+    fused pass 0 is completed by a streaming pass over just those uniques (not by brute force)."""
+    cfg = synth.CONFIGS["cfg5"].scaled(50000)
+    keys, lens, quals = synth.SynthSource(cfg).reads()
+    rng = np.random.default_rng(8)
+    heavy = np.concatenate([np.repeat(keys[i:i + 1], 950, axis=0) for i in range(100, 180)])
+    allk = np.concatenate([keys, heavy])
+    allk = allk[rng.permutation(len(allk))]
+    for method in ("directional", "highest_count"):
+        want = oracle.cluster(allk, None, 1, False, method, 1.0)
+        got = cluster_keys(allk, None, 1, False, method, 1.0, context=gpu_ctx)
+        assert_same(got, want, f"many spilled/{method}")
+        assert got.stats["plan_flags"] & 5 == 5      # streaming dedupe with fused pass 0
