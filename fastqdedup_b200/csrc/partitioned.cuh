@@ -45,19 +45,54 @@ static_assert(TILE_R <= 1024, "tile-local indices are packed into 10 bits");
 constexpr uint32_t TILE_EMPTY = 0xFFFFFFFFu;
 constexpr uint32_t EDGE_ONE = 0x80000000u; // edge flag: both ends have count 1 (also joins the count-1 forest)
 
-__device__ __forceinline__ void stage_tile(uint32_t *recs, uint32_t *tab, const uint32_t *src, uint32_t cnt)
-{
-    const uint4 *s4 = reinterpret_cast<const uint4 *>(src);
-    uint4 *d4 = reinterpret_cast<uint4 *>(recs);
-    for (uint32_t i = threadIdx.x; i < cnt * (PART_RW / 4); i += TILE_THREADS) d4[i] = __ldcs(s4 + i);
-    for (uint32_t i = threadIdx.x; i < (uint32_t)TILE_T; i += TILE_THREADS) tab[i] = TILE_EMPTY;
-}
-
 __device__ __forceinline__ void tile_load_rec(const uint32_t *recs, uint32_t i, uint32_t (&e)[PART_RW])
 {
     const uint4 *r4 = reinterpret_cast<const uint4 *>(recs + (size_t)i * PART_RW);
     const uint4 a = r4[0], b = r4[1];
     e[0] = a.x; e[1] = a.y; e[2] = a.z; e[3] = a.w; e[4] = b.x; e[5] = b.y; e[6] = b.z; e[7] = b.w;
+}
+
+// ONE bulk asynchronous copy (TMA engine: cp.async.bulk global -> shared, completion on an mbarrier,
+// evict-first in the L2: the data is read exactly once) of `bytes` bytes (16-byte aligned, a multiple of
+// 16).  Called by every thread of the block; `between` runs while the copy is in flight; returns with
+// the data (and whatever `between` wrote to shared memory) visible to the whole block.
+template <typename Between>
+__device__ __forceinline__ void bulk_load_to_shared(void *dst, const void *src, uint32_t bytes, Between between)
+{
+    __shared__ __align__(8) uint64_t mbar;
+    const uint32_t mbar_a = (uint32_t)__cvta_generic_to_shared(&mbar);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar_a), "r"(1) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint64_t policy;
+        asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar_a), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                     ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src), "r"(bytes), "r"(mbar_a), "l"(policy)
+                     : "memory");
+    }
+    between();
+    uint32_t done;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(mbar_a), "r"(0) : "memory");
+    } while (!done);
+    __syncthreads();
+}
+__device__ __forceinline__ void bulk_load_to_shared(void *dst, const void *src, uint32_t bytes)
+{
+    bulk_load_to_shared(dst, src, bytes, [] {});
+}
+
+// Stage one tile (cnt >= 1 records) while all threads clear `tab_n` table entries.
+__device__ __forceinline__ void stage_tile(uint32_t *recs, uint32_t *tab, uint32_t tab_n, const uint32_t *src, uint32_t cnt)
+{
+    bulk_load_to_shared(recs, src, cnt * (PART_RW * 4u), [&] {
+        for (uint32_t i = threadIdx.x; i < tab_n; i += TILE_THREADS) tab[i] = TILE_EMPTY;
+    });
 }
 
 // ---- the partition pass of the common large job -----------------------------------------------------
@@ -79,15 +114,13 @@ static __global__ void __launch_bounds__(256) partition_dna_kernel(const __grid_
     const uint32_t nblk = (uint32_t)min((uint64_t)(256u * ROWS), P.n - t0);
     const uint32_t nwords = nblk * NW;
     const uint32_t *src = reinterpret_cast<const uint32_t *>(P.keys + t0 * (4u * NW));
-    if ((reinterpret_cast<uintptr_t>(src) & 15u) == 0) {
-        const uint4 *s4 = reinterpret_cast<const uint4 *>(src);
-        uint4 *d4 = reinterpret_cast<uint4 *>(stage);
-        for (uint32_t i = tid; i < nwords / 4; i += 256) d4[i] = __ldcs(s4 + i);
-        for (uint32_t i = (nwords & ~3u) + tid; i < nwords; i += 256) stage[i] = __ldcs(src + i);
+    if ((reinterpret_cast<uintptr_t>(src) & 15u) == 0 && (nwords & 3u) == 0) {
+        // one bulk asynchronous copy (TMA engine) instead of a load/store loop: the pass is instruction-bound
+        bulk_load_to_shared(stage, src, nwords * 4u);
     } else {
         for (uint32_t i = tid; i < nwords; i += 256) stage[i] = __ldcs(src + i);
+        __syncthreads();
     }
-    __syncthreads();
     uint32_t e[ROWS][PART_RW], part[ROWS], pos[ROWS];
     bool go[ROWS];
 #pragma unroll
@@ -283,8 +316,7 @@ static __global__ void __launch_bounds__(TILE_THREADS) dedupe_tile_kernel(const 
         if (tid == 0) O.oversize[atomicAdd(O.n_oversize, 1u)] = p;
         return;
     }
-    stage_tile(recs, tab, Q.buf + (size_t)p * TILE_R * PART_RW, cnt);
-    __syncthreads();
+    stage_tile(recs, tab, TILE_T, Q.buf + (size_t)p * TILE_R * PART_RW, cnt);
 
     // A record either wins an empty table entry (it becomes the representative of its key) or
     // meets the representative and adds its weight / lowers the first index there.
@@ -450,9 +482,7 @@ static __global__ void __launch_bounds__(TILE_THREADS) bucket_tile_kernel(const 
         if (tid == 0) *E.overflow = 1u;
         return;
     }
-    const uint4 *s4 = reinterpret_cast<const uint4 *>(Q.buf + (size_t)p * TILE_R * PART_RW);
-    uint4 *d4 = reinterpret_cast<uint4 *>(recs);
-    for (uint32_t i = tid; i < cnt * (PART_RW / 4); i += TILE_THREADS) d4[i] = __ldcs(s4 + i);
+    stage_tile(recs, tab, 0, Q.buf + (size_t)p * TILE_R * PART_RW, cnt);   // (the pass clears the table itself)
     uint32_t merges = 0, cand = 0;
     tile_bucket_pass<K, PW, true>(   // (starts with a barrier)
         recs, tab, TILE_T, s_edges, TILE_E, cnt, [](uint32_t k) { return k; },
