@@ -297,11 +297,21 @@ struct DedupeOut {
 // as the block multimap (see bucket_tile_kernel) and pass 0 never touches HBM again.  The
 // forest does not exist yet (U is unknown), so hits can only be deferred: when a buffer is
 // too small the overflow flag makes the caller run pass 0 the ordinary way as well.
+// EMIT (with FUSED): the uniques leave a second time as {key, count, id} entries of the NEXT pass,
+// appended to the tiles of its block hash (X.next) -- that pass then starts with its tiles in
+// place instead of reading the unique set back and partitioning it.
+struct NextPass {
+    PartParams next;        // next.buf == null: nothing to emit
+    uint32_t st, bl;        // block of the next pass for keys of max_len symbols (cf. PassParams::fix_st)
+    int pass_j;
+};
+
 template <int K, int PW, bool FUSED>
 static __global__ void __launch_bounds__(TILE_THREADS) dedupe_tile_kernel(const __grid_constant__ PartParams Q,
                                                                           const __grid_constant__ DedupeOut O,
                                                                           const __grid_constant__ PassParams P,
-                                                                          const __grid_constant__ EdgeSink E)
+                                                                          const __grid_constant__ EdgeSink E,
+                                                                          const __grid_constant__ NextPass X)
 {
     constexpr int KW = K * PW, RW = slot_words(KW);
     static_assert(RW == PART_RW, "partitioned plan: 32-byte records");
@@ -378,7 +388,23 @@ static __global__ void __launch_bounds__(TILE_THREADS) dedupe_tile_kernel(const 
         for (int j = 0; j < KW; j++) O.ukey[(size_t)pos * KW + j] = e[j];
         O.ucount[pos] = e[KW];
         O.ufirst[pos] = e[KW + 1];
-        if constexpr (FUSED) recs[(size_t)i * PART_RW + KW + 1] = pos;   // the record now carries its unique id
+        if constexpr (FUSED) {
+            recs[(size_t)i * PART_RW + KW + 1] = pos;   // the record now carries its unique id
+            if (X.next.buf) {
+                Key<K, PW> ki;
+#pragma unroll
+                for (int j = 0; j < KW; j++) ki.w[j] = e[j];
+                uint32_t st = X.st, bl = X.bl, len = P.max_len;
+                if (P.varlen) {
+                    len = key_length(ki, P.pad_code, P.max_len);
+                    st = block_start(len, (uint32_t)X.pass_j, (uint32_t)P.d + 1u);
+                    bl = block_start(len, (uint32_t)X.pass_j + 1u, (uint32_t)P.d + 1u) - st;
+                }
+                const uint64_t sig = block_hash(ki, st, bl, ((uint64_t)X.pass_j << 32) | len);   // == pass_variant of that pass
+                e[KW + 1] = pos;
+                part_append(X.next, part_of(sig, X.next.nparts), e);
+            }
+        }
     }
 
     if constexpr (FUSED) {

@@ -96,6 +96,10 @@ struct FusedPass0 {
     uint32_t edge_cap = 0;
     uint32_t *aux = nullptr;   // [0] edge count, [1] overflow flag
     uint32_t spill_lo = 0, spill_hi = 0;   // unique ids that came out of the spill path (compared by brute force)
+    // pass 1 pre-partitioned by the dedupe tiles (NextPass): tiles sized by a guess of the unique count
+    uint32_t *next_buf = nullptr, *next_cursor = nullptr;
+    uint32_t next_nparts = 0;
+    bool next_valid = false;
 };
 constexpr uint32_t FUSED_SPILL_BRUTE = 4096;   // at most this many spilled uniques are compared by brute force
 
@@ -314,9 +318,17 @@ int stage_dedupe(fqd_context *ctx, const DeviceJob &job, const Codec &codec, uin
                 p0.fix_bl = block_start(job.max_len, 1u, (uint32_t)job.d + 1u);
                 p0.dominated = fp->dominated; p0.dead = fp->dead; p0.ctr = ctx->d_ctr;
                 sink0 = EdgeSink{fp->edges, fp->aux, fp->edge_cap, fp->aux + 1};
-                dedupe_tile_kernel<K, PW, true><<<nparts, TILE_THREADS, 0, s>>>(pp.part, out, p0, sink0);
+                NextPass nx{};
+                if (fp->next_buf) {
+                    FQD_CUDA(cudaMemsetAsync(fp->next_cursor, 0, (size_t)fp->next_nparts * 4, s));
+                    nx.next = PartParams{fp->next_buf, fp->next_cursor, fp->next_nparts, nullptr, nullptr, 0};
+                    nx.pass_j = 1;
+                    nx.st = block_start(job.max_len, 1u, (uint32_t)job.d + 1u);
+                    nx.bl = block_start(job.max_len, 2u, (uint32_t)job.d + 1u) - nx.st;
+                }
+                dedupe_tile_kernel<K, PW, true><<<nparts, TILE_THREADS, 0, s>>>(pp.part, out, p0, sink0, nx);
             } else {
-                dedupe_tile_kernel<K, PW, false><<<nparts, TILE_THREADS, 0, s>>>(pp.part, out, p0, sink0);
+                dedupe_tile_kernel<K, PW, false><<<nparts, TILE_THREADS, 0, s>>>(pp.part, out, p0, sink0, NextPass{});
             }
             tt.launches++;
             FQD_CUDA(cudaGetLastError());
@@ -367,6 +379,7 @@ int stage_dedupe(fqd_context *ctx, const DeviceJob &job, const Codec &codec, uin
                     fp->spill_lo = h_aux[2];
                     fp->spill_hi = U;
                     fp->done = !h_f[1];
+                    fp->next_valid = fp->done && fp->next_buf != nullptr;
                     if (getenv("FQD_TRACE"))
                         fprintf(stderr, "[fqd trace] fused pass 0: edges %u overflow %u oversize partitions %u spill %u (%u uniques) -> %s\n",
                                 h_f[0], h_f[1], h_aux[3], h_aux[0], U - h_aux[2], fp->done ? "done" : "redo");
@@ -496,7 +509,7 @@ int stage_forest_alloc(fqd_context *ctx, int method, uint32_t U, Forest &f, cons
 template <int K, int PW>
 int stage_passes(fqd_context *ctx, const DeviceJob &job, const Codec &codec, const Uniques &uq,
                  Forest &f, int rank, int world, fqd_cluster_stats *st, StageTimes &tt, int first_pass = 0,
-                 int end_pass = -1, uint32_t u_lo = 0)
+                 int end_pass = -1, uint32_t u_lo = 0, const FusedPass0 *pre = nullptr)
 {
     constexpr int KW = K * PW, FW = fat_words(KW);
     cudaStream_t s = ctx->stream;
@@ -577,38 +590,69 @@ int stage_passes(fqd_context *ctx, const DeviceJob &job, const Codec &codec, con
         return FQD_OK;
     };
 
+    // one Hamming pass in tiles: partition (unless the dedupe tiles already did it), tile kernel, hooks
+    auto tile_pass = [&](int j, bool prepart) -> int {
+        if constexpr (FW == PART_RW) {
+            pp.pass_j = j;
+            pp.fix_st = block_start(job.max_len, (uint32_t)j, (uint32_t)job.d + 1u);
+            pp.fix_bl = block_start(job.max_len, (uint32_t)j + 1u, (uint32_t)job.d + 1u) - pp.fix_st;
+            PartParams qp{pbuf, pcursor + (size_t)j * nparts, nparts, nullptr, nullptr, 0};
+            sink.n_edges = paux + 4 * j;
+            sink.overflow = paux + 4 * j + 1;
+            if (prepart) {
+                // (only the uniques that left the dedupe stage through the spill path are missing)
+                qp = PartParams{pre->next_buf, pre->next_cursor, pre->next_nparts, nullptr, nullptr, 0};
+                if (pre->spill_hi > pre->spill_lo) {
+                    PassParams sp = pp;
+                    sp.u_lo = pre->spill_lo;
+                    bucket_partition_kernel<K, PW><<<cdiv(pre->spill_hi - pre->spill_lo, 256 * BP_ROWS), 256, 0, s>>>(sp, qp);
+                    tt.launches++;
+                }
+            } else {
+                bucket_partition_kernel<K, PW><<<cdiv(U - u_lo, 256 * BP_ROWS), 256, 0, s>>>(pp, qp);
+                tt.launches++;
+            }
+            FQD_CUDA(cudaEventRecord(cev[2 * j], s));
+            bucket_tile_kernel<K, PW><<<qp.nparts, TILE_THREADS, 0, s>>>(qp, pp, sink);
+            apply_edges_kernel<<<ctx->sm_count * 8, 256, 0, s>>>(sink.edges, sink.n_edges, sink.cap, f.parent_full, f.parent_one,
+                                                                ctx->d_ctr);
+            FQD_CUDA(cudaEventRecord(cev[2 * j + 1], s));
+            FQD_CUDA(cudaGetLastError());
+            tt.launches += 2;
+        }
+        return FQD_OK;
+    };
+    auto read_aux = [&](std::vector<uint32_t> &h_aux) -> int {
+        h_aux.assign((size_t)npass * 4, 0);
+        FQD_CUDA(cudaMemcpyAsync(h_aux.data(), paux, h_aux.size() * 4, cudaMemcpyDeviceToHost, s));
+        FQD_CUDA(cudaStreamSynchronize(s));
+        return FQD_OK;
+    };
+
     for (int attempt = 0; attempt < 2; attempt++) {
         if (use_part) {
-            if constexpr (FW == PART_RW) {
-                FQD_CUDA(cudaMemsetAsync(pcursor, 0, (size_t)npass * nparts * 4, s));
-                FQD_CUDA(cudaMemsetAsync(paux, 0, (size_t)npass * 16, s));
-                for (int j = first_pass; j < npass; j++) {
-                    pp.pass_j = j;
-                    pp.fix_st = block_start(job.max_len, (uint32_t)j, (uint32_t)job.d + 1u);
-                    pp.fix_bl = block_start(job.max_len, (uint32_t)j + 1u, (uint32_t)job.d + 1u) - pp.fix_st;
-                    PartParams qp{pbuf, pcursor + (size_t)j * nparts, nparts, nullptr, nullptr, 0};
-                    sink.n_edges = paux + 4 * j;
-                    sink.overflow = paux + 4 * j + 1;
-                    bucket_partition_kernel<K, PW><<<cdiv(U - u_lo, 256 * BP_ROWS), 256, 0, s>>>(pp, qp);
-                    FQD_CUDA(cudaEventRecord(cev[2 * j], s));
-                    bucket_tile_kernel<K, PW><<<nparts, TILE_THREADS, 0, s>>>(qp, pp, sink);
-                    apply_edges_kernel<<<ctx->sm_count * 8, 256, 0, s>>>(sink.edges, sink.n_edges, sink.cap, f.parent_full,
-                                                                        f.parent_one, ctx->d_ctr);
-                    FQD_CUDA(cudaEventRecord(cev[2 * j + 1], s));
-                    FQD_CUDA(cudaGetLastError());
-                    tt.launches += 3;
-                }
-                // passes whose partitions outgrew a tile (few distinct block values): counting-sort plan
-                std::vector<uint32_t> h_aux((size_t)npass * 4, 0);
-                FQD_CUDA(cudaMemcpyAsync(h_aux.data(), paux, h_aux.size() * 4, cudaMemcpyDeviceToHost, s));
-                FQD_CUDA(cudaStreamSynchronize(s));
-                tt.passes_partitioned = true;
-                for (int j = first_pass; j < npass; j++) {
-                    if (getenv("FQD_TRACE"))
-                        fprintf(stderr, "[fqd trace] pass %d over uniques [%u, %u): %u tiles, %u edges%s\n", j, u_lo, U, nparts,
-                                h_aux[4 * j], h_aux[4 * j + 1] ? ", a tile overflowed -> counting-sort plan" : "");
-                    if (h_aux[4 * j + 1]) { tt.passes_partitioned = false; FQD_TRY(legacy_pass(j)); }
-                }
+            FQD_CUDA(cudaMemsetAsync(pcursor, 0, (size_t)npass * nparts * 4, s));
+            FQD_CUDA(cudaMemsetAsync(paux, 0, (size_t)npass * 16, s));
+            const bool pre1 = pre && pre->next_valid && attempt == 0 && u_lo == 0;   // pass 1 arrives pre-partitioned
+            for (int j = first_pass; j < npass; j++) FQD_TRY(tile_pass(j, pre1 && j == 1));
+            std::vector<uint32_t> h_aux;
+            FQD_TRY(read_aux(h_aux));
+            if (pre1 && first_pass <= 1 && npass > 1 && h_aux[4 * 1 + 1]) {
+                // more uniques than the dedupe stage guessed overflowed the pre-partitioned tiles: pass 1 again,
+                // partitioned the ordinary way (the edges it already found are true edges: harmless)
+                if (getenv("FQD_TRACE")) fprintf(stderr, "[fqd trace] pass 1: pre-partitioned tiles overflowed, partitioning again\n");
+                FQD_CUDA(cudaMemsetAsync(paux + 4, 0, 16, s));
+                FQD_TRY(tile_pass(1, false));
+                FQD_TRY(read_aux(h_aux));
+            }
+            // passes whose partitions outgrew a tile (few distinct block values): counting-sort plan
+            tt.passes_partitioned = true;
+            for (int j = first_pass; j < npass; j++) {
+                if (getenv("FQD_TRACE"))
+                    fprintf(stderr, "[fqd trace] pass %d over uniques [%u, %u): %u edges%s%s\n", j, u_lo, U, h_aux[4 * j],
+                            pre1 && j == 1 ? " (tiles filled by the dedupe stage)" : "",
+                            h_aux[4 * j + 1] ? ", a tile overflowed -> counting-sort plan" : "");
+                if (h_aux[4 * j + 1]) { tt.passes_partitioned = false; FQD_TRY(legacy_pass(j)); }
             }
         } else {
             for (int j = first_pass; j < npass; j++) FQD_TRY(legacy_pass(j));
@@ -724,6 +768,13 @@ int run_typed(fqd_context *ctx, const DeviceJob &job, const Codec &codec, fqd_cl
         FQD_TRY(arena(ctx, (size_t)fp.edge_cap, &fp.edges));
         FQD_TRY(arena(ctx, 4, &fp.aux));
         FQD_CUDA(cudaMemsetAsync(fp.aux, 0, 16, s));
+        if (job.d >= 1 && !getenv("FQD_NO_NEXT_EMIT")) {
+            // the dedupe tiles also hand every unique to its pass-1 tile; U is unknown, guess n/2
+            // (more uniques than that overflow those tiles and pass 1 partitions the ordinary way)
+            fp.next_nparts = tile_partitions(std::max<uint64_t>(job.n / 2, 1u << 16));
+            FQD_TRY(arena(ctx, (size_t)fp.next_nparts * TILE_R * PART_RW, &fp.next_buf));
+            FQD_TRY(arena(ctx, fp.next_nparts, &fp.next_cursor));
+        }
         if (job.method == METHOD_DIRECTIONAL) {
             FQD_TRY(arena(ctx, job.n, &fp.dominated));
             FQD_TRY(arena(ctx, job.n, &fp.dead));
@@ -766,7 +817,7 @@ int run_typed(fqd_context *ctx, const DeviceJob &job, const Codec &codec, fqd_cl
             FQD_TRY(stage_passes<K, PW>(ctx, job, codec, uq, f, 0, 1, st, tt, 0, 1, fp.spill_lo));
         }
     }
-    FQD_TRY(stage_passes<K, PW>(ctx, job, codec, uq, f, 0, 1, st, tt, first_pass));
+    FQD_TRY(stage_passes<K, PW>(ctx, job, codec, uq, f, 0, 1, st, tt, first_pass, -1, 0, &fp));
     if (job.method == METHOD_ADJACENCY) {
         FQD_TRY(fetch_counters(ctx));
         f.n_edges = ctx->h_ctr->n_edges;

@@ -26,7 +26,7 @@ ctx = _native.Context(0)
 kp = ctx.upload(keys)
 del keys
 
-KNOBS = ("FQD_NO_LEAN", "FQD_TILE_FILL_PCT", "FQD_NO_FUSED_PASS0", "FQD_NO_PARTITION", "FQD_NO_PARTITION_PASSES", "FQD_NO_SWAR")
+KNOBS = ("FQD_NO_NEXT_EMIT", "FQD_NO_LEAN", "FQD_TILE_FILL_PCT", "FQD_NO_FUSED_PASS0", "FQD_NO_PARTITION", "FQD_NO_PARTITION_PASSES", "FQD_NO_SWAR")
 
 
 def run(tag, **env):
@@ -49,8 +49,8 @@ def run(tag, **env):
 
 run("legacy (no partition)", FQD_NO_PARTITION=1)
 run("default")
-run("general ingest kernel", FQD_NO_LEAN=1)
+run("pass 1 partitioned separately", FQD_NO_NEXT_EMIT=1)
 run("no fused pass 0", FQD_NO_FUSED_PASS0=1)
-for fill in (50, 70, 80):
+for fill in (70,):
     run(f"fill={fill}", FQD_TILE_FILL_PCT=fill)
 ctx.device_free(kp)
