@@ -374,16 +374,18 @@ def run_ours(args, rank, world, local_rank):
     mean = lambda f: float(np.mean([getattr(s_, f) for s_ in stats]))
     streaming = bool(st.plan_flags & 1)
     fused = bool(st.plan_flags & 4)
+    emitted = bool(st.plan_flags & 8)      # the dedupe tiles also wrote the bucket-ordered entries of pass 1
     passes_left = st.n_passes - (1 if fused else 0)
     read_b = (n * L if filter_on else 0) + st.number_of_sequences * W
     if streaming:
         groups = [
             (("partition_dna_kernel<2,9>" if not filter_on else "ingest_kernel<3,2> partition mode") + " (pack + hash + partition into tiles)",
              mean("ms_partition_kernel"), read_b),
-            ("dedupe_tile_kernel<3,2>" + (" fused with pass 0" if fused else "") + " (exact dedupe in shared-memory tiles)",
-             mean("ms_dedupe_kernel"), U * (R + 4) + (3 * U * R if fused else 0)),
-            (f"{passes_left} pass(es): bucket_partition_kernel + bucket_tile_kernel + apply_edges_kernel",
-             mean("ms_neighbour"), 3 * passes_left * U * R),
+            ("dedupe_tile_kernel<3,2>" + (" fused with pass 0" if fused else "") + (" + pass-1 tiles" if emitted else "") +
+             " (exact dedupe in shared-memory tiles)",
+             mean("ms_dedupe_kernel"), U * (R + 4) + (3 * U * R if fused else 0) + (U * R if emitted else 0)),
+            (f"{passes_left} pass(es): " + ("" if emitted else "bucket_partition_kernel + ") + "bucket_tile_kernel + apply_edges_kernel",
+             mean("ms_neighbour"), 3 * passes_left * U * R - (U * R if emitted else 0)),
             ("root_best_kernel + select_kernel (dissection + keep bitmap)", mean("ms_select"), 9 * U),
         ]
     else:
@@ -414,7 +416,8 @@ def run_ours(args, rank, world, local_rank):
                                "achieved_gbs": total_b / (ms_per_step / 1e3) / 1e9,
                                "frac": total_b / (ms_per_step / 1e3) / 1e9 / peak},
                 "kernels": kernels,
-                "plan": {"streaming_dedupe": streaming, "pass0_fused": fused, "streaming_passes": bool(st.plan_flags & 2)}}
+                "plan": {"streaming_dedupe": streaming, "pass0_fused": fused, "pass1_tiles_from_dedupe": emitted,
+                         "streaming_passes": bool(st.plan_flags & 2)}}
 
     # ---- CPU baseline on a bounded sample of the same workload ----
     sample = min(n, env_int("FQD_CPU_SAMPLE", 2_000_000))

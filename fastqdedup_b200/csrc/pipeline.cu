@@ -83,7 +83,7 @@ struct Forest {
 struct StageTimes {
     float table_clear = 0, ingest_kernel = 0, dedupe_kernel = 0, ingest = 0, compare = 0, h2d = 0;
     uint32_t launches = 0;
-    bool streamed = false, partitioned = false, passes_partitioned = false, pass0_fused = false;
+    bool streamed = false, partitioned = false, passes_partitioned = false, pass0_fused = false, pass1_emitted = false;
 };
 
 // Pass 0 of the Hamming search done inside the dedupe tiles (partitioned.cuh, FUSED).  The flag
@@ -645,6 +645,7 @@ int stage_passes(fqd_context *ctx, const DeviceJob &job, const Codec &codec, con
                 FQD_TRY(tile_pass(1, false));
                 FQD_TRY(read_aux(h_aux));
             }
+            else if (pre1 && first_pass <= 1 && npass > 1) tt.pass1_emitted = true;
             // passes whose partitions outgrew a tile (few distinct block values): counting-sort plan
             tt.passes_partitioned = true;
             for (int j = first_pass; j < npass; j++) {
@@ -842,7 +843,7 @@ int run_typed(fqd_context *ctx, const DeviceJob &job, const Codec &codec, fqd_cl
     st->ms_bucket_build = st->ms_neighbour - tt.compare;
     st->launches = tt.launches;
     st->plan_flags = (tt.partitioned ? FQD_PLAN_DEDUPE_PARTITIONED : 0u) | (tt.passes_partitioned ? FQD_PLAN_PASSES_PARTITIONED : 0u) |
-                     (tt.pass0_fused ? FQD_PLAN_PASS0_FUSED : 0u);
+                     (tt.pass0_fused ? FQD_PLAN_PASS0_FUSED : 0u) | (tt.pass1_emitted ? FQD_PLAN_PASS1_TILES_EMITTED : 0u);
     st->ms_partition_kernel = tt.partitioned ? tt.ingest_kernel : 0.f;
     st->ms_dedupe_kernel = tt.dedupe_kernel;
     publish_result(ctx, uq, f, job.n, c2.n_selected);

@@ -135,6 +135,7 @@ typedef struct {
 #define FQD_PLAN_DEDUPE_PARTITIONED 1u /* exact dedupe: partition by hash, tables in shared-memory tiles */
 #define FQD_PLAN_PASSES_PARTITIONED 2u /* Hamming passes: partition by block hash, multimap in shared-memory tiles */
 #define FQD_PLAN_PASS0_FUSED 4u        /* pass 0 ran inside the dedupe tiles (records partitioned by block 0) */
+#define FQD_PLAN_PASS1_TILES_EMITTED 8u /* the dedupe tiles also filled the tiles of pass 1 */
 
 /* Runs the job.  On success the per-unique result stays in the context until the next
  * job.  keep_bitmap (optional, in the job's memory space, (n_records+31)/32 uint32 words,

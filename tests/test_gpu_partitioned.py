@@ -165,3 +165,19 @@ def test_many_spilled_uniques_redo_pass0_as_a_ranged_pass(gpu_ctx, oracle):
         got = cluster_keys(allk, None, 1, False, method, 1.0, context=gpu_ctx)
         assert_same(got, want, f"many spilled/{method}")
         assert got.stats["plan_flags"] & 5 == 5      # streaming dedupe with fused pass 0
+
+
+def test_pass1_tiles_from_the_dedupe_stage_overflow_and_are_redone(gpu_ctx, oracle, reference):
+    """Hardly any duplicates: far more uniques than the dedupe stage guessed (n/2) overflow the pass-1
+    tiles it fills; pass 1 is partitioned again the ordinary way and the result still matches."""
+    rng = np.random.default_rng(21)
+    mol = rng.choice(list(b"ACGT"), size=(150000, 24)).astype(np.uint8)
+    extra = mol[rng.integers(0, len(mol), size=30000)].copy()
+    pos = rng.integers(0, 24, size=len(extra))
+    extra[np.arange(len(extra)), pos] = rng.choice(list(b"ACGT"), size=len(extra)).astype(np.uint8)
+    rows = np.concatenate([mol, extra])
+    rows = rows[rng.permutation(len(rows))]
+    want = oracle.ref_cluster(rows, None, 1, False, "directional", 1.0)
+    got = cluster_keys(rows, None, 1, False, "directional", 1.0, context=gpu_ctx)
+    assert_same(got, want, "pass-1 tile overflow")
+    assert got.stats["plan_flags"] & 7 == 7
