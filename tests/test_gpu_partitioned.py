@@ -181,3 +181,24 @@ def test_pass1_tiles_from_the_dedupe_stage_overflow_and_are_redone(gpu_ctx, orac
     got = cluster_keys(rows, None, 1, False, "directional", 1.0, context=gpu_ctx)
     assert_same(got, want, "pass-1 tile overflow")
     assert got.stats["plan_flags"] & 7 == 7
+
+
+def test_streaming_plan_with_record_multiplicities(gpu_ctx, oracle):
+    """record_counts through the streaming plan: weights accumulate in the tiles, duplicates of a
+    pre-counted key still merge, the statistics count reads."""
+    rng = np.random.default_rng(3)
+    strings = list({bytes(rng.choice(list(b"ACGT"), size=12).astype(np.uint8)) for _ in range(3000)})
+    strings = strings + strings[:500]                       # some keys appear twice in the pre-counted list
+    counts = rng.integers(1, 40, size=len(strings)).astype(np.uint32)
+    expanded = [s for s, c in zip(strings, counts) for _ in range(int(c))]
+    for method in METHODS:
+        want = oracle.cluster(expanded, None, 1, False, method, 1.0)
+        got = cluster_keys(strings, None, 1, False, method, 1.0, counts=counts, context=gpu_ctx)
+        assert got.stats["plan_flags"] & 1
+        assert got.number_of_sequences == want["number_of_sequences"]
+        assert got.number_of_uniques == want["number_of_uniques"]
+        assert got.number_of_clusters == want["number_of_clusters"]
+        assert got.number_selected == want["number_selected"]
+        sel_got = sorted(strings[i] for i in got.selected_first.tolist())
+        sel_want = sorted(expanded[i] for i in want["selected_first"].tolist())
+        assert sel_got == sel_want
