@@ -3,8 +3,8 @@
 // Random probes into an HBM-sized hash table (the single-table plan) pay one 128-byte DRAM line
 // per record and sit at ~30 % of HBM bandwidth; a counting sort of the bucket entries pays
 // random 32-byte scatter writes.  For large jobs both stages are therefore rebuilt around ONE
-// idea: PARTITION the 32-byte records by the top hash bits so finely (TILE_R = 1024 records per
-// region, ~65 % full) that one partition is one SHARED-MEMORY TILE, then give every partition
+// idea: PARTITION the 32-byte records by the top hash bits so finely (TILE_R = 512 records per
+// region, ~60 % full) that one partition is one SHARED-MEMORY TILE, then give every partition
 // to one thread block that stages it with coalesced streaming loads and does all the random
 // work -- hash probes, key compares, counting -- inside shared memory.  HBM only ever sees
 // streaming reads and writes; there is no table in HBM or L2 at all and no inter-block
@@ -39,8 +39,8 @@
 namespace fqd {
 
 constexpr int TILE_T = 2 * TILE_R;         // table entries per tile (load <= 0.5)
-constexpr int TILE_THREADS = 256;
-constexpr int TILE_E = 512;                // edges a tile buffers in shared memory before hooking inline
+constexpr int TILE_THREADS = 128;
+constexpr int TILE_E = 256;                // edges a tile buffers in shared memory before hooking inline
 static_assert(TILE_R <= 1024, "tile-local indices are packed into 10 bits");
 constexpr uint32_t TILE_EMPTY = 0xFFFFFFFFu;
 constexpr uint32_t EDGE_ONE = 0x80000000u; // edge flag: both ends have count 1 (also joins the count-1 forest)

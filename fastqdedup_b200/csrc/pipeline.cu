@@ -183,7 +183,7 @@ uint32_t env_u32(const char *name, uint32_t fallback)
     return e && *e ? (uint32_t)strtoul(e, nullptr, 10) : fallback;
 }
 
-// partitions of the streaming plan: regions of TILE_R records filled to ~65 % on average
+// partitions of the streaming plan: regions of TILE_R records filled to ~60 % on average
 uint32_t tile_partitions(uint64_t n)
 {
     const uint32_t fill_pct = std::min(90u, std::max(20u, env_u32("FQD_TILE_FILL_PCT", 60)));

@@ -166,7 +166,7 @@ __device__ __forceinline__ void load_key_stream(const uint32_t *__restrict__ uke
 // ---- partition buffers of the streaming plan (partitioned.cuh) ---------------------------------
 
 constexpr int PART_RW = 8;                 // the plan handles 32-byte records (keys up to 6 words)
-constexpr int TILE_R = 1024;               // records per partition region = one shared-memory tile
+constexpr int TILE_R = 512;                // records per partition region = one shared-memory tile
 constexpr uint32_t WARP_FULL = 0xFFFFFFFFu;
 // salt of the hash that spreads records over the tiles by their pigeonhole block 0: it must not be the
 // pass-0 signature itself, or the uniques of a few tiles would land in a few tiles again when a pass

@@ -157,7 +157,7 @@ def test_many_spilled_uniques_redo_pass0_as_a_ranged_pass(gpu_ctx, oracle):
     cfg = synth.CONFIGS["cfg5"].scaled(50000)
     keys, lens, quals = synth.SynthSource(cfg).reads()
     rng = np.random.default_rng(8)
-    heavy = np.concatenate([np.repeat(keys[i:i + 1], 950, axis=0) for i in range(100, 180)])
+    heavy = np.concatenate([np.repeat(keys[i:i + 1], 500, axis=0) for i in range(100, 200)])
     allk = np.concatenate([keys, heavy])
     allk = allk[rng.permutation(len(allk))]
     for method in ("directional", "highest_count"):
