@@ -51,6 +51,6 @@ run("legacy (no partition)", FQD_NO_PARTITION=1)
 run("default")
 run("pass 1 partitioned separately", FQD_NO_NEXT_EMIT=1)
 run("no fused pass 0", FQD_NO_FUSED_PASS0=1)
-for fill in (70,):
+for fill in (50, 70):
     run(f"fill={fill}", FQD_TILE_FILL_PCT=fill)
 ctx.device_free(kp)
