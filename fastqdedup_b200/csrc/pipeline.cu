@@ -113,9 +113,9 @@ int arena(fqd_context *ctx, size_t count, T **p)
 }
 
 // ---- stage 1: filter + pack + exact dedupe of this rank's records ----------------------------
-// Produces the dense unique arrays of `uq`.  Large jobs take the partitioned plan (streaming,
-// L2-resident tables); small ones, and jobs whose duplication is so skewed that a partition
-// overflows, take the single-table plan.
+// Produces the dense unique arrays of `uq`.  Large jobs take the streaming plan (records
+// partitioned into shared-memory sized tiles, partitioned.cuh); small ones, and jobs whose
+// duplication is so skewed that even the spill buffer overflows, take the single-table plan.
 
 // Launches `kernel(params)` over the records: in one go when they are in HBM, chunk by chunk
 // behind the H2D copies when they are still in host memory.

@@ -1,6 +1,8 @@
-// pipeline.cuh -- device kernels of the clustering path (sm_100a) and their launch plan.
+// pipeline.cuh -- device kernels of the clustering path (sm_100a): the single-table plan (small
+// jobs, long keys, Levenshtein passes, fallback), the dissection, the sharding helpers, and the
+// shared pieces of the streaming plan, whose kernels are in partitioned.cuh (included at the end).
 //
-// Stages (DESIGN.md has the data layout and the per-kernel roofline):
+// Stages of the single-table plan (DESIGN.md has the data layout and the per-kernel roofline):
 //   ingest   : per record quality filter (bit-exact double sum), bit-plane packing and
 //              exact dedupe with counts + first index in an open-addressing table in HBM
 //              (replaces Trie.add_sequence, reference _triemodule.c:222-288, and
