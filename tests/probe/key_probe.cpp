@@ -74,6 +74,25 @@ int run(int op, const HostCodec &hc, const uint8_t *a, uint32_t la, const uint8_
             return ok ? (key_equal<K, PW>(ks, ka) ? 1 : 0) : 2;
         }
         return -1;
+    case 9:   // straight-line packer for keys of exactly 4*NW symbols == table packing (or both reject)
+        if constexpr (K == 3) {
+            alignas(4) uint8_t buf[4 * 8 * PW + 8] = {};
+            memcpy(buf, a, la);
+            Key<K, PW> ks;
+            bool ok = false, known = true;
+            const uint32_t *w = reinterpret_cast<const uint32_t *>(buf);
+            if (la == 12) ok = pack_key_acgtn_fixed<PW, 3>(w, ks);
+            else if (la == 24) ok = pack_key_acgtn_fixed<PW, 6>(w, ks);
+            else if (la == 36) { if constexpr (PW >= 2) ok = pack_key_acgtn_fixed<PW, 9>(w, ks); else known = false; }
+            else if (la == 48) { if constexpr (PW >= 2) ok = pack_key_acgtn_fixed<PW, 12>(w, ks); else known = false; }
+            else known = false;
+            if (!known) return -1;
+            return ok ? (key_equal<K, PW>(ks, ka) ? 1 : 0) : 2;
+        }
+        return -1;
+    case 10:  // the partition hash of the leading block is a function of that block (and the salt) only
+        return block0_hash<K, PW>(ka, p2, 99) == block0_hash<K, PW>(kb, p2, 99) ? 1 : 0;
+    case 11: *out64 = hash_key32<K, PW>(ka); return 0;
     }
     return -1;
 }

@@ -11,7 +11,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SRC = os.path.join(ROOT, "tests", "probe", "key_probe.cpp")
 OUT = os.path.join(ROOT, "tests", "probe", "build", "key_probe.so")
 
-OPS = dict(hamming=0, myers=1, less=2, equal=3, length=4, blockeq=5, hash=6, symbol=7, swar=8)
+OPS = dict(hamming=0, myers=1, less=2, equal=3, length=4, blockeq=5, hash=6, symbol=7, swar=8, fixed=9,
+           block0eq=10, hash32=11)
 
 
 @pytest.fixture(scope="module")
@@ -32,8 +33,8 @@ def probe():
         out = ctypes.c_uint64()
         r = lib.key_probe(K, PW, OPS[op], alphabet, len(alphabet), int(varlen), a, len(a), b, len(b),
                           max_len, d, p0, p1, p2, ctypes.byref(out))
-        assert r >= 0 or (op == "swar" and r == -2), r
-        return out.value if op == "hash" else r
+        assert r >= 0 or (op in ("swar", "fixed") and r == -2), r
+        return out.value if op in ("hash", "hash32") else r
     return call
 
 
@@ -141,3 +142,36 @@ def test_table_free_dna_packing(probe, PW, L):
             a[pos] = byte
             r = probe(3, PW, "swar", b"ACGTN", False, bytes(a), bytes(a), L)
             assert r == (1 if byte in b"ACGTN" else -2), (byte, pos, r)
+
+
+@pytest.mark.parametrize("PW,L", [(1, 12), (1, 24), (2, 24), (2, 36), (2, 48)])
+def test_straight_line_dna_packing(probe, PW, L):
+    """pack_key_acgtn_fixed (the lean partition kernel's packer) == the table packer on keys of exactly
+    12/24/36/48 symbols, and rejects every foreign byte at every position class."""
+    rng = np.random.default_rng(7 * PW + L)
+    for _ in range(1500):
+        a = bytes(rng.choice(list(b"ACGTN"), size=L).astype(np.uint8))
+        assert probe(3, PW, "fixed", b"ACGTN", False, a, a, L) == 1, a
+    for byte in range(256):
+        for pos in (0, 1, 2, 3, 4, 7, L - 5, L - 1):
+            a = bytearray(b"ACGT" * 12)[:L]
+            a[pos] = byte
+            r = probe(3, PW, "fixed", b"ACGTN", False, bytes(a), bytes(a), L)
+            assert r == (1 if byte in b"ACGTN" else -2), (byte, pos, r)
+
+
+def test_partition_hash_depends_on_the_leading_block_only(probe):
+    """Records are partitioned by block0_hash: keys that share their first pigeonhole block must share
+    a tile (the fused pass 0 relies on it), keys that differ there should not collide."""
+    rng = np.random.default_rng(11)
+    seen = {}
+    for _ in range(2000):
+        a = bytes(rng.choice(list(b"ACGTN"), size=36).astype(np.uint8))
+        b = a[:18] + bytes(rng.choice(list(b"ACGTN"), size=18).astype(np.uint8))
+        assert probe(3, 2, "block0eq", b"ACGTN", False, a, b, 36, p2=18) == 1
+        c = bytearray(a)
+        pos = int(rng.integers(0, 18))
+        c[pos] = ord("A") if c[pos] != ord("A") else ord("C")
+        assert probe(3, 2, "block0eq", b"ACGTN", False, a, bytes(c), 36, p2=18) == 0
+        h = probe(3, 2, "hash32", b"ACGTN", False, a, a, 36)
+        assert seen.setdefault(h, a) == a      # 2000 keys, 32 bits: a collision would be a bug, not bad luck
