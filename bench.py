@@ -420,7 +420,7 @@ def run_ours(args, rank, world, local_rank):
                          "streaming_passes": bool(st.plan_flags & 2)}}
 
     # ---- CPU baseline on a bounded sample of the same workload ----
-    sample = min(n, env_int("FQD_CPU_SAMPLE", 2_000_000))
+    sample = min(n, env_int("FQD_CPU_SAMPLE", 4_000_000))
     uniq_s, secs, split, kind = time_reference(
         cfg, host_keys.array[:sample], None if host_quals is None else host_quals.array[:sample])
     cpu = {"value": uniq_s / secs, "unit": UNIT, "cores": 1, "kind": kind,
