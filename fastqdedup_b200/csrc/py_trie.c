@@ -145,7 +145,7 @@ Trie_raw_stats(TrieObject *self, PyObject *Py_UNUSED(ignored))
 {
     size_t row_len = 0;
     size_t rows = fqd_trie_raw_stats(self->trie, NULL, 0, &row_len);
-    uint64_t *buf = PyMem_Calloc(rows * row_len ? rows * row_len : 1, sizeof(uint64_t));
+    uint64_t *buf = PyMem_Calloc((rows && row_len) ? rows * row_len : 1, sizeof(uint64_t));
     if (buf == NULL)
         return PyErr_NoMemory();
     fqd_trie_raw_stats(self->trie, buf, rows * row_len, &row_len);
