@@ -4,6 +4,7 @@
 
     python bench.py --gpus N --steps K --warmup W            # our arm (CUDA path)
     python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path
+    python bench.py --config cfg3 [--distance D] [--method M]  # the other BASELINE configs (1 GPU)
 
 One "step" is one complete pass of the hot path (quality filter off for this config, pack,
 exact dedupe, neighbour search, components, dissection) over the whole synthetic batch.
@@ -26,8 +27,14 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-METRIC = "unique UMIs clustered/sec (d=1, directional)"
 UNIT = "unique keys/s"
+
+
+def metric_name(cfg):
+    """BASELINE.json's metric, qualified by what the configuration actually runs."""
+    dist = f"Levenshtein d={cfg.max_distance}" if cfg.use_edit_distance else f"d={cfg.max_distance}"
+    filt = ", quality filter on" if cfg.max_average_error_rate < 1.0 else ""
+    return f"unique UMIs clustered/sec ({dist}, {cfg.method}{filt})"
 
 
 def env_int(name, default):
@@ -47,10 +54,15 @@ def log(*a):
 
 def make_config(args):
     from fastqdedup_b200 import synth
+    from dataclasses import replace
     cfg = synth.CONFIGS[args.config]
     n = env_int("FQD_BENCH_READS", 0) or args.reads or cfg.n_reads
     if n != cfg.n_reads:
         cfg = cfg.scaled(n)
+    if args.distance is not None:
+        cfg = replace(cfg, max_distance=args.distance)
+    if args.method:
+        cfg = replace(cfg, method=args.method)
     return cfg
 
 
@@ -164,6 +176,15 @@ def survey_key_bytes(L):
     return 4 * ((L + 15) // 16) + 4 * ((L + 31) // 32)
 
 
+def survey_passes(cfg, hamming_passes):
+    """P of SURVEY.md section 8(d): Hamming d+1; Levenshtein (d+1)(2s+1) shifted-block passes with
+    s = floor(d/2) for keys of one length (the synthetic configs) -- the library runs the shifts of one
+    block as variants inside one pass, so its pass count is d+1 either way."""
+    if not cfg.use_edit_distance:
+        return hamming_passes
+    return hamming_passes * (2 * (cfg.max_distance // 2) + 1)
+
+
 def algorithmic_bytes(cfg, n, n_ok, u, passes, filter_on):
     W = survey_key_bytes(cfg.key_length)
     R = W + 4
@@ -230,12 +251,28 @@ def time_reference(cfg, keys, quals):
     return uniques, t3 - t0, split, kind
 
 
+# reference speed per read on one host core (add + pop_cluster + dissection),
+# used only to size the bounded sample of the reference arm
+REF_US_PER_READ = {"cfg1": 1.0, "cfg2": 3.5, "cfg3": 11.0, "cfg4": 3.0, "cfg5": 3.5}
+
+
+def reference_sample_reads(cfg, args):
+    """Reads per step of the reference arm: a prefix of the same synthetic workload sized so that the
+    whole --steps/--warmup run ends within a few minutes (FQD_REF_SAMPLE overrides)."""
+    forced = env_int("FQD_REF_SAMPLE", 0)
+    if forced:
+        return min(cfg.n_reads, forced)
+    us = REF_US_PER_READ.get(cfg.name, 3.5) * (6.0 if cfg.use_edit_distance and cfg.max_distance >= 2 else 1.0)
+    budget_s = 240.0 / max(1, args.steps + args.warmup)
+    return int(min(cfg.n_reads, 4_000_000, max(250_000, budget_s / (us * 1e-6))))
+
+
 def run_reference_arm(args, rank, world):
     if rank != 0:
         return
     cfg = make_config(args)
-    sample = min(cfg.n_reads, env_int("FQD_REF_SAMPLE", 1_000_000))
-    from fastqdedup_b200 import synth
+    sample = reference_sample_reads(cfg, args)
+    from fastqdedup_b200 import synth      # pure Python: the package resolves its native names lazily
     src = synth.SynthSource(cfg)
     keys, _, quals = src.reads(0, sample)
     times, uniques = [], 0
@@ -246,12 +283,17 @@ def run_reference_arm(args, rank, world):
         log(f"[reference] step {it}: {uniques} uniques in {dt:.2f}s {split}")
     ms = 1e3 * sum(times) / len(times)
     value = uniques / (ms / 1e3)
+    config = workload_config(cfg, args.gpus)
+    config["reference_sample"] = {
+        "reads_per_step": sample, "unique_keys_per_step": uniques,
+        "note": "the reference's per-unique cost grows with the trie, so a prefix sample flatters it; "
+                "the value is an extrapolation to the full workload, not a full-size run"}
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
+        "impl": "reference", "metric": metric_name(cfg), "value": value, "unit": UNIT,
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u32",
         "data": "synthetic",
-        "config": workload_config(cfg, args.gpus),
+        "config": config,
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": kind,
                          "sample": f"first {sample} of {cfg.n_reads} reads per step "
                                    f"({uniques} unique keys); add+pop_cluster+dissection, "
@@ -261,14 +303,28 @@ def run_reference_arm(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+WORKLOADS = {
+    "cfg1": "BASELINE config 1: single-end, 12-nt prepended UMI, --check-lengths 12 -E",
+    "cfg2": "BASELINE config 2: paired-end + UMI file, --check-lengths 16,8,12 -E (36-nt key)",
+    "cfg3": "BASELINE config 3: single-end, 16-nt UMI + 32-nt prefix (48-nt key), quality filter on (-e 0.001)",
+    "cfg4": "BASELINE config 4: single-end, 24-nt key, --edit -E",
+    "cfg5": "BASELINE config 5: 12-nt UMI + 24-nt prefix (36-nt key), -E",
+}
+
+
 def workload_config(cfg, gpus):
-    return {"workload": f"BASELINE config 5: {cfg.n_reads} reads, {cfg.key_length}-nt key "
-                        f"(12-nt UMI + 24-nt prefix), Hamming d={cfg.max_distance}, {cfg.method}, "
-                        f"quality filter off (-E)",
+    dist = ("Levenshtein" if cfg.use_edit_distance else "Hamming") + f" d={cfg.max_distance}"
+    filt = "off (-E)" if cfg.max_average_error_rate >= 1.0 else f"on (-e {cfg.max_average_error_rate})"
+    return {"workload": f"{WORKLOADS.get(cfg.name, cfg.name)}: {cfg.n_reads} reads, {cfg.key_length}-nt key, "
+                        f"{dist}, {cfg.method}, quality filter {filt}",
+            "name": cfg.name,
             "reads": cfg.n_reads, "key_length": cfg.key_length, "molecules": cfg.n_molecules,
-            "max_distance": cfg.max_distance, "method": cfg.method,
+            "max_distance": cfg.max_distance, "edit_distance": bool(cfg.use_edit_distance),
+            "method": cfg.method, "quality_filter": cfg.max_average_error_rate < 1.0,
             "sharding": "1 GPU" if gpus == 1 else f"{gpus} GPUs, reads split contiguously",
-            "l2": "inputs (reads x key bytes) exceed the 126 MB L2; no flush needed"}
+            "l2": "inputs (reads x key bytes) exceed the 126 MB L2; no flush needed"
+                  if cfg.n_reads * cfg.key_length > (126 << 20) else
+                  "inputs fit the 126 MB L2: a 256 MB buffer is overwritten between timed steps"}
 
 
 # ---------------------------------------------------------------------------------------
@@ -310,7 +366,13 @@ def run_ours(args, rank, world, local_rank):
     bitmap_words = (n + 31) // 32
     d_bitmap = ctx.device_alloc(bitmap_words * 4)
 
+    # inputs smaller than the L2 (config 1): overwrite a 256 MB buffer between timed steps
+    flush_bytes = (256 << 20) if n * L * (2 if host_quals is not None else 1) <= (126 << 20) else 0
+    d_flush = ctx.device_alloc(flush_bytes) if flush_bytes else None
+
     def device_step():
+        if d_flush:
+            ctx.memset(d_flush, 0x5A, flush_bytes)
         return cluster_device(ctx, n, d_keys, L, quals_ptr=d_quals, qual_length=L,
                               max_distance=cfg.max_distance, use_edit_distance=cfg.use_edit_distance,
                               method=cfg.method, max_average_error_rate=cfg.max_average_error_rate,
@@ -367,32 +429,47 @@ def run_ours(args, rank, world, local_rank):
     # ---- roofline of the dominant kernel ----
     # Every term of SURVEY.md section 8(d)'s B_total is charged to the kernel (group) that does that
     # work; times are CUDA-event averages over the timed steps, taken inside the library on its stream.
-    total_b, ingest_b = algorithmic_bytes(cfg, n, st.number_of_sequences, U, st.n_passes, filter_on)
+    P = survey_passes(cfg, st.n_passes)
+    total_b, ingest_b = algorithmic_bytes(cfg, n, st.number_of_sequences, U, P, filter_on)
     peak, peak_src = measured_peak()
     W = survey_key_bytes(L)
     R = W + 4
     mean = lambda f: float(np.mean([getattr(s_, f) for s_ in stats]))
     streaming = bool(st.plan_flags & 1)
+    tiled_passes = bool(st.plan_flags & 2)
     fused = bool(st.plan_flags & 4)
     emitted = bool(st.plan_flags & 8)      # the dedupe tiles also wrote the bucket-ordered entries of pass 1
+    K_, PW_ = st.key_bits, st.key_words // max(st.key_bits, 1)
+    inst = f"<{K_},{PW_}>"
+    lean = streaming and not filter_on and K_ == 3 and L % 4 == 0
     passes_left = st.n_passes - (1 if fused else 0)
+    per_pass = P // max(st.n_passes, 1)    # SURVEY passes per library pass (Levenshtein shifts)
     read_b = (n * L if filter_on else 0) + st.number_of_sequences * W
+    if cfg.use_edit_distance:
+        pass_kernels = "sig_count + scan + scatter + compare_kernel (Myers bit-vector verify)"
+    elif tiled_passes:
+        pass_kernels = ("" if emitted else "bucket_partition_kernel + ") + f"bucket_tile_kernel{inst} + apply_edges_kernel"
+    else:
+        pass_kernels = f"sig_count + scan + scatter_fat + compare_fat_kernel{inst}"
+    select_kernels = {"directional": "root_best_kernel + select_kernel", "highest_count": "root_best_kernel + select_kernel",
+                      "adjacency": "adj_edge/adj_node rounds + select_kernel"}[cfg.method] + " (dissection + keep bitmap)"
     if streaming:
         groups = [
-            (("partition_dna_kernel<2,9>" if not filter_on else "ingest_kernel<3,2> partition mode") + " (pack + hash + partition into tiles)",
+            ((f"partition_dna_kernel<{PW_},{L // 4}>" if lean else f"ingest_kernel{inst} partition mode") +
+             " (" + ("quality filter + " if filter_on else "") + "pack + hash + partition into tiles)",
              mean("ms_partition_kernel"), read_b),
-            ("dedupe_tile_kernel<3,2>" + (" fused with pass 0" if fused else "") + (" + pass-1 tiles" if emitted else "") +
+            (f"dedupe_tile_kernel{inst}" + (" fused with pass 0" if fused else "") + (" + pass-1 tiles" if emitted else "") +
              " (exact dedupe in shared-memory tiles)",
-             mean("ms_dedupe_kernel"), U * (R + 4) + (3 * U * R if fused else 0) + (U * R if emitted else 0)),
-            (f"{passes_left} pass(es): " + ("" if emitted else "bucket_partition_kernel + ") + "bucket_tile_kernel + apply_edges_kernel",
-             mean("ms_neighbour"), 3 * passes_left * U * R - (U * R if emitted else 0)),
-            ("root_best_kernel + select_kernel (dissection + keep bitmap)", mean("ms_select"), 9 * U),
+             mean("ms_dedupe_kernel"), U * (R + 4) + (3 * U * R * per_pass if fused else 0) + (U * R if emitted else 0)),
+            (f"{passes_left} pass(es): " + pass_kernels,
+             mean("ms_neighbour"), 3 * passes_left * per_pass * U * R - (U * R if emitted else 0)),
+            (select_kernels, mean("ms_select"), 9 * U),
         ]
     else:
         groups = [
-            ("ingest_kernel<3,2> (filter + pack + exact dedupe, HBM table)", mean("ms_ingest"), ingest_b),
-            (f"{st.n_passes} pass(es): sig_count + scan + scatter_fat + compare_fat", mean("ms_neighbour"), 3 * st.n_passes * U * R),
-            ("root_best_kernel + select_kernel (dissection + keep bitmap)", mean("ms_select"), 9 * U),
+            (f"ingest_kernel{inst} (filter + pack + exact dedupe, HBM table)", mean("ms_ingest"), ingest_b),
+            (f"{st.n_passes} pass(es): " + pass_kernels, mean("ms_neighbour"), 3 * P * U * R),
+            (select_kernels, mean("ms_select"), 9 * U),
         ]
     kernels = [{"kernel": k, "ms": ms, "algorithmic_bytes": int(b), "achieved_gbs": b / (ms / 1e3) / 1e9 if ms > 0 else None,
                 "frac": b / (ms / 1e3) / 1e9 / peak if ms > 0 else None} for k, ms, b in groups]
@@ -401,11 +478,17 @@ def run_ours(args, rank, world, local_rank):
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
         try:
-            for name, val in json.load(open(tpath)).items():
-                if not name.startswith("_") and dom["kernel"].startswith(name):
+            for name, val in json.load(open(tpath)).get(cfg.name, {}).items():
+                if dom["kernel"].startswith(name):
                     traffic = val
         except Exception:
             traffic = None
+    # compare phase against the integer-issue roofline: per candidate pair
+    # 4*ceil(L/16) + 3*ceil(L/32) + 2 integer operations (Hamming), ~17 L (Myers); INT peak measured by
+    # fqd_int_peak (dependent-free LOP3 + POPC streams) on this GPU
+    ops_pair = 17 * L if cfg.use_edit_distance else 4 * ((L + 15) // 16) + 3 * ((L + 31) // 32) + 2
+    int_peak = ctx.int_peak()
+    t_int_ms = 1e3 * st.candidate_pairs * ops_pair / (int_peak["mixed_ops_per_s"] or 1.0)
     roofline = {"bound": "hbm", "kernel": dom["kernel"],
                 "achieved": dom["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": dom["frac"],
                 "traffic": traffic, "peak_source": peak_src,
@@ -413,11 +496,21 @@ def run_ours(args, rank, world, local_rank):
                 "kernel_ms": dom["ms"],
                 "whole_path": {"algorithmic_bytes": total_b,
                                "bytes_per_unique": total_b / max(U, 1),
+                               "survey_passes": P,
                                "achieved_gbs": total_b / (ms_per_step / 1e3) / 1e9,
                                "frac": total_b / (ms_per_step / 1e3) / 1e9 / peak},
                 "kernels": kernels,
+                "integer": {"candidate_pairs": int(st.candidate_pairs), "int_ops_per_pair": ops_pair,
+                            "int_peak_ops_per_s": int_peak["mixed_ops_per_s"],
+                            "lop3_peak_ops_per_s": int_peak["lop3_ops_per_s"],
+                            "popc_peak_ops_per_s": int_peak["popc_ops_per_s"],
+                            "t_int_ms": t_int_ms,
+                            "compare_phase_ms": mean("ms_compare") if not fused else None,
+                            "note": "t_int = candidate pairs x ops / measured INT peak: the compare arithmetic itself "
+                                    "is far from the integer-issue limit; the passes are bound by tile staging and "
+                                    "shared-memory probe latency (DESIGN.md section 4)"},
                 "plan": {"streaming_dedupe": streaming, "pass0_fused": fused, "pass1_tiles_from_dedupe": emitted,
-                         "streaming_passes": bool(st.plan_flags & 2)}}
+                         "streaming_passes": tiled_passes}}
 
     # ---- CPU baseline on a bounded sample of the same workload ----
     sample = min(n, env_int("FQD_CPU_SAMPLE", 4_000_000))
@@ -429,7 +522,7 @@ def run_ours(args, rank, world, local_rank):
                      f"host has {os.cpu_count()} logical cores"}
 
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps,
+        "metric": metric_name(cfg), "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
         "config": workload_config(cfg, 1),
@@ -537,7 +630,7 @@ def run_ours_sharded(args, cfg, rank, world, local_rank, dist):
                                        cfg.max_average_error_rate < 1.0)
         peak, peak_src = measured_peak()
         line = {
-            "metric": METRIC, "value": U / (ms_per_step / 1e3), "unit": UNIT, "n_gpus": world,
+            "metric": metric_name(cfg), "value": U / (ms_per_step / 1e3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u32",
             "data": "synthetic", "config": workload_config(cfg, world),
@@ -568,6 +661,9 @@ def main():
     ap.add_argument("--impl", choices=("ours", "reference"), default="ours")
     ap.add_argument("--config", default="cfg5")
     ap.add_argument("--reads", type=int, default=0, help="override the read count (debugging)")
+    ap.add_argument("--distance", type=int, default=None, help="override the config's max distance (cfg4: 1 or 2)")
+    ap.add_argument("--method", default="", choices=("", "directional", "adjacency", "highest_count"),
+                    help="override the config's dissection method (cfg2: adjacency or highest_count)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     if env_int("FQD_WATCHDOG", 0):

@@ -78,11 +78,11 @@ class ClusterStats(Structure):
 EXPORTS = [
     "fqd_last_error", "fqd_device_count", "fqd_context_create", "fqd_context_destroy",
     "fqd_default_context", "fqd_device_alloc", "fqd_device_free", "fqd_device_upload",
-    "fqd_device_download", "fqd_context_synchronize", "fqd_host_alloc", "fqd_host_free",
+    "fqd_device_download", "fqd_device_memset", "fqd_context_synchronize", "fqd_host_alloc", "fqd_host_free",
     "fqd_cluster", "fqd_cluster_fetch", "fqd_cluster_fetch_selected",
     "fqd_nccl_unique_id", "fqd_comm_create", "fqd_comm_destroy", "fqd_cluster_sharded",
     "fqd_cluster_sharded_local",
-    "fqd_average_error_rate", "fqd_within_distance",
+    "fqd_average_error_rate", "fqd_within_distance", "fqd_int_peak",
     "fqd_trie_new", "fqd_trie_free", "fqd_trie_add_sequence", "fqd_trie_contains_sequence",
     "fqd_trie_pop_cluster", "fqd_trie_cluster_item", "fqd_trie_number_of_sequences",
     "fqd_trie_alphabet", "fqd_trie_memory_size", "fqd_trie_raw_stats",
@@ -110,7 +110,9 @@ def load():
     lib.fqd_device_free.argtypes = [c_void_p, c_void_p]
     lib.fqd_device_upload.argtypes = [c_void_p, c_void_p, c_void_p, c_size_t]
     lib.fqd_device_download.argtypes = [c_void_p, c_void_p, c_void_p, c_size_t]
+    lib.fqd_device_memset.argtypes = [c_void_p, c_void_p, c_int, c_size_t]
     lib.fqd_context_synchronize.argtypes = [c_void_p]
+    lib.fqd_int_peak.argtypes = [c_void_p, POINTER(c_double), POINTER(c_double), POINTER(c_double)]
     lib.fqd_host_alloc.argtypes = [c_size_t, POINTER(c_void_p)]
     lib.fqd_host_free.argtypes = [c_void_p]
     lib.fqd_cluster.argtypes = [c_void_p, POINTER(ClusterJob), POINTER(ClusterStats), c_void_p]
@@ -194,8 +196,17 @@ class Context:
         check(self.lib.fqd_device_download(self.handle, out.ctypes.data, c_void_p(ptr), nbytes))
         return out
 
+    def memset(self, ptr, value, nbytes):
+        check(self.lib.fqd_device_memset(self.handle, c_void_p(ptr), int(value), nbytes))
+
     def synchronize(self):
         check(self.lib.fqd_context_synchronize(self.handle))
+
+    def int_peak(self):
+        """Measured integer-issue peak of this GPU (thread-level operations per second)."""
+        a, b, c = c_double(), c_double(), c_double()
+        check(self.lib.fqd_int_peak(self.handle, byref(a), byref(b), byref(c)))
+        return {"lop3_ops_per_s": a.value, "popc_ops_per_s": b.value, "mixed_ops_per_s": c.value}
 
     # ---- the batched job ----
     def cluster(self, job, keep_bitmap_ptr=None):

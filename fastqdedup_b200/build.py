@@ -24,9 +24,13 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xptxas", "-v",
 ]
-CU_SOURCES = ["api.cu", "pipeline.cu", "trie_shim.cu", "nccl_exchange.cu"]
-HEADERS = ["key.cuh", "pipeline.cuh", "partitioned.cuh", "common.h", "exchange.h", "phred_lut.h",
-           os.path.join("..", "..", "include", "fqd_b200.h")]
+N_GROUPS = 7   # instance groups of csrc/instances.h: pipeline_inst.cu is compiled once per group, in parallel
+# (source, object stem, extra flags); the heavy groups first so the pool finishes early
+CU_SOURCES = [("pipeline_inst.cu", f"pipeline_g{g}", [f"-DFQD_GROUP={g}"]) for g in (2, 6, 4, 0, 1, 3, 5)] + \
+             [(s, os.path.splitext(s)[0], []) for s in ("api.cu", "pipeline.cu", "trie_shim.cu", "nccl_exchange.cu",
+                                                        "microbench.cu")]
+HEADERS = ["key.cuh", "pipeline.cuh", "partitioned.cuh", "pipeline_impl.cuh", "instances.h", "common.h", "exchange.h",
+           "phred_lut.h", os.path.join("..", "..", "include", "fqd_b200.h")]
 PY_MODULES = {"_trie": "py_trie.c", "_distance": "py_distance.c", "_fastq": "py_fastq.c"}
 
 
@@ -37,12 +41,19 @@ def _stale(target, deps):
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
 
-def _nvcc(src):
-    obj = os.path.join(OBJ, os.path.splitext(src)[0] + ".o")
+def _nvcc(item):
+    src, stem, extra = item
+    obj = os.path.join(OBJ, stem + ".o")
     deps = [os.path.join(CSRC, src)] + [os.path.join(CSRC, h) for h in HEADERS]
     if not _stale(obj, deps):
         return obj, ""
-    cmd = ["nvcc"] + NVCC_FLAGS + ["-c", os.path.join(CSRC, src), "-o", obj]
+    # development shortcut, never used by build_all() callers that ship: FQD_BUILD_GROUPS=0,3 recompiles only
+    # those instance groups and links the existing objects of the others (valid while the cross-TU structs
+    # of common.h are unchanged)
+    only = os.environ.get("FQD_BUILD_GROUPS")
+    if only and stem.startswith("pipeline_g") and os.path.exists(obj) and stem[len("pipeline_g"):] not in only.split(","):
+        return obj, ""
+    cmd = ["nvcc"] + NVCC_FLAGS + extra + ["-c", os.path.join(CSRC, src), "-o", obj]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode:
         raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")
@@ -53,12 +64,15 @@ def _nvcc(src):
 
 def build_library(verbose=False):
     os.makedirs(OBJ, exist_ok=True)
-    sources = [s for s in CU_SOURCES if os.path.exists(os.path.join(CSRC, s))]
-    with concurrent.futures.ThreadPoolExecutor(max_workers=len(sources)) as ex:
+    sources = [s for s in CU_SOURCES if os.path.exists(os.path.join(CSRC, s[0]))]
+    with concurrent.futures.ThreadPoolExecutor(max_workers=min(len(sources), os.cpu_count() or 4)) as ex:
         objs = [o for o, _ in ex.map(_nvcc, sources)]
     if _stale(LIB, objs):
-        cmd = ["nvcc", "-shared", "-o", LIB] + objs
+        # static cudart (nvcc's default), deliberately: the library must not depend on WHICH libcudart.so.12
+        # the host process has mapped (a torch process brings the 12.8 runtime, this toolkit is 12.9)
+        cmd = ["nvcc", "-shared", "-o", LIB + ".tmp"] + objs
         subprocess.run(cmd, check=True)
+        os.replace(LIB + ".tmp", LIB)   # never a half-written library in the tree
     if verbose:
         print("built", LIB)
     return LIB
@@ -75,9 +89,10 @@ def build_python_modules(verbose=False):
         out = os.path.join(HERE, mod + suffix)
         if _stale(out, [srcp, os.path.join(CSRC, "py_common.h"), LIB]):
             cmd = ["gcc", "-O2", "-fPIC", "-shared", "-Wall", f"-I{include}",
-                   f"-I{os.path.join(HERE, '..', 'include')}", srcp, "-o", out,
+                   f"-I{os.path.join(HERE, '..', 'include')}", srcp, "-o", out + ".tmp",
                    f"-L{HERE}", "-lfqd_b200", "-Wl,-rpath,$ORIGIN"]
             subprocess.run(cmd, check=True)
+            os.replace(out + ".tmp", out)
         outs.append(out)
         if verbose:
             print("built", out)

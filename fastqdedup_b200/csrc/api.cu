@@ -259,6 +259,13 @@ int fqd_device_download(fqd_context *ctx, void *host, const void *dptr, size_t b
     return FQD_OK;
 }
 
+int fqd_device_memset(fqd_context *ctx, void *dptr, int value, size_t bytes)
+{
+    FQD_TRY(check_device(ctx));
+    FQD_CUDA(cudaMemsetAsync(dptr, value, bytes, ctx->stream));
+    return FQD_OK;
+}
+
 int fqd_context_synchronize(fqd_context *ctx)
 {
     FQD_TRY(check_device(ctx));

@@ -132,6 +132,7 @@ struct DeviceJob {
 };
 
 constexpr int RC_RETRY_ALPHABET = -100;   // internal: unknown bytes were seen, grow the alphabet
+constexpr int RC_NOT_IN_GROUP = -101;     // internal: the (K, PW) instantiation lives in another instance group
 
 // pipeline.cu: runs the stages for one (K, PW) instantiation
 int run_pipeline(fqd_context *ctx, const DeviceJob &job, const Codec &codec,

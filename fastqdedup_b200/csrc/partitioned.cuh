@@ -423,8 +423,9 @@ static __global__ void __launch_bounds__(TILE_THREADS) dedupe_tile_kernel(const 
     }
 }
 
-// Spill path: the records of the oversize partitions (their full regions, blockIdx.y picks one)
-// or of the spill buffer (list == null) go through the single-table insert.
+// Spill path: the records of the oversize partitions (their full regions: TILE_R / 256 consecutive
+// blocks per partition, all on blockIdx.x -- a skewed 100 M-read job can have more oversize partitions
+// than gridDim.y allows) or of the spill buffer (list == null) go through the single-table insert.
 template <int K, int PW>
 static __global__ void __launch_bounds__(256) spill_insert_kernel(const uint32_t *__restrict__ recs, const uint32_t *__restrict__ list,
                                                                   uint32_t n, const __grid_constant__ TableRef tab,
@@ -432,8 +433,9 @@ static __global__ void __launch_bounds__(256) spill_insert_kernel(const uint32_t
 {
     constexpr int KW = K * PW, RW = slot_words(KW);
     static_assert(RW == PART_RW, "partitioned plan: 32-byte records");
-    const uint32_t i = blockIdx.x * 256u + threadIdx.x;
-    const uint32_t *src = list ? recs + (size_t)list[blockIdx.y] * TILE_R * PART_RW : recs;
+    constexpr uint32_t BPP = TILE_R / 256;   // blocks per oversize partition
+    const uint32_t i = (list ? blockIdx.x % BPP : blockIdx.x) * 256u + threadIdx.x;
+    const uint32_t *src = list ? recs + (size_t)list[blockIdx.x / BPP] * TILE_R * PART_RW : recs;
     uint32_t claimed = NO_CLAIM;
     if (i < n) {
         uint32_t e[PART_RW];

@@ -233,6 +233,7 @@ def _deduplicate_with_callable(keys, quals, max_distance, max_average_error_rate
     from ._fastq import average_error_rate
     flat, off = keys
     data = flat.tobytes()
+    qdata = quals[0].tobytes() if filter_on_quality else b""
     n = len(off) - 1
     trie = Trie(alphabet="ACGTN")
     first: Dict[str, int] = {}
@@ -241,7 +242,7 @@ def _deduplicate_with_callable(keys, quals, max_distance, max_average_error_rate
         key = data[off[t]:off[t + 1]].decode("latin-1")
         first.setdefault(key, t)
         if filter_on_quality:
-            q = quals[0].tobytes()[quals[1][t]:quals[1][t + 1]].decode("latin-1")
+            q = qdata[quals[1][t]:quals[1][t + 1]].decode("latin-1")
             if average_error_rate(q) > max_average_error_rate:
                 discarded += 1
                 continue

@@ -62,6 +62,7 @@ int fqd_device_alloc(fqd_context *ctx, size_t bytes, void **dptr);
 int fqd_device_free(fqd_context *ctx, void *dptr);
 int fqd_device_upload(fqd_context *ctx, void *dptr, const void *host, size_t bytes);
 int fqd_device_download(fqd_context *ctx, void *host, const void *dptr, size_t bytes);
+int fqd_device_memset(fqd_context *ctx, void *dptr, int value, size_t bytes);
 int fqd_context_synchronize(fqd_context *ctx);
 /* Host staging memory that H2D copies can stream from (cudaHostAlloc). */
 int fqd_host_alloc(size_t bytes, void **hptr);
@@ -129,7 +130,7 @@ typedef struct {
     uint32_t launches;             /* kernels launched by this job */
     uint32_t plan_flags;           /* FQD_PLAN_*: which launch plan the stages took */
     float ms_partition_kernel;     /* partitioned dedupe: filter + pack + partition pass */
-    float ms_dedupe_kernel;        /* partitioned dedupe: the persistent L2-resident dedupe kernel */
+    float ms_dedupe_kernel;        /* partitioned dedupe: the shared-memory tile kernel (dedupe + fused pass 0) */
 } fqd_cluster_stats;
 
 #define FQD_PLAN_DEDUPE_PARTITIONED 1u /* exact dedupe: partition by hash, tables in shared-memory tiles */
@@ -196,6 +197,14 @@ int fqd_average_error_rate(fqd_context *ctx, const uint8_t *phred, const uint64_
 int fqd_within_distance(fqd_context *ctx, const uint8_t *a, const uint64_t *a_offsets,
                         const uint8_t *b, const uint64_t *b_offsets, uint64_t n_pairs,
                         int32_t max_distance, int32_t use_edit_distance, uint8_t *out);
+
+/* Measurement aid (not on the product path): the integer-issue peak of the
+ * context's GPU in thread-level operations per second, from dependent-free instruction streams --
+ * LOP3 alone, POPC alone, and the 4 LOP3 : 1 POPC mix of the XOR+POPC Hamming compare that replaces
+ * within_hamming_distance (src/fastqdedup/distances.h:8-31).  bench.py reports the compare phase
+ * against it. */
+int fqd_int_peak(fqd_context *ctx, double *lop3_ops_per_s, double *popc_ops_per_s,
+                 double *mixed_ops_per_s);
 
 /* _trie.Trie (src/fastqdedup/_triemodule.c:596-983).  Sequences are staged on the host;
  * the neighbour search / clustering runs on the GPU when contains_sequence or
