@@ -57,11 +57,12 @@ void dev_free(fqd_context *, void *) {}
 int arena_reset(fqd_context *ctx)
 {
     fqd_arena &a = ctx->arena;
+    a.last_high = a.high > a.last_high || a.high > a.cap ? a.high : a.last_high;
     if (!a.overflow.empty() || a.high > a.cap) {
         FQD_CUDA(cudaStreamSynchronize(ctx->stream));
         for (void *q : a.overflow) cudaFree(q);
         a.overflow.clear();
-        if (a.high > a.cap) {
+        if (a.high > a.cap && !a.shared) {   // (a shared slab is only replaced by arena_reserve)
             if (a.base) cudaFree(a.base);
             a.base = nullptr;
             a.cap = 0;
@@ -73,6 +74,25 @@ int arena_reset(fqd_context *ctx)
     }
     a.off = 0;
     a.high = 0;
+    return FQD_OK;
+}
+
+int arena_reserve(fqd_context *ctx, size_t bytes)
+{
+    fqd_arena &a = ctx->arena;
+    if (a.cap >= bytes) return FQD_OK;
+    FQD_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (void *q : a.overflow) cudaFree(q);
+    a.overflow.clear();
+    if (a.base) cudaFree(a.base);
+    a.base = nullptr;
+    a.cap = 0;
+    a.off = a.high = 0;
+    a.generation++;
+    void *q = nullptr;
+    FQD_CUDA(cudaMalloc(&q, bytes));
+    a.base = (char *)q;
+    a.cap = bytes;
     return FQD_OK;
 }
 
@@ -487,6 +507,99 @@ int fqd_cluster(fqd_context *ctx, const fqd_cluster_job *job, fqd_cluster_stats 
     return finish_job(ctx, r, stats);
 }
 
+// every rank learns the `n` 64-bit values of every rank (NCCL ranks: a host-synchronous all-gather; ranks of
+// this process: a copy)
+static int gather_u64(fqd_context **ctxs, int n_local, Exchange *ex, int world, int n,
+                      const std::vector<std::vector<uint64_t>> &mine, std::vector<uint64_t> &all)
+{
+    all.assign((size_t)world * n, 0);
+    if (!ex) {
+        for (int g = 0; g < n_local; g++)
+            for (int i = 0; i < n; i++) all[(size_t)g * n + i] = mine[g][i];
+        return FQD_OK;
+    }
+    fqd_context *ctx = ctxs[0];
+    uint64_t *d_buf = nullptr;   // not from the arena: the slab may be replaced between two of these calls
+    FQD_CUDA(cudaMalloc(&d_buf, (size_t)(world + 1) * n * 8));
+    int rc = FQD_OK;
+    if (cudaMemcpyAsync(d_buf, mine[0].data(), (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) rc = FQD_ERR_CUDA;
+    if (rc == FQD_OK) rc = ex->allgather(d_buf, d_buf + n, (size_t)n * 8, ctx->stream);
+    if (rc == FQD_OK && cudaMemcpyAsync(all.data(), d_buf + n, (size_t)world * n * 8, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess)
+        rc = FQD_ERR_CUDA;
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess && rc == FQD_OK) rc = FQD_ERR_CUDA;
+    cudaFree(d_buf);
+    if (rc == FQD_ERR_CUDA) { cudaGetLastError(); set_error("CUDA failure in the rank agreement exchange"); }
+    return rc;
+}
+
+// Views of the peers' arena slabs.  Ranks of this process: the slabs themselves (peer access enabled between
+// different GPUs).  NCCL ranks: CUDA IPC handles, exchanged and (re)opened only when a slab changed.
+static int map_peer_arenas(fqd_context **ctxs, int n_local, Exchange *ex, ShardWorld &W)
+{
+    W.peers_mapped = false;
+    if (!ex) {
+        for (int g = 0; g < n_local; g++) {
+            W.peer_base[g] = ctxs[g]->arena.base;
+            for (int r = 0; r < n_local; r++) {
+                if (ctxs[r]->device == ctxs[g]->device) continue;
+                int can = 0;
+                FQD_CUDA(cudaDeviceCanAccessPeer(&can, ctxs[r]->device, ctxs[g]->device));
+                if (!can) return FQD_OK;   // no peer path: the replicated-set plan runs instead
+                FQD_CUDA(cudaSetDevice(ctxs[r]->device));
+                const cudaError_t e = cudaDeviceEnablePeerAccess(ctxs[g]->device, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return cuda_fail(e, "cudaDeviceEnablePeerAccess", __FILE__, __LINE__);
+                cudaGetLastError();
+            }
+        }
+        W.peers_mapped = true;
+        return FQD_OK;
+    }
+    fqd_context *ctx = ctxs[0];
+    std::vector<std::vector<uint64_t>> mine(1, std::vector<uint64_t>(9, 0));
+    cudaIpcMemHandle_t h;
+    static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    bool ok = ctx->arena.base != nullptr && cudaIpcGetMemHandle(&h, ctx->arena.base) == cudaSuccess;
+    if (!ok) cudaGetLastError();
+    if (ok) memcpy(mine[0].data(), &h, 64);
+    mine[0][8] = ok ? 1 : 0;
+    std::vector<uint64_t> all;
+    FQD_TRY(gather_u64(ctxs, n_local, ex, W.world, 9, mine, all));
+    for (int g = 0; g < W.world; g++) ok = ok && all[(size_t)g * 9 + 8] == 1;
+    if (!ok) return FQD_OK;            // some rank cannot export its slab: replicated-set plan
+    ctx->arena.shared = true;
+    for (int g = 0; g < W.world; g++) {
+        if (g == ex->rank) { W.peer_base[g] = ctx->arena.base; continue; }
+        const unsigned char *hb = reinterpret_cast<const unsigned char *>(&all[(size_t)g * 9]);
+        if (ex->peer_open[g] && memcmp(ex->peer_handle[g], hb, 64) != 0) {
+            cudaIpcCloseMemHandle(ex->peer_map[g]);
+            ex->peer_open[g] = false;
+        }
+        if (!ex->peer_open[g]) {
+            cudaIpcMemHandle_t ph;
+            memcpy(&ph, hb, 64);
+            void *p = nullptr;
+            const cudaError_t e = cudaIpcOpenMemHandle(&p, ph, cudaIpcMemLazyEnablePeerAccess);
+            if (e != cudaSuccess) {
+                cudaGetLastError();
+                if (getenv("FQD_TRACE")) fprintf(stderr, "[fqd trace] cudaIpcOpenMemHandle(rank %d): %s -> replicated-set plan\n", g, cudaGetErrorString(e));
+                ok = false;
+                continue;
+            }
+            ex->peer_map[g] = p;
+            memcpy(ex->peer_handle[g], hb, 64);
+            ex->peer_open[g] = true;
+        }
+        W.peer_base[g] = static_cast<char *>(ex->peer_map[g]);
+    }
+    // all ranks must agree on whether the views exist
+    mine[0].assign(9, 0);
+    mine[0][0] = ok ? 1 : 0;
+    FQD_TRY(gather_u64(ctxs, n_local, ex, W.world, 9, mine, all));
+    for (int g = 0; g < W.world; g++) ok = ok && all[(size_t)g * 9] == 1;
+    W.peers_mapped = ok;
+    return FQD_OK;
+}
+
 // Shared by the two sharded entry points: `n_local` shards of a `world`-rank job.
 static int cluster_sharded_common(fqd_context **ctxs, int n_local, Exchange *ex, int world,
                                   const fqd_cluster_job *jobs, const uint64_t *index_bases,
@@ -495,33 +608,93 @@ static int cluster_sharded_common(fqd_context **ctxs, int n_local, Exchange *ex,
     std::vector<Resolved> R(n_local);
     std::vector<uint8_t> alphabet;
     FQD_TRY(parse_alphabet(&jobs[0], alphabet));
+    ShardWorld W;
+    W.world = world;
     uint32_t lmin = 0xFFFFFFFFu, lmax = 0;
-    for (int i = 0; i < n_local; i++) {
-        FQD_TRY(check_device(ctxs[i]));
-        memset(&stats[i], 0, sizeof stats[i]);
-        FQD_TRY(validate_job(&jobs[i]));
-        if (index_bases[i] + jobs[i].n_records >= 0xFFFFFFF0ull) { set_error("global record index exceeds 32 bits"); return FQD_ERR_UNSUPPORTED; }
-        ctxs[i]->res = fqd_result{};
-        FQD_TRY(arena_reset(ctxs[i]));
-        FQD_TRY(resolve_job(ctxs[i], &jobs[i], keep_bitmaps ? keep_bitmaps[i] : nullptr, R[i]));
-        if (jobs[i].n_records) { lmin = std::min(lmin, R[i].len_min); lmax = std::max(lmax, R[i].len_max); }
+    const bool want_tiles = world <= MAX_RANKS && !jobs[0].use_edit_distance && !getenv("FQD_SHARD_REPLICATED");
+    for (int i = 0; i < n_local; i++) memset(&stats[i], 0, sizeof stats[i]);
+    for (int attempt = 0;; attempt++) {
+        lmin = 0xFFFFFFFFu; lmax = 0;
+        int rc_local = FQD_OK;
+        for (int i = 0; i < n_local && rc_local == FQD_OK; i++) {
+            rc_local = check_device(ctxs[i]);
+            if (rc_local == FQD_OK) rc_local = validate_job(&jobs[i]);
+            if (rc_local == FQD_OK && index_bases[i] + jobs[i].n_records >= 0xFFFFFFF0ull) {
+                set_error("global record index exceeds 32 bits");
+                rc_local = FQD_ERR_UNSUPPORTED;
+            }
+            if (rc_local != FQD_OK) break;
+            ctxs[i]->res = fqd_result{};
+            if (R[i].h0) { cudaEventDestroy(R[i].h0); cudaEventDestroy(R[i].h1); }
+            R[i] = Resolved{};
+            rc_local = arena_reset(ctxs[i]);
+            if (rc_local == FQD_OK) rc_local = resolve_job(ctxs[i], &jobs[i], keep_bitmaps ? keep_bitmaps[i] : nullptr, R[i]);
+            if (rc_local == FQD_OK && jobs[i].n_records) { lmin = std::min(lmin, R[i].len_min); lmax = std::max(lmax, R[i].len_max); }
+        }
+        // agreement: [rc, lmin, lmax, n, index base, arena capacity, arena offset after the inputs, previous high-water mark]
+        std::vector<std::vector<uint64_t>> mine(n_local, std::vector<uint64_t>(8, 0));
+        for (int i = 0; i < n_local; i++) {
+            mine[i][0] = (uint64_t)rc_local;
+            mine[i][1] = ex ? lmin : (jobs[i].n_records && rc_local == FQD_OK ? R[i].len_min : 0xFFFFFFFFu);
+            mine[i][2] = ex ? lmax : (jobs[i].n_records && rc_local == FQD_OK ? R[i].len_max : 0);
+            mine[i][3] = jobs[i].n_records;
+            mine[i][4] = index_bases[i];
+            mine[i][5] = ctxs[i]->arena.cap;
+            mine[i][6] = ctxs[i]->arena.off;
+            mine[i][7] = ctxs[i]->arena.last_high;
+        }
+        std::vector<uint64_t> all;
+        FQD_TRY(gather_u64(ctxs, n_local, ex, world, 8, mine, all));
+        int rc_any = FQD_OK;
+        for (int g = 0; g < world; g++) if (all[(size_t)g * 8] != FQD_OK && rc_any == FQD_OK) rc_any = (int)all[(size_t)g * 8];
+        if (rc_any != FQD_OK) {
+            if (rc_local == FQD_OK) set_error("another rank of the sharded job failed before the plan started (status %d)", rc_any);
+            return rc_local != FQD_OK ? rc_local : rc_any;
+        }
+        lmin = 0xFFFFFFFFu; lmax = 0;
+        W.n_total = W.n_max = 0;
+        size_t off = 0, prev_high = 0;
+        for (int g = 0; g < world; g++) {
+            const uint64_t *v = &all[(size_t)g * 8];
+            if (v[3]) { lmin = std::min<uint32_t>(lmin, (uint32_t)v[1]); lmax = std::max<uint32_t>(lmax, (uint32_t)v[2]); }
+            W.base[g] = v[4];
+            W.base[g + 1] = v[4] + v[3];
+            W.n_total += v[3];
+            W.n_max = std::max(W.n_max, v[3]);
+            off = std::max<size_t>(off, (size_t)v[6]);
+            prev_high = std::max<size_t>(prev_high, (size_t)v[7]);
+        }
+        for (int g = 0; g + 1 < world; g++)
+            if (all[(size_t)(g + 1) * 8 + 4] != W.base[g + 1]) { set_error("the shards of the ranks are not contiguous in rank order"); return FQD_ERR_ARG; }
+        if (lmin == 0xFFFFFFFFu) lmin = lmax = 0;   // no records anywhere
+        if (!want_tiles) break;
+        // the tile-sharded plan lets ranks read each other's arena slabs: every slab must hold the whole job
+        // (nothing in overflow chunks) and must not move while others look at it
+        W.shared_off = (off + 4095) & ~(size_t)4095;
+        size_t need = W.shared_off + tile_plan_bytes(W.n_total, W.n_max, world, jobs[0].max_distance, jobs[0].method);
+        need = std::max(need, prev_high + prev_high / 16);
+        bool any_grow = false;
+        std::vector<bool> grows(world);
+        for (int g = 0; g < world; g++) { grows[g] = (size_t)all[(size_t)g * 8 + 5] < need; any_grow = any_grow || grows[g]; }
+        if (!any_grow) break;
+        if (attempt >= 2) { set_error("internal: arena reservation did not converge"); return FQD_ERR_NOMEM; }
+        // (1) everybody drops its view of the slabs about to be replaced, (2) barrier, (3) the owners replace them
+        if (ex) {
+            for (int g = 0; g < world; g++)
+                if (grows[g] && ex->peer_open[g]) { cudaIpcCloseMemHandle(ex->peer_map[g]); ex->peer_open[g] = false; }
+            std::vector<std::vector<uint64_t>> dummy(1, std::vector<uint64_t>(1, 0));
+            FQD_TRY(gather_u64(ctxs, n_local, ex, world, 1, dummy, all));
+        }
+        for (int i = 0; i < n_local; i++) {
+            const int g = ex ? ex->rank : i;
+            if (!grows[g]) continue;
+            FQD_CUDA(cudaSetDevice(ctxs[i]->device));
+            // a little more than asked for, so that jobs of similar size do not trigger the protocol again
+            int rc = arena_reserve(ctxs[i], need + need / 8);
+            if (rc != FQD_OK) return rc;   // (the next agreement round would report it; out of memory is fatal anyway)
+        }
     }
-    if (ex) {   // agree on the global key length range
-        fqd_context *ctx = ctxs[0];
-        const size_t mark = arena_mark(ctx);
-        void *din = nullptr, *dout = nullptr;
-        FQD_TRY(dev_alloc(ctx, 16, &din));
-        FQD_TRY(dev_alloc(ctx, (size_t)world * 8 + 16, &dout));
-        uint32_t mine[2] = {lmin, lmax};
-        std::vector<uint32_t> all((size_t)world * 2);
-        FQD_CUDA(cudaMemcpyAsync(din, mine, 8, cudaMemcpyHostToDevice, ctx->stream));
-        FQD_TRY(ex->allgather(din, dout, 8, ctx->stream));
-        FQD_CUDA(cudaMemcpyAsync(all.data(), dout, (size_t)world * 8, cudaMemcpyDeviceToHost, ctx->stream));
-        FQD_CUDA(cudaStreamSynchronize(ctx->stream));
-        for (int g = 0; g < world; g++) { lmin = std::min(lmin, all[2 * g]); lmax = std::max(lmax, all[2 * g + 1]); }
-        arena_release(ctx, mark);
-    }
-    if (lmin == 0xFFFFFFFFu) lmin = lmax = 0;   // no records anywhere
+    if (want_tiles) FQD_TRY(map_peer_arenas(ctxs, n_local, ex, W));
     std::vector<DeviceJob> dj(n_local);
     std::vector<uint32_t> bases(n_local);
     std::vector<fqd_cluster_stats *> sp(n_local);
@@ -534,17 +707,20 @@ static int cluster_sharded_common(fqd_context **ctxs, int n_local, Exchange *ex,
         marks[i] = arena_mark(ctxs[i]);
     }
     int rc = FQD_OK;
-    for (int attempt = 0; attempt < 3; attempt++) {
+    bool replicated = !want_tiles || !W.peers_mapped;
+    for (int attempt = 0; attempt < 4; attempt++) {
         for (int i = 0; i < n_local; i++) { arena_release(ctxs[i], marks[i]); dj[i] = R[i].dj; }
         Codec codec;
         FQD_TRY(make_codec(alphabet, lmin != lmax, &codec));
         uint32_t unknown[8] = {};
-        rc = run_sharded(ctxs, dj.data(), bases.data(), sp.data(), n_local, ex, world, codec, lmax, unknown);
+        rc = run_sharded(ctxs, dj.data(), bases.data(), sp.data(), n_local, ex, W, codec, lmax, unknown, replicated);
+        if (rc == RC_FALLBACK_REPLICATED && !replicated) { replicated = true; continue; }
         if (rc != RC_RETRY_ALPHABET) break;
         for (int c = 0; c < 256; c++)
             if (unknown[c >> 5] & (1u << (c & 31))) alphabet.push_back((uint8_t)c);
     }
     if (rc == RC_RETRY_ALPHABET) { set_error("internal: alphabet did not converge"); rc = FQD_ERR_CUDA; }
+    if (rc == RC_FALLBACK_REPLICATED) { set_error("internal: plan fallback did not converge"); rc = FQD_ERR_CUDA; }
     if (rc != FQD_OK) return rc;
     for (int i = 0; i < n_local; i++) {
         FQD_CUDA(cudaSetDevice(ctxs[i]->device));
@@ -569,6 +745,9 @@ int fqd_comm_create(fqd_context *ctx, int rank, int world, const uint8_t id[128]
 void fqd_comm_destroy(fqd_comm *comm)
 {
     if (!comm) return;
+    if (comm->ex)
+        for (int g = 0; g < 64; g++)
+            if (comm->ex->peer_open[g]) cudaIpcCloseMemHandle(comm->ex->peer_map[g]);
     delete comm->ex;
     delete comm;
 }

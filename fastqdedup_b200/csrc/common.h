@@ -5,6 +5,7 @@
 #include <stdarg.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include <string>
 #include <vector>
@@ -51,6 +52,11 @@ struct fqd_arena {
     size_t off = 0;          // bump pointer (may exceed cap: then the job ran on overflow chunks)
     size_t high = 0;         // high-water mark of off over the last job
     std::vector<void *> overflow;
+    // sharded jobs read each other's slabs (peer memory): once a slab has been shown to other ranks it is only
+    // ever replaced through arena_reserve, between jobs, after every rank has dropped its view of it
+    bool shared = false;
+    uint64_t generation = 0; // bumped whenever the slab is replaced
+    size_t last_high = 0;    // high-water mark of the previous job (sizes the next reservation)
 };
 
 struct fqd_context {
@@ -74,6 +80,7 @@ void dev_free(fqd_context *ctx, void *p);
 int arena_reset(fqd_context *ctx);                    // start of a job: everything is released
 inline size_t arena_mark(fqd_context *ctx) { return ctx->arena.off; }
 void arena_release(fqd_context *ctx, size_t mark);    // drop everything allocated after mark
+int arena_reserve(fqd_context *ctx, size_t bytes);    // (empty arena only) make the slab at least this large
 
 // RAII holder for job-lifetime device buffers
 struct DevBuf {
@@ -132,7 +139,21 @@ struct DeviceJob {
 };
 
 constexpr int RC_RETRY_ALPHABET = -100;   // internal: unknown bytes were seen, grow the alphabet
+constexpr int RC_FALLBACK_REPLICATED = -102;   // internal: the tile-sharded plan gave up (skew), run the replicated-set plan
 constexpr int RC_NOT_IN_GROUP = -101;     // internal: the (K, PW) instantiation lives in another instance group
+
+// What every rank of a sharded job knows about the others before the plan starts (agreed in
+// cluster_sharded_common, api.cu).
+constexpr int MAX_WORLD = 64;
+struct ShardWorld {
+    int world = 1;
+    uint64_t base[MAX_WORLD + 1] = {};   // rank g holds the records [base[g], base[g+1])
+    uint64_t n_total = 0, n_max = 0;     // all records; the largest shard
+    size_t shared_off = 0;               // arena offset (the same on every rank) where the plan's buffers start
+    char *peer_base[MAX_WORLD] = {};     // arena slab of rank g as this process sees it (own slab, peer memory
+                                         // mapped through CUDA IPC, or another context of this process)
+    bool peers_mapped = false;           // false: no peer views (the tile-sharded plan cannot run)
+};
 
 // pipeline.cu: runs the stages for one (K, PW) instantiation
 int run_pipeline(fqd_context *ctx, const DeviceJob &job, const Codec &codec,
@@ -141,8 +162,26 @@ int run_pipeline(fqd_context *ctx, const DeviceJob &job, const Codec &codec,
 // virtual ranks when ex == nullptr, exactly one over NCCL otherwise)
 struct Exchange;
 int run_sharded(fqd_context **ctxs, const DeviceJob *jobs, const uint32_t *index_base,
-                fqd_cluster_stats **stats, int n_local, Exchange *ex, int world, const Codec &codec,
-                uint32_t max_len, uint32_t unknown_out[8]);
+                fqd_cluster_stats **stats, int n_local, Exchange *ex, const ShardWorld &W, const Codec &codec,
+                uint32_t max_len, uint32_t unknown_out[8], bool replicated_plan);
+// whether a job can take the tile-sharded plan, and how much arena it needs past W.shared_off
+bool tile_plan_eligible(const DeviceJob &job, const Codec &codec, uint32_t max_len, int world);
+size_t tile_plan_bytes(uint64_t n_total, uint64_t n_max, int world, int d, int method);
+
+inline uint32_t env_u32(const char *name, uint32_t fallback)
+{
+    const char *e = getenv(name);
+    return e && *e ? (uint32_t)strtoul(e, nullptr, 10) : fallback;
+}
+
+// partitions of the streaming plan: regions of TILE_R records filled to ~60 % on average
+inline uint32_t tile_partitions(uint64_t n)
+{
+    const uint32_t fill_pct = env_u32("FQD_TILE_FILL_PCT", 60);
+    const uint32_t pct = fill_pct < 20 ? 20 : fill_pct > 90 ? 90 : fill_pct;
+    const uint64_t parts = (n * 100 + (uint64_t)TILE_R * pct - 1) / ((uint64_t)TILE_R * pct);
+    return (uint32_t)(parts < 1 ? 1 : parts);
+}
 
 // largest key (in symbols) this build can pack for a given number of code bits
 uint32_t max_supported_length(int bits);

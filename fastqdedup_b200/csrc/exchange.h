@@ -11,6 +11,10 @@ namespace fqd {
 
 struct Exchange {
     int rank = 0, world = 1;
+    // views of the other ranks' arena slabs (CUDA IPC), kept across jobs while the slabs stay the same
+    void *peer_map[64] = {};
+    unsigned char peer_handle[64][64] = {};
+    bool peer_open[64] = {};
     virtual ~Exchange() {}
     // every rank contributes `bytes` bytes; recv holds world * bytes
     virtual int allgather(const void *send, void *recv, size_t bytes, cudaStream_t s) = 0;

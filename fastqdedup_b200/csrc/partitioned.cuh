@@ -43,7 +43,33 @@ constexpr int TILE_THREADS = 128;
 constexpr int TILE_E = 256;                // edges a tile buffers in shared memory before hooking inline
 static_assert(TILE_R <= 1024, "tile-local indices are packed into 10 bits");
 constexpr uint32_t TILE_EMPTY = 0xFFFFFFFFu;
-constexpr uint32_t EDGE_ONE = 0x80000000u; // edge flag: both ends have count 1 (also joins the count-1 forest)
+// An edge is (x, y | state): ids use the low 29 bits of y, the state says what the edge means to the dissection
+// (closed forms).  One GPU writes the directional flag bytes at once and only ever stores
+// NONE / ONE; a sharded job cannot (x and y belong to other ranks), so there every consequence of an edge
+// travels in its state and is applied where the edge lists of all ranks are merged (apply_edges_kernel).
+constexpr uint32_t EDGE_SHIFT = 29;
+constexpr uint32_t EDGE_ID = (1u << EDGE_SHIFT) - 1u;
+constexpr uint32_t EDGE_NONE = 0u << EDGE_SHIFT;
+constexpr uint32_t EDGE_ONE = 1u << EDGE_SHIFT;      // both ends have count 1: the edge also joins the count-1 forest
+constexpr uint32_t EDGE_DEAD_X = 2u << EDGE_SHIFT;   // x has count 1 and touches a key with count >= 2
+constexpr uint32_t EDGE_DEAD_Y = 3u << EDGE_SHIFT;
+constexpr uint32_t EDGE_DOM_X = 4u << EDGE_SHIFT;    // x (count >= 2) has a neighbour with count >= 2 * count_x - 1
+constexpr uint32_t EDGE_DOM_Y = 5u << EDGE_SHIFT;
+constexpr uint32_t EDGE_STATE = 7u << EDGE_SHIFT;
+
+// Where the records of a tile come from.  One GPU: one partition buffer, one fill counter per tile.  A job
+// sharded over G ranks: every rank partitions ITS records into its own buffer (all tiles, each ~1/G full);
+// tile t belongs to rank t / ntiles_per_rank, and the owner's tile kernel fetches the G fragments of the tile
+// straight from the peers' HBM (NVLink peer memory) with one bulk copy each -- the all-to-all of the records IS
+// the staging of the tile, there is no exchange buffer and no second partition pass.
+constexpr int MAX_RANKS = 16;
+struct TileSource {
+    const uint32_t *buf[MAX_RANKS];   // partition buffers (peer-mapped for the other ranks), regions indexed by GLOBAL tile
+    const uint32_t *cnt;              // [G][ntiles] fill counters of the owned tiles, gathered from all ranks
+    uint32_t G, self;
+    uint32_t first_tile;              // global index of owned tile 0
+    uint32_t ntiles;                  // owned tiles
+};
 
 __device__ __forceinline__ void tile_load_rec(const uint32_t *recs, uint32_t i, uint32_t (&e)[PART_RW])
 {
@@ -87,12 +113,53 @@ __device__ __forceinline__ void bulk_load_to_shared(void *dst, const void *src, 
     bulk_load_to_shared(dst, src, bytes, [] {});
 }
 
-// Stage one tile (cnt >= 1 records) while all threads clear `tab_n` table entries.
-__device__ __forceinline__ void stage_tile(uint32_t *recs, uint32_t *tab, uint32_t tab_n, const uint32_t *src, uint32_t cnt)
+// Stage owned tile j: its G fragments (one bulk copy each, issued by the first G lanes, all completing on one
+// mbarrier) land back to back in `recs` while all threads clear `tab_n` table entries.  Returns the number of
+// records staged; 0 = empty tile, > TILE_R = oversize tile (nothing was staged).
+__device__ __forceinline__ uint32_t stage_tile(uint32_t *recs, uint32_t *tab, uint32_t tab_n, const TileSource &S, uint32_t j)
 {
-    bulk_load_to_shared(recs, src, cnt * (PART_RW * 4u), [&] {
-        for (uint32_t i = threadIdx.x; i < tab_n; i += TILE_THREADS) tab[i] = TILE_EMPTY;
-    });
+    __shared__ __align__(8) uint64_t mbar;
+    const uint32_t tid = threadIdx.x;
+    uint32_t total = 0, mine = 0, before = 0;
+    bool over = false;
+    for (uint32_t g = 0; g < S.G; g++) {
+        const uint32_t c = S.cnt[(size_t)g * S.ntiles + j];
+        over |= c > (uint32_t)TILE_R;       // the rank's own region overflowed (the surplus is in its spill buffer)
+        if (g < tid) before += c;
+        if (g == tid) mine = c;
+        total += c;
+    }
+    if (total == 0) return 0;
+    if (over || total > (uint32_t)TILE_R) return TILE_R + 1;
+    const uint32_t mbar_a = (uint32_t)__cvta_generic_to_shared(&mbar);
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar_a), "r"(1) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0)
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar_a), "r"(total * (PART_RW * 4u)) : "memory");
+    if (tid < S.G && mine) {
+        const uint32_t *src = S.buf[tid] + (size_t)(S.first_tile + j) * TILE_R * PART_RW;
+        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(recs + (size_t)before * PART_RW);
+        if (tid == S.self) {   // local HBM: read exactly once, evict-first in the L2
+            uint64_t policy;
+            asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                         ::"r"(dst), "l"(src), "r"(mine * (PART_RW * 4u)), "r"(mbar_a), "l"(policy) : "memory");
+        } else {               // a peer's HBM over NVLink
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(dst), "l"(src), "r"(mine * (PART_RW * 4u)), "r"(mbar_a) : "memory");
+        }
+    }
+    for (uint32_t i = tid; i < tab_n; i += TILE_THREADS) tab[i] = TILE_EMPTY;
+    uint32_t done;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(mbar_a), "r"(0) : "memory");
+    } while (!done);
+    __syncthreads();
+    return total;
 }
 
 // ---- the partition pass of the common large job -----------------------------------------------------
@@ -155,9 +222,9 @@ static __global__ void __launch_bounds__(256) partition_dna_kernel(const __grid_
         if (go[r]) part_place(P.part, part[r], pos[r], e[r]);
 }
 
-// pass edges: (ui, uj | EDGE_ONE) pairs waiting for apply_edges_kernel
+// pass edges: (ui, uj | state) pairs waiting for apply_edges_kernel
 struct EdgeSink {
-    uint2 *edges;          // (ui, uj | EDGE_ONE) pairs of this pass
+    uint2 *edges;          // (ui, uj | state) pairs of this pass
     uint32_t *n_edges;
     uint32_t cap;
     uint32_t *overflow;    // set when a partition outgrew its tile: the pass is redone by the counting-sort plan
@@ -168,9 +235,19 @@ template <int K, int PW>
 __device__ __forceinline__ uint32_t tile_edge_flags(const PassParams &P, uint32_t ui, uint32_t uj, uint32_t ci, uint32_t cj,
                                                     const Key<K, PW> &ki, const Key<K, PW> &kj)
 {
-    uint32_t flag = 0;
+    uint32_t flag = EDGE_NONE;
     if (P.method == METHOD_DIRECTIONAL) {
         // closed form of reference __init__.py:60-91
+        if (P.edge_flags) {
+            // sharded job: ui / uj are global ids of other ranks' keys -- the consequence travels with the edge
+            // (the five cases exclude each other: two counts >= 2 cannot dominate each other)
+            if (ci == 1 && cj == 1) flag = EDGE_ONE;
+            else if (ci == 1) flag = EDGE_DEAD_X;
+            else if (cj == 1) flag = EDGE_DEAD_Y;
+            else if ((unsigned long long)cj >= 2ull * ci - 1ull) flag = EDGE_DOM_X;
+            else if ((unsigned long long)ci >= 2ull * cj - 1ull) flag = EDGE_DOM_Y;
+            return flag;
+        }
         if (ci >= 2 && (unsigned long long)cj >= 2ull * ci - 1ull) P.dominated[ui] = 1;
         if (cj >= 2 && (unsigned long long)ci >= 2ull * cj - 1ull) P.dominated[uj] = 1;
         if (ci == 1 && cj == 1) flag = EDGE_ONE;
@@ -253,11 +330,11 @@ __device__ __forceinline__ void tile_bucket_pass(const uint32_t *recs, uint32_t 
                     const uint32_t gpos = atomicAdd(E.n_edges, 1u);
                     if (gpos < E.cap) {
                         E.edges[gpos] = make_uint2(ui, f[KW + 1] | flag);
-                    } else if constexpr (CAN_UNION) {
+                    } else if (CAN_UNION && !P.edge_flags) {
                         if (uf_union(P.parent_full, ui, f[KW + 1])) merges++;
-                        if (flag) uf_union(P.parent_one, ui, f[KW + 1]);
+                        if (flag == EDGE_ONE) uf_union(P.parent_one, ui, f[KW + 1]);
                     } else {
-                        *E.overflow = 1u;           // the forest does not exist yet: the caller redoes the pass
+                        *E.overflow = 1u;           // no forest to hook into (yet / on this rank): the caller redoes the pass
                     }
                 }
             }
@@ -273,10 +350,10 @@ __device__ __forceinline__ void tile_bucket_pass(const uint32_t *recs, uint32_t 
         const uint32_t ed = s_edge[k];
         const uint32_t ui = recs[(size_t)(ed & 1023u) * PART_RW + KW + 1], uj = recs[(size_t)((ed >> 10) & 1023u) * PART_RW + KW + 1];
         if (pos < E.cap) {
-            E.edges[pos] = make_uint2(ui, uj | (ed & EDGE_ONE));
-        } else if constexpr (CAN_UNION) {
+            E.edges[pos] = make_uint2(ui, uj | (ed & EDGE_STATE));
+        } else if (CAN_UNION && !P.edge_flags) {
             if (uf_union(P.parent_full, ui, uj)) merges++;
-            if (ed & EDGE_ONE) uf_union(P.parent_one, ui, uj);
+            if ((ed & EDGE_STATE) == EDGE_ONE) uf_union(P.parent_one, ui, uj);
         } else {
             *E.overflow = 1u;
         }
@@ -290,7 +367,9 @@ struct DedupeOut {
     uint32_t *n_unique;     // dense output cursor
     uint32_t *oversize;     // list of partitions that outgrew their region (handled by the spill path)
     uint32_t *n_oversize;
-    int keep_zero;          // sharded jobs keep keys whose every record was filtered (weight 0)
+    int keep_zero;          // replicated-set plan: keep keys whose every record was filtered (weight 0)
+    uint32_t cap;           // entries of the dense arrays (a tile that would write past them sets *overflow)
+    uint32_t *overflow;
 };
 
 // FUSED: the records were partitioned by the hash of pigeonhole block 0, so a tile holds whole
@@ -308,7 +387,7 @@ struct NextPass {
 };
 
 template <int K, int PW, bool FUSED>
-static __global__ void __launch_bounds__(TILE_THREADS) dedupe_tile_kernel(const __grid_constant__ PartParams Q,
+static __global__ void __launch_bounds__(TILE_THREADS) dedupe_tile_kernel(const __grid_constant__ TileSource S,
                                                                           const __grid_constant__ DedupeOut O,
                                                                           const __grid_constant__ PassParams P,
                                                                           const __grid_constant__ EdgeSink E,
@@ -320,14 +399,13 @@ static __global__ void __launch_bounds__(TILE_THREADS) dedupe_tile_kernel(const 
     __shared__ uint32_t tab[TILE_T];
     __shared__ uint32_t warp_sums[32];
     __shared__ uint32_t total, s_base;
-    const uint32_t p = blockIdx.x, tid = threadIdx.x;
-    const uint32_t cnt = Q.cursor[p];
+    const uint32_t p = blockIdx.x, tid = threadIdx.x;   // p: owned tile
+    const uint32_t cnt = stage_tile(recs, tab, TILE_T, S, p);
     if (cnt == 0) return;
     if (cnt > (uint32_t)TILE_R) {
         if (tid == 0) O.oversize[atomicAdd(O.n_oversize, 1u)] = p;
         return;
     }
-    stage_tile(recs, tab, TILE_T, Q.buf + (size_t)p * TILE_R * PART_RW, cnt);
 
     // A record either wins an empty table entry (it becomes the representative of its key) or
     // meets the representative and adds its weight / lowers the first index there.
@@ -381,6 +459,10 @@ static __global__ void __launch_bounds__(TILE_THREADS) dedupe_tile_kernel(const 
         if ((rep >> r) & 1u) replist[off++] = (uint16_t)(r * TILE_THREADS + tid);
     __syncthreads();
     const uint32_t nrep = total, base = s_base;
+    if (base + nrep > O.cap) {   // (only a sharded job sizes the arrays below the record count)
+        if (tid == 0) *O.overflow = 1u;
+        return;
+    }
     for (uint32_t k = tid; k < nrep; k += TILE_THREADS) {
         const uint32_t i = replist[k], pos = base + k;
         uint32_t e[PART_RW];
@@ -390,7 +472,8 @@ static __global__ void __launch_bounds__(TILE_THREADS) dedupe_tile_kernel(const 
         O.ucount[pos] = e[KW];
         O.ufirst[pos] = e[KW + 1];
         if constexpr (FUSED) {
-            recs[(size_t)i * PART_RW + KW + 1] = pos;   // the record now carries its unique id
+            const uint32_t gid = pos * S.G + S.self;    // unique id in the job-wide id space (ranks interleaved)
+            recs[(size_t)i * PART_RW + KW + 1] = gid;   // the record now carries its unique id
             if (X.next.buf) {
                 Key<K, PW> ki;
 #pragma unroll
@@ -402,7 +485,7 @@ static __global__ void __launch_bounds__(TILE_THREADS) dedupe_tile_kernel(const 
                     bl = block_start(len, (uint32_t)X.pass_j + 1u, (uint32_t)P.d + 1u) - st;
                 }
                 const uint64_t sig = block_hash(ki, st, bl, ((uint64_t)X.pass_j << 32) | len);   // == pass_variant of that pass
-                e[KW + 1] = pos;
+                e[KW + 1] = gid;
                 part_append(X.next, part_of(sig, X.next.nparts), e);
             }
         }
@@ -473,7 +556,7 @@ static __global__ void __launch_bounds__(256) bucket_partition_kernel(const __gr
 #pragma unroll
         for (int i = 0; i < KW; i++) e[r][i] = key.w[i];
         e[r][KW] = __ldcs(P.ucount + u);
-        e[r][KW + 1] = (uint32_t)u;
+        e[r][KW + 1] = (uint32_t)u * P.id_mul + P.id_add;   // job-wide id (sharded: ranks interleaved)
     }
 #pragma unroll
     for (int r = 0; r < BP_ROWS; r++) {
@@ -485,7 +568,7 @@ static __global__ void __launch_bounds__(256) bucket_partition_kernel(const __gr
         uint64_t sig;
         bool build;
         pass_variant<K, PW>(key, len, P, 0, sig, build);
-        go[r] = !(P.world > 1 && (uint32_t)(sig >> 32) % (uint32_t)P.world != (uint32_t)P.my_rank);
+        go[r] = !(P.world > 1 && !P.edge_flags && (uint32_t)(sig >> 32) % (uint32_t)P.world != (uint32_t)P.my_rank);
         part[r] = part_of(sig, Q.nparts);
         if (go[r]) pos[r] = atomicAdd(Q.cursor + part[r], 1u);
     }
@@ -495,7 +578,7 @@ static __global__ void __launch_bounds__(256) bucket_partition_kernel(const __gr
 }
 
 template <int K, int PW>
-static __global__ void __launch_bounds__(TILE_THREADS) bucket_tile_kernel(const __grid_constant__ PartParams Q,
+static __global__ void __launch_bounds__(TILE_THREADS) bucket_tile_kernel(const __grid_constant__ TileSource S,
                                                                           const __grid_constant__ PassParams P,
                                                                           const __grid_constant__ EdgeSink E)
 {
@@ -504,14 +587,13 @@ static __global__ void __launch_bounds__(TILE_THREADS) bucket_tile_kernel(const 
     __shared__ __align__(16) uint32_t recs[TILE_R * PART_RW];
     __shared__ uint32_t tab[TILE_T];
     __shared__ uint32_t s_edges[TILE_E];
-    const uint32_t p = blockIdx.x, tid = threadIdx.x;
-    const uint32_t cnt = Q.cursor[p];
+    const uint32_t p = blockIdx.x, tid = threadIdx.x;   // p: owned tile
+    const uint32_t cnt = stage_tile(recs, tab, 0, S, p);   // (the pass clears the table itself)
     if (cnt == 0) return;
     if (cnt > (uint32_t)TILE_R) {
         if (tid == 0) *E.overflow = 1u;
         return;
     }
-    stage_tile(recs, tab, 0, Q.buf + (size_t)p * TILE_R * PART_RW, cnt);   // (the pass clears the table itself)
     uint32_t merges = 0, cand = 0;
     tile_bucket_pass<K, PW, true>(   // (starts with a barrier)
         recs, tab, TILE_T, s_edges, TILE_E, cnt, [](uint32_t k) { return k; },
@@ -556,21 +638,283 @@ static __global__ void __launch_bounds__(256) range_pairs_kernel(const __grid_co
     }
 }
 
-static __global__ void __launch_bounds__(256) apply_edges_kernel(const uint2 *__restrict__ edges, const uint32_t *__restrict__ n_edges,
-                                                                 uint32_t cap, uint32_t *parent_full, uint32_t *parent_one,
+// The edge lists of all ranks (one list on one GPU).  A sharded job never gathers them: every rank's
+// apply_edges_kernel streams the peers' lists out of their HBM over NVLink while it hooks -- the all-gather of
+// the edges is fused into the union-find that consumes them.
+struct EdgeSource {
+    const uint2 *edges[MAX_RANKS];
+    uint32_t cap[MAX_RANKS];
+    const uint32_t *n_edges;    // [G * n_stride] edge counters of all ranks (gathered; a local copy)
+    uint32_t n_stride;          // counter of rank g: n_edges[g * n_stride]
+    uint32_t G, self;
+};
+
+// Per-key state of the dissection that edges set (all byte arrays over the job-wide id space; null = not needed).
+struct EdgeFlags {
+    uint8_t *dominated;   // directional: written for this rank's own ids only
+    uint8_t *dead;        // directional: every rank keeps all of them (a dead member kills its whole count-1 component)
+    uint8_t *linked;      // the key has an edge of the kind the dissection reduces over (directional: count-1 edges;
+                          // highest_count: any edge) -- keys without one are their own component and need no exchange
+    int any_edge;         // highest_count: `linked` for every edge
+};
+
+static __global__ void __launch_bounds__(256) apply_edges_kernel(const __grid_constant__ EdgeSource E, uint32_t *parent_full,
+                                                                 uint32_t *parent_one, const __grid_constant__ EdgeFlags F,
                                                                  DevCounters *ctr)
 {
-    const uint32_t n = min(*n_edges, cap);
     uint32_t merges = 0;
     // (prefetching the next edge's parents into the L2 while hooking the current one was measured slower)
-    for (uint32_t i = blockIdx.x * 256u + threadIdx.x; i < n; i += gridDim.x * 256u) {
-        const uint2 ed = __ldcs(edges + i);
-        const uint32_t uj = ed.y & ~EDGE_ONE;
-        if (uf_union(parent_full, ed.x, uj)) merges++;
-        if (ed.y & EDGE_ONE) uf_union(parent_one, ed.x, uj);
+    for (uint32_t k = 0; k < E.G; k++) {
+        const uint32_t g = (k + blockIdx.x) % E.G;   // blocks start on different peers: all NVLink ports busy at once
+        const uint32_t n = min(E.n_edges[(size_t)g * E.n_stride], E.cap[g]);
+        const uint2 *edges = E.edges[g];
+        for (uint32_t i = blockIdx.x * 256u + threadIdx.x; i < n; i += gridDim.x * 256u) {
+            const uint2 ed = __ldcs(edges + i);
+            const uint32_t x = ed.x, y = ed.y & EDGE_ID, st = ed.y & EDGE_STATE;
+            if (uf_union(parent_full, x, y)) merges++;
+            if (st == EDGE_ONE) {
+                if (parent_one) uf_union(parent_one, x, y);
+                if (F.linked) { F.linked[x] = 1; F.linked[y] = 1; }
+            } else if (st == EDGE_DEAD_X) {
+                F.dead[x] = 1;
+            } else if (st == EDGE_DEAD_Y) {
+                F.dead[y] = 1;
+            } else if (st == EDGE_DOM_X) {
+                if (x % E.G == E.self) F.dominated[x] = 1;
+            } else if (st == EDGE_DOM_Y) {
+                if (y % E.G == E.self) F.dominated[y] = 1;
+            }
+            if (F.any_edge) { F.linked[x] = 1; F.linked[y] = 1; }
+        }
     }
     for (int o = 16; o; o >>= 1) merges += __shfl_xor_sync(WARP_FULL, merges, o);
     if ((threadIdx.x & 31) == 0 && merges) atomicAdd(&ctr->n_merges, merges);
+}
+
+// ---- dissection of a tile-sharded job ---------------------------------------------------------------
+//
+// Every rank holds the whole forests (it applied all edges) but only ITS keys.  Flags and roots are enough
+// for most keys; where a component's answer depends on the keys of several members (the largest key of a
+// count-1 component, the largest (count, key) of a cluster) the members that matter become CANDIDATES --
+// {key, count, id} records in each rank's candidate list -- and every rank reduces all candidate lists
+// (read from the peers' HBM) into best[root].
+
+// directional: a dead member makes its count-1 component dead (replicated: all ids)
+static __global__ void __launch_bounds__(256) deadroot_kernel(uint32_t n_ids, const uint8_t *__restrict__ dead,
+                                                              const uint8_t *__restrict__ linked, uint32_t *parent_one,
+                                                              uint8_t *deadroot)
+{
+    const uint32_t g = blockIdx.x * 256u + threadIdx.x;
+    if (g >= n_ids || !dead[g]) return;
+    if (!linked[g]) return;   // its own component: select_own_kernel reads dead[] directly
+    deadroot[uf_find(parent_one, g)] = 1;
+}
+
+struct CandParams {
+    uint32_t U;               // this rank's uniques
+    uint32_t G, self;
+    const uint32_t *ukey, *ucount;
+    uint32_t *forest;         // parent_one (directional) / parent_full (highest_count)
+    const uint8_t *dead, *linked, *deadroot;
+    uint32_t *root_of;        // per own unique: root of its component in `forest`
+    uint32_t *loc_of;         // per own unique: (self << 28 | index) of its candidate record, or NO_CLAIM
+    uint32_t *cand;           // candidate records {key[KW], count, id} of PART_RW words
+    uint32_t *cand_root;
+    uint32_t *n_cand;
+    uint32_t cap;
+    int method;
+};
+
+template <int K, int PW>
+static __global__ void __launch_bounds__(256) candidates_kernel(const __grid_constant__ CandParams P)
+{
+    constexpr int KW = K * PW;
+    static_assert(slot_words(KW) == PART_RW, "candidate records are 32 bytes");
+    const uint32_t u = blockIdx.x * 256u + threadIdx.x;
+    bool emit = false;
+    uint32_t root = 0, gid = 0, c = 0;
+    if (u < P.U) {
+        gid = u * P.G + P.self;
+        c = P.ucount[u];
+        root = gid;
+        if (P.method == METHOD_DIRECTIONAL) {
+            if (c == 1 && P.linked[gid] && !P.dead[gid]) {
+                root = uf_find(P.forest, gid);
+                emit = !P.deadroot[root];
+            }
+        } else if (P.linked[gid]) {
+            root = uf_find(P.forest, gid);
+            emit = true;
+        }
+        P.root_of[u] = root;
+    }
+    const uint32_t pos = block_reserve(emit, P.n_cand);
+    if (u < P.U) P.loc_of[u] = (emit && pos < P.cap) ? ((P.self << 28) | pos) : NO_CLAIM;
+    if (emit && pos < P.cap) {
+        uint32_t e[PART_RW];
+#pragma unroll
+        for (int i = 0; i < PART_RW; i++) e[i] = 0;
+        Key<K, PW> key;
+        load_key_stream<K, PW>(P.ukey, u, key);
+#pragma unroll
+        for (int i = 0; i < KW; i++) e[i] = key.w[i];
+        e[KW] = c;
+        e[KW + 1] = gid;
+        store_rec_stream(P.cand + (size_t)pos * PART_RW, e);
+        P.cand_root[pos] = root;
+    }
+}
+
+struct BestParams {
+    const uint32_t *cand[MAX_RANKS];
+    const uint32_t *cand_root[MAX_RANKS];
+    uint32_t cap[MAX_RANKS];
+    const uint32_t *n_cand;   // [G * n_stride] (gathered)
+    uint32_t n_stride;
+    uint32_t G;
+    uint32_t *best;           // per root: (rank << 28 | index) of the best candidate so far; NO_CLAIM = none
+    uint8_t rank_of_code[256];
+};
+
+// Per root keep the candidate with the largest (count, key) -- the head of the reference's descending sort
+// (__init__.py:99-101) resp. the survivor of a count-1 chain (:72, :91).  Replicated on every rank.
+template <int K, int PW>
+static __global__ void __launch_bounds__(256) best_candidate_kernel(const __grid_constant__ BestParams P)
+{
+    constexpr int KW = K * PW;
+    for (uint32_t k = 0; k < P.G; k++) {
+        const uint32_t g = (k + blockIdx.x) % P.G;
+        const uint32_t n = min(P.n_cand[(size_t)g * P.n_stride], P.cap[g]);
+        for (uint32_t i = blockIdx.x * 256u + threadIdx.x; i < n; i += gridDim.x * 256u) {
+            uint32_t e[PART_RW];
+            load_rec_stream(P.cand[g] + (size_t)i * PART_RW, e);
+            const uint32_t r = __ldcs(P.cand_root[g] + i);
+            const uint32_t me = (g << 28) | i;
+            Key<K, PW> km;
+#pragma unroll
+            for (int w = 0; w < KW; w++) km.w[w] = e[w];
+            uint32_t cur = ld_relaxed_u32(P.best + r);
+            for (;;) {
+                if (cur != NO_CLAIM) {
+                    uint32_t f[PART_RW];
+                    tile_load_rec(P.cand[cur >> 28], cur & 0x0FFFFFFFu, f);
+                    Key<K, PW> kc;
+#pragma unroll
+                    for (int w = 0; w < KW; w++) kc.w[w] = f[w];
+                    if (!prio_less<K, PW>(f[KW], kc, e[KW], km, P.rank_of_code)) break;   // cur >= me
+                }
+                const uint32_t old = atomicCAS(P.best + r, cur, me);
+                if (old == cur) break;
+                cur = old;
+            }
+        }
+    }
+}
+
+struct SelectOwnParams {
+    uint32_t U, G, self;
+    const uint32_t *ucount, *ufirst;
+    const uint32_t *root_of, *loc_of, *best;
+    const uint8_t *dominated, *dead, *linked, *deadroot, *state;
+    uint8_t *selected;        // per own unique
+    uint32_t *bitmap[MAX_RANKS];       // keep bitmaps of all ranks (peer memory): bit (f - base[q]) of rank q
+    uint32_t base[MAX_RANKS + 1];      // record index ranges of the ranks
+    int method;
+    DevCounters *ctr;
+};
+
+// The keys of this rank decide; the keep bit of a selected key goes to the rank that holds its first record
+// (reference pass 2, __init__.py:201-206) with one remote atomic OR.
+static __global__ void __launch_bounds__(256) select_own_kernel(const __grid_constant__ SelectOwnParams P)
+{
+    const uint32_t u = blockIdx.x * 256u + threadIdx.x;
+    bool sel = false;
+    if (u < P.U) {
+        const uint32_t gid = u * P.G + P.self;
+        const uint32_t c = __ldcs(P.ucount + u);
+        if (P.method == METHOD_DIRECTIONAL) {
+            if (c >= 2) sel = !P.dominated[gid];
+            else if (P.dead[gid]) sel = false;
+            else if (!P.linked[gid]) sel = true;
+            else sel = !P.deadroot[P.root_of[u]] && P.best[P.root_of[u]] == P.loc_of[u];
+        } else if (P.method == METHOD_HIGHEST) {
+            sel = !P.linked[gid] || P.best[P.root_of[u]] == P.loc_of[u];
+        } else {
+            sel = P.state[gid] == 1;
+        }
+        P.selected[u] = sel ? 1 : 0;
+        if (sel) {
+            const uint32_t f = __ldcs(P.ufirst + u);
+            uint32_t q = 0;
+            while (q + 1 < P.G && f >= P.base[q + 1]) q++;
+            const uint32_t t = f - P.base[q];
+            atomicOr(P.bitmap[q] + (t >> 5), 1u << (t & 31));
+        }
+    }
+    block_add(sel ? 1u : 0u, &P.ctr->n_selected);
+}
+
+// Oversize tiles of a sharded job: the fragments of the listed owned tiles (all ranks' regions) go through the
+// single-table insert on the owner.  grid.x = n_listed * G * (TILE_R / 256).
+template <int K, int PW>
+static __global__ void __launch_bounds__(256) spill_insert_tiles_kernel(const __grid_constant__ TileSource S,
+                                                                        const uint32_t *__restrict__ list,
+                                                                        const __grid_constant__ TableRef tab, uint32_t *n_claimed)
+{
+    constexpr int KW = K * PW;
+    constexpr uint32_t BPP = TILE_R / 256;
+    const uint32_t j = list[blockIdx.x / (S.G * BPP)], g = (blockIdx.x / BPP) % S.G;
+    const uint32_t i = (blockIdx.x % BPP) * 256u + threadIdx.x;
+    const uint32_t n = min(S.cnt[(size_t)g * S.ntiles + j], (uint32_t)TILE_R);
+    uint32_t claimed = NO_CLAIM;
+    if (i < n) {
+        uint32_t e[PART_RW];
+        load_rec_stream(S.buf[g] + ((size_t)(S.first_tile + j) * TILE_R + i) * PART_RW, e);
+        Key<K, PW> key;
+#pragma unroll
+        for (int w = 0; w < KW; w++) key.w[w] = e[w];
+        claimed = table_insert<K, PW>(tab, key, hash_key(key), e[KW + 1], e[KW]);
+    }
+    const uint32_t pos = block_reserve(claimed != NO_CLAIM, n_claimed);
+    if (claimed != NO_CLAIM) tab.uslot[pos] = claimed;
+}
+
+// ... and the records a rank had to spill (its own region of a tile was full): every owner scans every rank's
+// spill buffer and takes the records of its tiles.
+template <int K, int PW>
+static __global__ void __launch_bounds__(256) spill_insert_owned_kernel(const uint32_t *__restrict__ spill, uint32_t n,
+                                                                        uint32_t part_blocks, uint32_t d1, uint32_t nparts,
+                                                                        uint32_t first_tile, uint32_t ntiles, uint32_t max_len,
+                                                                        uint32_t pad_code, int varlen,
+                                                                        const __grid_constant__ TableRef tab, uint32_t *n_claimed)
+{
+    constexpr int KW = K * PW;
+    const uint32_t i = blockIdx.x * 256u + threadIdx.x;
+    uint32_t claimed = NO_CLAIM;
+    if (i < n) {
+        uint32_t e[PART_RW];
+        load_rec_stream(spill + (size_t)i * PART_RW, e);
+        Key<K, PW> key;
+#pragma unroll
+        for (int w = 0; w < KW; w++) key.w[w] = e[w];
+        const uint32_t len = varlen ? key_length(key, pad_code, max_len) : max_len;
+        const uint64_t h = part_blocks ? block0_hash(key, block_start(len, 1, d1), PART_SALT | len) : hash_key(key);
+        const uint32_t t = part_of(h, nparts);
+        if (t >= first_tile && t - first_tile < ntiles) claimed = table_insert<K, PW>(tab, key, hash_key(key), e[KW + 1], e[KW]);
+    }
+    const uint32_t pos = block_reserve(claimed != NO_CLAIM, n_claimed);
+    if (claimed != NO_CLAIM) tab.uslot[pos] = claimed;
+}
+
+// adjacency runs several rounds over the (higher, lower) edges of all ranks: fetch them from the peers once
+static __global__ void __launch_bounds__(256) adjacency_copy_kernel(const __grid_constant__ EdgeSource E, uint2 *dst,
+                                                                    const uint32_t *__restrict__ offsets)
+{
+    for (uint32_t g = 0; g < E.G; g++) {
+        const uint32_t n = min(E.n_edges[(size_t)g * E.n_stride], E.cap[g]);
+        const uint32_t off = offsets[g];
+        for (uint32_t i = blockIdx.x * 256u + threadIdx.x; i < n; i += gridDim.x * 256u) dst[off + i] = __ldcs(E.edges[g] + i);
+    }
 }
 
 }  // namespace fqd

@@ -684,7 +684,11 @@ struct PassParams {
     uint32_t max_len, pad_code;
     int pass_j, V;
     uint32_t fix_st, fix_bl;   // Hamming block of pass_j for keys of max_len symbols (set with pass_j)
-    int my_rank, world;     // buckets are owned by rank (sig >> 32) % world
+    int my_rank, world;     // replicated-set plan: buckets are owned by rank (sig >> 32) % world
+    // tile-sharded plan: ids are job-wide (local id * id_mul + id_add, ranks interleaved) and the consequences of
+    // an edge travel in its state bits instead of being written to the flag bytes (partitioned.cuh, EDGE_*)
+    uint32_t id_mul = 1, id_add = 0;
+    int edge_flags = 0;
     uint32_t nb_mask;
     uint32_t *cnt;          // NB+1 counters -> exclusive offsets after the scan
     uint32_t *rank;         // U*V
@@ -1232,7 +1236,8 @@ static __global__ void __launch_bounds__(256) gather_nonzero_kernel(uint32_t U, 
                                                                     uint32_t *__restrict__ ukey,
                                                                     uint32_t *__restrict__ ucount,
                                                                     uint32_t *__restrict__ ufirst,
-                                                                    uint32_t *kept, int keep_zero = 0)
+                                                                    uint32_t *kept, int keep_zero = 0,
+                                                                    uint32_t cap = 0xFFFFFFFFu, uint32_t *overflow = nullptr)
 {
     constexpr int KW = K * PW, RW = slot_words(KW);
     const uint32_t u = blockIdx.x * 256u + threadIdx.x;
@@ -1246,6 +1251,7 @@ static __global__ void __launch_bounds__(256) gather_nonzero_kernel(uint32_t U, 
     }
     if (w[KW] == 0 && !keep_zero) return;
     const uint32_t pos = aggregated_inc(kept);
+    if (pos >= cap) { *overflow = 1u; return; }
 #pragma unroll
     for (int i = 0; i < KW; i++) ukey[(size_t)pos * KW + i] = w[i];
     ucount[pos] = w[KW];

@@ -180,21 +180,71 @@ bool codec_is_dna(const Codec &c)
            c.lut['T'] == 2 && c.lut['G'] == 3 && c.lut['N'] == 7;
 }
 
-uint32_t env_u32(const char *name, uint32_t fallback)
-{
-    const char *e = getenv(name);
-    return e && *e ? (uint32_t)strtoul(e, nullptr, 10) : fallback;
-}
-
-// partitions of the streaming plan: regions of TILE_R records filled to ~60 % on average
-uint32_t tile_partitions(uint64_t n)
-{
-    const uint32_t fill_pct = std::min(90u, std::max(20u, env_u32("FQD_TILE_FILL_PCT", 60)));
-    return (uint32_t)std::max<uint64_t>(1, (n * 100 + (uint64_t)TILE_R * fill_pct - 1) / ((uint64_t)TILE_R * fill_pct));
-}
-
 constexpr uint64_t PARTITION_MIN_RECORDS = 4u << 20;
 constexpr uint64_t PARTITION_MIN_UNIQUES = 1u << 20;
+
+// One GPU: a tile has one source, the partition buffer of this GPU.
+inline TileSource single_source(const PartParams &q)
+{
+    TileSource S{};
+    S.buf[0] = q.buf;
+    S.cnt = q.cursor;
+    S.G = 1; S.self = 0; S.first_tile = 0; S.ntiles = q.nparts;
+    return S;
+}
+
+inline EdgeSource single_edges(const uint2 *edges, const uint32_t *n_edges, uint32_t cap)
+{
+    EdgeSource E{};
+    E.edges[0] = edges; E.cap[0] = cap; E.n_edges = n_edges; E.n_stride = 1; E.G = 1; E.self = 0;
+    return E;
+}
+
+// The partition pass of the streaming plan over the job's records: filter + pack + hash, every record appended to
+// the tile of its hash (of pigeonhole block 0 of `part_blocks` when > 0, of the whole key otherwise).
+template <int K, int PW>
+int launch_partition(fqd_context *ctx, const DeviceJob &job, const Codec &codec, const IngestParams &ip, const PartParams &part,
+                     uint32_t part_blocks, uint32_t index_base, StageTimes &tt)
+{
+    cudaStream_t s = ctx->stream;
+    uint32_t stride = 0;
+    if (!job.key_off) stride = job.key_stride;
+    if (job.filter_on && !job.qual_off) stride = std::max(stride, job.qual_stride);
+    const bool fixed_any = !job.key_off || (job.filter_on && !job.qual_off);
+    constexpr uint32_t BR = 256u * INGEST_ROWS;   // records per block
+    IngestParams pp = ip;
+    pp.part = part;
+    pp.phase = 0;
+    pp.part_blocks = part_blocks;
+    pp.codec.swar = codec.swar || (K == 3 && codec_is_dna(codec) && !getenv("FQD_NO_SWAR"));
+    size_t smem = 1280;
+    if (fixed_any && (size_t)stride * BR + 1280 <= 200 * 1024) {
+        pp.stage_bytes = stride * BR;
+        smem += pp.stage_bytes;
+    }
+    FQD_CUDA(cudaFuncSetAttribute(ingest_kernel<K, PW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // the common large job has its own lean partition kernel (partitioned.cuh)
+    int lean_nw = 0;
+    if constexpr (K == 3 && slot_words(K * PW) == PART_RW) {
+        if (codec_is_dna(codec) && !job.filter_on && !job.key_off && !job.key_lens && !job.weights && !job.varlen &&
+            job.key_stride == job.key_len && job.key_len == job.max_len && (job.key_len & 3u) == 0 &&
+            !getenv("FQD_NO_SWAR") && !getenv("FQD_NO_LEAN"))
+            lean_nw = (int)(job.key_len >> 2);
+    }
+    FQD_TRY(for_each_input_chunk(ctx, job, pp, index_base, nullptr, tt, [&](const IngestParams &cp) {
+        if constexpr (K == 3 && slot_words(K * PW) == PART_RW) {
+            if (lean_nw == 3) { partition_dna_kernel<PW, 3><<<cdiv(cp.n, 256 * LEAN_ROWS), 256, 0, s>>>(cp); return; }
+            if (lean_nw == 6) { partition_dna_kernel<PW, 6><<<cdiv(cp.n, 256 * LEAN_ROWS), 256, 0, s>>>(cp); return; }
+            if constexpr (PW >= 2) {
+                if (lean_nw == 9) { partition_dna_kernel<PW, 9><<<cdiv(cp.n, 256 * LEAN_ROWS), 256, 0, s>>>(cp); return; }
+                if (lean_nw == 12) { partition_dna_kernel<PW, 12><<<cdiv(cp.n, 256 * LEAN_ROWS), 256, 0, s>>>(cp); return; }
+            }
+        }
+        ingest_kernel<K, PW><<<cdiv(cp.n, BR), 256, smem, s>>>(cp);
+    }));
+    FQD_CUDA(cudaGetLastError());
+    return FQD_OK;
+}
 
 template <int K, int PW>
 int stage_dedupe(fqd_context *ctx, const DeviceJob &job, const Codec &codec, uint32_t index_base,
@@ -277,40 +327,11 @@ int stage_dedupe(fqd_context *ctx, const DeviceJob &job, const Codec &codec, uin
             FQD_CUDA(cudaMemsetAsync(cursor, 0, (size_t)nparts * 4, s));
             FQD_CUDA(cudaMemsetAsync(aux, 0, 32, s));
             FQD_CUDA(cudaEventRecord(ev[1], s));
-            constexpr uint32_t BR = 256u * INGEST_ROWS;   // records per block
-            IngestParams pp = ip;
-            pp.part = PartParams{buf, cursor, nparts, spill, aux, spill_cap};
-            pp.phase = 0;
-            pp.part_blocks = fused ? (uint32_t)job.d + 1u : 0u;
-            pp.codec.swar = codec.swar || (K == 3 && codec_is_dna(codec) && !getenv("FQD_NO_SWAR"));
-            size_t smem = 1280;
-            if (fixed_any && (size_t)stride * BR + 1280 <= 200 * 1024) {
-                pp.stage_bytes = stride * BR;
-                smem += pp.stage_bytes;
-            }
-            FQD_CUDA(cudaFuncSetAttribute(ingest_kernel<K, PW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            // the common large job has its own lean partition kernel (partitioned.cuh)
-            int lean_nw = 0;
-            if constexpr (K == 3) {
-                if (codec_is_dna(codec) && !job.filter_on && !job.key_off && !job.key_lens && !job.weights && !job.varlen &&
-                    job.key_stride == job.key_len && job.key_len == job.max_len && (job.key_len & 3u) == 0 &&
-                    !getenv("FQD_NO_SWAR") && !getenv("FQD_NO_LEAN"))
-                    lean_nw = (int)(job.key_len >> 2);
-            }
-            FQD_TRY(for_each_input_chunk(ctx, job, pp, index_base, nullptr, tt, [&](const IngestParams &cp) {
-                if constexpr (K == 3) {
-                    if (lean_nw == 3) { partition_dna_kernel<PW, 3><<<cdiv(cp.n, 256 * LEAN_ROWS), 256, 0, s>>>(cp); return; }
-                    if (lean_nw == 6) { partition_dna_kernel<PW, 6><<<cdiv(cp.n, 256 * LEAN_ROWS), 256, 0, s>>>(cp); return; }
-                    if constexpr (PW >= 2) {
-                        if (lean_nw == 9) { partition_dna_kernel<PW, 9><<<cdiv(cp.n, 256 * LEAN_ROWS), 256, 0, s>>>(cp); return; }
-                        if (lean_nw == 12) { partition_dna_kernel<PW, 12><<<cdiv(cp.n, 256 * LEAN_ROWS), 256, 0, s>>>(cp); return; }
-                    }
-                }
-                ingest_kernel<K, PW><<<cdiv(cp.n, BR), 256, smem, s>>>(cp);
-            }));
+            const PartParams part{buf, cursor, nparts, spill, aux, spill_cap};
+            FQD_TRY((launch_partition<K, PW>(ctx, job, codec, ip, part, fused ? (uint32_t)job.d + 1u : 0u, index_base, tt)));
             FQD_CUDA(cudaGetLastError());
             FQD_CUDA(cudaEventRecord(ev[2], s));
-            DedupeOut out{uq.ukey, uq.ucount, uq.ufirst, aux + 2, oversize, aux + 3, sharded ? 1 : 0};
+            DedupeOut out{uq.ukey, uq.ucount, uq.ufirst, aux + 2, oversize, aux + 3, sharded ? 1 : 0, (uint32_t)n, aux + 5};
             PassParams p0{};
             EdgeSink sink0{};
             if (fused) {
@@ -329,9 +350,9 @@ int stage_dedupe(fqd_context *ctx, const DeviceJob &job, const Codec &codec, uin
                     nx.st = block_start(job.max_len, 1u, (uint32_t)job.d + 1u);
                     nx.bl = block_start(job.max_len, 2u, (uint32_t)job.d + 1u) - nx.st;
                 }
-                dedupe_tile_kernel<K, PW, true><<<nparts, TILE_THREADS, 0, s>>>(pp.part, out, p0, sink0, nx);
+                dedupe_tile_kernel<K, PW, true><<<nparts, TILE_THREADS, 0, s>>>(single_source(part), out, p0, sink0, nx);
             } else {
-                dedupe_tile_kernel<K, PW, false><<<nparts, TILE_THREADS, 0, s>>>(pp.part, out, p0, sink0, NextPass{});
+                dedupe_tile_kernel<K, PW, false><<<nparts, TILE_THREADS, 0, s>>>(single_source(part), out, p0, sink0, NextPass{});
             }
             tt.launches++;
             FQD_CUDA(cudaGetLastError());
@@ -616,9 +637,9 @@ int stage_passes(fqd_context *ctx, const DeviceJob &job, const Codec &codec, con
                 tt.launches++;
             }
             FQD_CUDA(cudaEventRecord(cev[2 * j], s));
-            bucket_tile_kernel<K, PW><<<qp.nparts, TILE_THREADS, 0, s>>>(qp, pp, sink);
-            apply_edges_kernel<<<ctx->sm_count * 8, 256, 0, s>>>(sink.edges, sink.n_edges, sink.cap, f.parent_full, f.parent_one,
-                                                                ctx->d_ctr);
+            bucket_tile_kernel<K, PW><<<qp.nparts, TILE_THREADS, 0, s>>>(single_source(qp), pp, sink);
+            apply_edges_kernel<<<ctx->sm_count * 8, 256, 0, s>>>(single_edges(sink.edges, sink.n_edges, sink.cap), f.parent_full,
+                                                                f.parent_one, EdgeFlags{}, ctx->d_ctr);
             FQD_CUDA(cudaEventRecord(cev[2 * j + 1], s));
             FQD_CUDA(cudaGetLastError());
             tt.launches += 2;
@@ -801,7 +822,8 @@ int run_typed(fqd_context *ctx, const DeviceJob &job, const Codec &codec, fqd_cl
     FQD_CUDA(cudaEventRecord(ev[6], s));
     int first_pass = 0;
     if (fp.done && U > 1) {
-        apply_edges_kernel<<<ctx->sm_count * 8, 256, 0, s>>>(fp.edges, fp.aux, fp.edge_cap, f.parent_full, f.parent_one, ctx->d_ctr);
+        apply_edges_kernel<<<ctx->sm_count * 8, 256, 0, s>>>(single_edges(fp.edges, fp.aux, fp.edge_cap), f.parent_full, f.parent_one,
+                                                            EdgeFlags{}, ctx->d_ctr);
         tt.launches++;
         tt.pass0_fused = true;
         first_pass = 1;

@@ -24,8 +24,8 @@ int FQD_CAT(run_typed_group, FQD_GROUP)(int bits, int pw, fqd_context *ctx, cons
 }
 
 int FQD_CAT(run_sharded_group, FQD_GROUP)(int bits, int pw, fqd_context **ctxs, const DeviceJob *jobs, const uint32_t *index_base,
-                                          fqd_cluster_stats **stats, int n_local, Exchange *ex, int world, const Codec &codec,
-                                          uint32_t unknown_out[8])
+                                          fqd_cluster_stats **stats, int n_local, Exchange *ex, const ShardWorld &W, const Codec &codec,
+                                          uint32_t unknown_out[8], bool replicated_plan)
 {
     std::vector<Shard> S(n_local);
     for (int i = 0; i < n_local; i++) {
@@ -34,7 +34,10 @@ int FQD_CAT(run_sharded_group, FQD_GROUP)(int bits, int pw, fqd_context **ctxs, 
         S[i].index_base = index_base[i];
         S[i].st = stats[i];
     }
-#define X(K_, PW_) if (bits == K_ && pw == PW_) return run_sharded_typed<K_, PW_>(S, ex, world, codec, unknown_out);
+#define X(K_, PW_)                                                                                               \
+    if (bits == K_ && pw == PW_)                                                                                 \
+        return replicated_plan ? run_sharded_typed<K_, PW_>(S, ex, W.world, codec, unknown_out)                   \
+                               : run_sharded_tiles<K_, PW_>(S, ex, W, codec, unknown_out);
     FQD_GROUP_INSTANCES(X)
 #undef X
     return RC_NOT_IN_GROUP;
