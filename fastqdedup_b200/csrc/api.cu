@@ -789,7 +789,17 @@ int fqd_cluster_fetch(fqd_context *ctx, uint64_t *first, uint32_t *count, uint64
         FQD_CUDA(cudaMemcpyAsync(selected, ctx->res.selected, (size_t)U, cudaMemcpyDeviceToHost, s));
     }
     struct Scope { fqd_context *c; size_t m; ~Scope() { cudaStreamSynchronize(c->stream); arena_release(c, m); } } scope{ctx, arena_mark(ctx)};
-    if (label) {
+    if (label && ctx->res.id_mul > 1) {
+        // tile-sharded job: this rank holds its own uniques only; label = root of the cluster in the job-wide id space
+        DevBuf root;
+        FQD_TRY(root.alloc(ctx, (size_t)U * 4));
+        root_gid_kernel<<<(U + 255) / 256, 256, 0, s>>>(U, ctx->res.id_mul, ctx->res.id_add, ctx->res.parent_full, root.as<uint32_t>());
+        FQD_CUDA(cudaGetLastError());
+        std::vector<uint32_t> hroot(U);
+        FQD_CUDA(cudaMemcpyAsync(hroot.data(), root.p, (size_t)U * 4, cudaMemcpyDeviceToHost, s));
+        FQD_CUDA(cudaStreamSynchronize(s));
+        for (uint32_t i = 0; i < U; i++) label[i] = hroot[i];
+    } else if (label) {
         DevBuf minfirst, root;
         FQD_TRY(minfirst.alloc(ctx, (size_t)U * 4));
         FQD_TRY(root.alloc(ctx, (size_t)U * 4));

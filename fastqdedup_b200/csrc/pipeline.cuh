@@ -1139,6 +1139,15 @@ static __global__ void __launch_bounds__(256) label_min_kernel(const __grid_cons
     atomicMin(P.minfirst + r, P.ufirst[u]);
 }
 
+// tile-sharded job: root of every own unique in the job-wide id space (the per-unique view of such a job labels a
+// cluster by its root; the caller that holds all ranks' views turns roots into smallest-first labels)
+static __global__ void __launch_bounds__(256) root_gid_kernel(uint32_t U, uint32_t id_mul, uint32_t id_add, uint32_t *parent,
+                                                              uint32_t *root)
+{
+    const uint32_t u = blockIdx.x * 256u + threadIdx.x;
+    if (u < U) root[u] = uf_find(parent, u * id_mul + id_add);
+}
+
 // ---- sharding across GPUs (DESIGN.md "Multi-GPU") ----------------------------------------------
 //
 // Records are split contiguously over the ranks.  Each rank dedupes its shard, sends every

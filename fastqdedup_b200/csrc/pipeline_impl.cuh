@@ -8,6 +8,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <type_traits>
 #include <vector>
 
 #include "common.h"
@@ -810,7 +811,7 @@ int run_typed(fqd_context *ctx, const DeviceJob &job, const Codec &codec, fqd_cl
     FQD_TRY(stage_dedupe<K, PW>(ctx, job, codec, 0, false, st, unknown_out, uq, tt, &fp));
     const uint32_t U = uq.U;
     st->number_of_uniques = U;
-    if (U > ENT_UID) { set_error("too many unique keys for one GPU (%u)", U); return FQD_ERR_UNSUPPORTED; }
+    if (U > EDGE_ID) { set_error("too many unique keys for one GPU (%u)", U); return FQD_ERR_UNSUPPORTED; }   // ids share a word with the edge state
     FQD_CUDA(cudaEventRecord(ev[5], s));
     Forest f;
     FQD_TRY(stage_forest_alloc(ctx, job.method, U, f, &fp));
@@ -1326,6 +1327,8 @@ int run_sharded_typed(std::vector<Shard> &S, Exchange *ex, int world, const Code
     lap("select + stats");
     return FQD_OK;
 }
+
+#include "sharded_tiles.cuh"
 
 }  // namespace
 

@@ -20,6 +20,8 @@ import numpy as np
 
 from . import _native
 from ._native import METHODS, MEM_DEVICE, MEM_HOST, ClusterJob, ClusterStats
+
+PLAN_SHARD_TILES = 16   # include/fqd_b200.h FQD_PLAN_SHARD_TILES
 from .clustering import ClusterResult, _as_rows
 
 
@@ -122,7 +124,26 @@ def cluster_keys_sharded_local(keys, quals=None, max_distance=1, use_edit_distan
                             st.number_of_uniques, st.number_of_clusters, st.number_selected,
                             st.as_dict(), words)
         res.per_rank_stats = [stats[r].as_dict() for r in range(world)]
-        if want_uniques:
+        if want_uniques and st.plan_flags & PLAN_SHARD_TILES:
+            # tile-sharded plan: every rank returns its own keys; `label` is the cluster's root in the job-wide id
+            # space -> smallest `first` of the cluster
+            parts = [c.fetch(stats[r].own_uniques) for r, c in enumerate(contexts)]
+            first = np.concatenate([p[0] for p in parts])
+            count = np.concatenate([p[1] for p in parts])
+            roots = np.concatenate([p[2] for p in parts])
+            sel = np.concatenate([p[3] for p in parts])
+            assert len(first) == st.number_of_uniques
+            if len(first):
+                uroots, inv = np.unique(roots, return_inverse=True)
+                minfirst = np.full(len(uroots), np.iinfo(np.uint64).max, dtype=np.uint64)
+                np.minimum.at(minfirst, inv, first)
+                label = minfirst[inv]
+            else:
+                label = roots
+            order = np.argsort(first, kind="stable")
+            res.first, res.count = first[order], count[order]
+            res.label, res.selected = label[order], sel[order].astype(bool)
+        elif want_uniques:
             first, count, label, sel = contexts[0].fetch(st.number_of_uniques)
             for c in contexts[1:]:       # a rank decides only the keys whose first record is its own
                 sel |= c.fetch(st.number_of_uniques)[3]

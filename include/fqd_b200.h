@@ -131,12 +131,14 @@ typedef struct {
     uint32_t plan_flags;           /* FQD_PLAN_*: which launch plan the stages took */
     float ms_partition_kernel;     /* partitioned dedupe: filter + pack + partition pass */
     float ms_dedupe_kernel;        /* partitioned dedupe: the shared-memory tile kernel (dedupe + fused pass 0) */
+    uint64_t own_uniques;          /* tile-sharded job: unique keys this rank owns (what fqd_cluster_fetch returns) */
 } fqd_cluster_stats;
 
 #define FQD_PLAN_DEDUPE_PARTITIONED 1u /* exact dedupe: partition by hash, tables in shared-memory tiles */
 #define FQD_PLAN_PASSES_PARTITIONED 2u /* Hamming passes: partition by block hash, multimap in shared-memory tiles */
 #define FQD_PLAN_PASS0_FUSED 4u        /* pass 0 ran inside the dedupe tiles (records partitioned by block 0) */
 #define FQD_PLAN_PASS1_TILES_EMITTED 8u /* the dedupe tiles also filled the tiles of pass 1 */
+#define FQD_PLAN_SHARD_TILES 16u       /* sharded job: tiles owned by ranks, fragments fetched from peer memory */
 
 /* Runs the job.  On success the per-unique result stays in the context until the next
  * job.  keep_bitmap (optional, in the job's memory space, (n_records+31)/32 uint32 words,
@@ -149,7 +151,11 @@ int fqd_cluster(fqd_context *ctx, const fqd_cluster_job *job, fqd_cluster_stats 
  * may be NULL): first = index of the first record carrying the key (over all records,
  * filtered or not); count = kept records with that key; label = `first` of the
  * smallest-first member of the unique's cluster; selected = 1 when dissection kept it.
- * Order is unspecified (sort by `first` for a canonical view). */
+ * Order is unspecified (sort by `first` for a canonical view).
+ * After a tile-sharded job (plan_flags & FQD_PLAN_SHARD_TILES) every rank returns ITS OWN
+ * stats.own_uniques keys and `label` is the cluster's root in the job-wide id space -- equal for all
+ * members of a cluster on all ranks; the caller holding every rank's view maps it to the smallest
+ * `first` (fastqdedup_b200/multigpu.py does). */
 int fqd_cluster_fetch(fqd_context *ctx, uint64_t *first, uint32_t *count, uint64_t *label,
                       uint8_t *selected);
 
@@ -159,13 +165,19 @@ int fqd_cluster_fetch_selected(fqd_context *ctx, uint64_t *indices);
 
 /* ------------------------------------------------------------------------------------
  * The same job sharded over the GPUs of one box (BASELINE.json config 5).  Records are split
- * contiguously over `world` ranks; rank r passes its own records and the global index of its
- * first record.  Exchange steps (NCCL over NVLink): all-to-all of the locally deduplicated
- * keys to their owner rank, all-gather of the merged unique set, all-gather of the
- * spanning-forest pairs / flags found by each rank.  Every rank ends with the keep bitmap of
- * ITS OWN records and the per-unique view of the whole job (fqd_cluster_fetch: first, count,
- * label for every key; `selected` only for the keys whose first record is the rank's own --
- * the union over ranks is the complete set).
+ * contiguously over `world` ranks (in rank order); rank r passes its own records and the global
+ * index of its first record.  Every rank ends with the keep bitmap of ITS OWN records.
+ *
+ * Two plans.  Tile-sharded (Hamming, keys up to 6 packed words, <= 16 ranks):
+ * the shared-memory tiles of the streaming plan get an owner rank each; every rank partitions its
+ * records locally and the owners' tile kernels fetch the fragments of a tile straight from the
+ * peers' HBM over NVLink (peer memory; CUDA IPC between processes), edges are read from all ranks'
+ * lists by the union-find that consumes them; NCCL only carries counters.  Replicated-set (every
+ * other job, and the fallback for skew the tiles cannot hold): all-to-all of the locally
+ * deduplicated keys to an owner rank, all-gather of the merged unique set, all-gather of
+ * spanning-forest pairs / flags.  fqd_cluster_fetch after the replicated-set plan: first, count,
+ * label for every key on every rank, `selected` only for the keys whose first record is the rank's
+ * own (the union over ranks is the complete set).
  * ------------------------------------------------------------------------------------ */
 typedef struct fqd_comm fqd_comm;
 /* rank 0 creates the id and hands the 128 bytes to the other ranks by any means */
