@@ -193,6 +193,16 @@ def algorithmic_bytes(cfg, n, n_ok, u, passes, filter_on):
     return total, ingest
 
 
+def bitmap_digest(parts):
+    """sha256 of the keep bitmap of the whole job in global record order; `parts` = [(uint32 words, records)]
+    per rank (bit t%32 of word t/32 over the rank's LOCAL record index).  The same reads give the same digest
+    whatever the GPU count: compare the lines of a scaling run."""
+    import hashlib
+    bits = [np.unpackbits(np.ascontiguousarray(w).view(np.uint8), bitorder="little")[:n] for w, n in parts]
+    packed = np.packbits(np.concatenate(bits) if len(bits) > 1 else bits[0], bitorder="little")
+    return hashlib.sha256(packed.tobytes()).hexdigest()[:32]
+
+
 def measured_peak():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -425,6 +435,7 @@ def run_ours(args, rank, world, local_rank):
     dev_bitmap = ctx.download(d_bitmap, bitmap_words * 4, np.uint32)
     assert np.array_equal(dev_bitmap, host_bitmap.array.view(np.uint32)), "e2e and device-resident results differ"
     assert est.number_selected == st.number_selected
+    digest = bitmap_digest([(dev_bitmap, n)])
 
     # ---- roofline of the dominant kernel ----
     # Every term of SURVEY.md section 8(d)'s B_total is charged to the kernel (group) that does that
@@ -528,6 +539,7 @@ def run_ours(args, rank, world, local_rank):
         "config": workload_config(cfg, 1),
         "unique_keys": int(U), "clusters": int(st.number_of_clusters),
         "selected": int(st.number_selected), "candidate_pairs": int(st.candidate_pairs),
+        "keep_bitmap_sha256_32": digest,
         "wall_ms_per_step": 1e3 * wall / args.steps,
         "e2e": {"value": U / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * e2e_s,
@@ -622,6 +634,8 @@ def run_ours_sharded(args, cfg, rank, world, local_rank, dist):
     e2e_s = max_over_ranks((time.perf_counter() - e0) / e2e_steps)
     dev_bitmap = ctx.download(d_bitmap, max(words, 1) * 4, np.uint32)
     assert np.array_equal(dev_bitmap[:words], host_bitmap.array.view(np.uint32)[:words])
+    gathered = [None] * world if rank == 0 else None
+    dist.gather_object((dev_bitmap[:words].copy(), nloc), gathered, dst=0)
     launches = int(sum(s.launches for s in stats))
     lt = torch.tensor([launches], dtype=torch.int64, device=f"cuda:{local_rank}")
     dist.all_reduce(lt)
@@ -636,6 +650,8 @@ def run_ours_sharded(args, cfg, rank, world, local_rank, dist):
             "data": "synthetic", "config": workload_config(cfg, world),
             "unique_keys": int(U), "clusters": int(st.number_of_clusters),
             "selected": int(st.number_selected), "candidate_pairs": int(st.candidate_pairs),
+            "keep_bitmap_sha256_32": bitmap_digest(gathered),
+            "plan": "tile-sharded (peer-memory tile fetch)" if st.plan_flags & 16 else "replicated unique set",
             "wall_ms_per_step": 1e3 * wall / args.steps,
             "e2e": {"value": U / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(n * L * (2 if host_quals is not None else 1)),
                     "d2h_bytes_per_step": int(((n + 31) // 32) * 4), "ms_per_step": 1e3 * e2e_s, "steps": e2e_steps},

@@ -69,6 +69,8 @@ struct TileSource {
     uint32_t G, self;
     uint32_t first_tile;              // global index of owned tile 0
     uint32_t ntiles;                  // owned tiles
+    uint32_t region;                  // records per region of every rank's buffer (PartParams::region)
+    int peer_ldg;                     // measurement switch: fetch peer fragments with 16-byte loads instead of bulk copies
 };
 
 __device__ __forceinline__ void tile_load_rec(const uint32_t *recs, uint32_t i, uint32_t (&e)[PART_RW])
@@ -120,11 +122,12 @@ __device__ __forceinline__ uint32_t stage_tile(uint32_t *recs, uint32_t *tab, ui
 {
     __shared__ __align__(8) uint64_t mbar;
     const uint32_t tid = threadIdx.x;
-    uint32_t total = 0, mine = 0, before = 0;
+    uint32_t total = 0, mine = 0, before = 0, local = 0;
     bool over = false;
     for (uint32_t g = 0; g < S.G; g++) {
         const uint32_t c = S.cnt[(size_t)g * S.ntiles + j];
-        over |= c > (uint32_t)TILE_R;       // the rank's own region overflowed (the surplus is in its spill buffer)
+        if (g == S.self) local = c;
+        over |= c > S.region;               // the rank's own region overflowed (the surplus is in its spill buffer)
         if (g < tid) before += c;
         if (g == tid) mine = c;
         total += c;
@@ -137,10 +140,11 @@ __device__ __forceinline__ uint32_t stage_tile(uint32_t *recs, uint32_t *tab, ui
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    if (tid == 0)
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar_a), "r"(total * (PART_RW * 4u)) : "memory");
-    if (tid < S.G && mine) {
-        const uint32_t *src = S.buf[tid] + (size_t)(S.first_tile + j) * TILE_R * PART_RW;
+    const uint32_t bulk_bytes = (S.peer_ldg ? local : total) * (PART_RW * 4u);
+    if (tid == 0 && bulk_bytes)
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar_a), "r"(bulk_bytes) : "memory");
+    if (tid < S.G && mine && !(S.peer_ldg && tid != S.self)) {
+        const uint32_t *src = S.buf[tid] + (size_t)(S.first_tile + j) * S.region * PART_RW;
         const uint32_t dst = (uint32_t)__cvta_generic_to_shared(recs + (size_t)before * PART_RW);
         if (tid == S.self) {   // local HBM: read exactly once, evict-first in the L2
             uint64_t policy;
@@ -153,11 +157,35 @@ __device__ __forceinline__ uint32_t stage_tile(uint32_t *recs, uint32_t *tab, ui
         }
     }
     for (uint32_t i = tid; i < tab_n; i += TILE_THREADS) tab[i] = TILE_EMPTY;
-    uint32_t done;
-    do {
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(done) : "r"(mbar_a), "r"(0) : "memory");
-    } while (!done);
+    if (S.peer_ldg) {
+        // the peers' fragments by plain 16-byte loads, four in flight per thread
+        uint32_t off = 0;
+        for (uint32_t g = 0; g < S.G; g++) {
+            const uint32_t c = S.cnt[(size_t)g * S.ntiles + j];
+            if (g != S.self && c) {
+                const uint4 *src = reinterpret_cast<const uint4 *>(S.buf[g] + (size_t)(S.first_tile + j) * S.region * PART_RW);
+                uint4 *dst = reinterpret_cast<uint4 *>(recs + (size_t)off * PART_RW);
+                const uint32_t n16 = c * (PART_RW / 4);
+                for (uint32_t i = tid; i < n16; i += 4 * TILE_THREADS) {
+                    uint4 v[4];
+#pragma unroll
+                    for (int u = 0; u < 4; u++)
+                        if (i + u * TILE_THREADS < n16) v[u] = __ldcs(src + i + u * TILE_THREADS);
+#pragma unroll
+                    for (int u = 0; u < 4; u++)
+                        if (i + u * TILE_THREADS < n16) dst[i + u * TILE_THREADS] = v[u];
+                }
+            }
+            off += c;
+        }
+    }
+    if (bulk_bytes) {
+        uint32_t done;
+        do {
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                         : "=r"(done) : "r"(mbar_a), "r"(0) : "memory");
+        } while (!done);
+    }
     __syncthreads();
     return total;
 }
@@ -574,7 +602,7 @@ static __global__ void __launch_bounds__(256) bucket_partition_kernel(const __gr
     }
 #pragma unroll
     for (int r = 0; r < BP_ROWS; r++)
-        if (go[r] && pos[r] < (uint32_t)TILE_R) store_rec_stream(Q.buf + ((size_t)part[r] * TILE_R + pos[r]) * PART_RW, e[r]);
+        if (go[r] && pos[r] < Q.region) store_rec_stream(Q.buf + ((size_t)part[r] * Q.region + pos[r]) * PART_RW, e[r]);
 }
 
 template <int K, int PW>
@@ -865,11 +893,11 @@ static __global__ void __launch_bounds__(256) spill_insert_tiles_kernel(const __
     constexpr uint32_t BPP = TILE_R / 256;
     const uint32_t j = list[blockIdx.x / (S.G * BPP)], g = (blockIdx.x / BPP) % S.G;
     const uint32_t i = (blockIdx.x % BPP) * 256u + threadIdx.x;
-    const uint32_t n = min(S.cnt[(size_t)g * S.ntiles + j], (uint32_t)TILE_R);
+    const uint32_t n = min(S.cnt[(size_t)g * S.ntiles + j], S.region);
     uint32_t claimed = NO_CLAIM;
     if (i < n) {
         uint32_t e[PART_RW];
-        load_rec_stream(S.buf[g] + ((size_t)(S.first_tile + j) * TILE_R + i) * PART_RW, e);
+        load_rec_stream(S.buf[g] + ((size_t)(S.first_tile + j) * S.region + i) * PART_RW, e);
         Key<K, PW> key;
 #pragma unroll
         for (int w = 0; w < KW; w++) key.w[w] = e[w];

@@ -182,6 +182,10 @@ struct PartParams {
     uint32_t *spill;       // records that did not fit their region (oversize partitions only)
     uint32_t *spill_cnt;   // [0] records appended to spill, [1] set when spill itself overflowed
     uint32_t spill_cap;
+    // records per region.  One GPU: TILE_R (a region is a whole tile).  Sharded over G ranks a rank's region only
+    // ever receives ~1/G of a tile, so it is sized for that (dense buffers: 1/G of the footprint, and the owner's
+    // peer fetch reads a contiguous run instead of the head of a mostly empty 16 KB region)
+    uint32_t region = TILE_R;
 };
 
 __device__ __forceinline__ uint32_t part_of(uint64_t h, uint32_t nparts)
@@ -212,8 +216,8 @@ __device__ __forceinline__ void part_append(const PartParams &Q, uint32_t part, 
 // the store half: `pos` is what the cursor atomic returned
 __device__ __forceinline__ void part_place(const PartParams &Q, uint32_t part, uint32_t pos, const uint32_t (&e)[PART_RW])
 {
-    if (pos < (uint32_t)TILE_R) {
-        store_rec_stream(Q.buf + ((size_t)part * TILE_R + pos) * PART_RW, e);
+    if (pos < Q.region) {
+        store_rec_stream(Q.buf + ((size_t)part * Q.region + pos) * PART_RW, e);
     } else if (Q.spill) {   // (without a spill buffer the tile kernel sees cursor > TILE_R and flags the overflow)
         const uint32_t sp = atomicAdd(Q.spill_cnt, 1u);
         if (sp < Q.spill_cap) store_rec_stream(Q.spill + (size_t)sp * PART_RW, e);

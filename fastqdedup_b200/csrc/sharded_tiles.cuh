@@ -58,16 +58,40 @@ int run_sharded_tiles(std::vector<Shard> &S, Exchange *ex, const ShardWorld &W, 
     const DeviceJob &j0 = S[0].job;
     const int d = j0.d, method = j0.method;
     const uint64_t N = W.n_total;
-    const bool trace = getenv("FQD_TRACE") && rank_of(0) == 0;
-    auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
-    double t_prev = now();
+    // FQD_TRACE=1: device time per phase of this process' first rank (CUDA events on its stream, no extra
+    // synchronisation; printed by rank 0, by every rank with FQD_TRACE=2)
+    const char *trace_env = getenv("FQD_TRACE");
+    const bool trace = trace_env && (rank_of(0) == 0 || atoi(trace_env) >= 2);
+    std::vector<std::pair<const char *, cudaEvent_t>> marks_ev;
     auto lap = [&](const char *what) {
         if (!trace) return;
-        for (auto &sh : S) { cudaSetDevice(sh.ctx->device); cudaStreamSynchronize(sh.ctx->stream); }
-        const double t = now();
-        fprintf(stderr, "[fqd trace] tiles: %-26s %8.3f ms\n", what, t - t_prev);
-        t_prev = t;
+        cudaEvent_t e;
+        cudaSetDevice(S[0].ctx->device);
+        if (cudaEventCreate(&e) != cudaSuccess) return;
+        cudaEventRecord(e, S[0].ctx->stream);
+        marks_ev.emplace_back(what, e);
     };
+    auto lap_report = [&]() {
+        if (marks_ev.empty()) return;
+        cudaSetDevice(S[0].ctx->device);
+        cudaStreamSynchronize(S[0].ctx->stream);
+        std::string line = "[fqd trace] rank " + std::to_string(rank_of(0)) + " tiles (device ms):";
+        float total = 0.f;
+        for (size_t k = 1; k < marks_ev.size(); k++) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, marks_ev[k - 1].second, marks_ev[k].second);
+            total += ms;
+            char buf[96];
+            snprintf(buf, sizeof buf, " %s %.3f |", marks_ev[k].first, ms);
+            line += buf;
+        }
+        char buf[48];
+        snprintf(buf, sizeof buf, " total %.3f", total);
+        fprintf(stderr, "%s%s\n", line.c_str(), buf);
+        for (auto &m : marks_ev) cudaEventDestroy(m.second);
+        marks_ev.clear();
+    };
+    lap("start");
     std::vector<TileRank> T(L);
     struct Cleanup {
         std::vector<TileRank> &T;
@@ -80,6 +104,12 @@ int run_sharded_tiles(std::vector<Shard> &S, Exchange *ex, const ShardWorld &W, 
     const uint64_t guessU = std::max<uint64_t>(N / 2, 1u << 16);
     const bool emit_next = fused && !getenv("FQD_NO_NEXT_EMIT");
     const uint32_t nperN = cdiv(tile_partitions(guessU), (uint32_t)G), npartsN = nperN * (uint32_t)G;
+    // a rank's region of a tile receives ~1/G of it: sized for that plus Poisson slack (surplus -> spill path)
+    const uint32_t fill_pct = std::min(90u, std::max(20u, env_u32("FQD_TILE_FILL_PCT", 60)));
+    const uint32_t avg_frag = (uint32_t)TILE_R * fill_pct / (100u * (uint32_t)G);
+    const uint32_t region = getenv("FQD_SHARD_FULL_REGIONS") ? (uint32_t)TILE_R
+                                                             : std::min<uint32_t>(TILE_R, ((avg_frag * 3 / 2 + 48 + 31) / 32) * 32);
+    const int peer_ldg = getenv("FQD_PEER_LDG") ? 1 : 0;
     const uint32_t spill_cap = (uint32_t)(W.n_max / 4 + 4096);
     const uint32_t cap_u = (uint32_t)std::min<uint64_t>((EDGE_ID + 1ull) / (uint64_t)G - 1, N / G + N / (4ull * G) + (1u << 16));
     const uint32_t cap_e = (uint32_t)std::min<uint64_t>(EDGE_ID, W.n_max + (1u << 16));
@@ -164,9 +194,9 @@ int run_sharded_tiles(std::vector<Shard> &S, Exchange *ex, const ShardWorld &W, 
                 inside = inside && in_slab(sh, *p, std::max<size_t>(count * sizeof(Elem), 16));
                 return FQD_OK;
             };
-            FQD_TRY(shared(&t.tiles0, (size_t)nparts0 * TILE_R * RW));
+            FQD_TRY(shared(&t.tiles0, (size_t)nparts0 * region * RW));
             FQD_TRY(shared(&t.spill, (size_t)spill_cap * RW));
-            if (emit_next) FQD_TRY(shared(&t.tilesN, (size_t)npartsN * TILE_R * RW));
+            if (emit_next) FQD_TRY(shared(&t.tilesN, (size_t)npartsN * region * RW));
             FQD_TRY(shared(&t.edges, (size_t)cap_e));
             if (cap_adj) FQD_TRY(shared(&t.adj, (size_t)cap_adj));
             FQD_TRY(shared(&t.cand, (size_t)cap_c * RW));
@@ -221,17 +251,18 @@ int run_sharded_tiles(std::vector<Shard> &S, Exchange *ex, const ShardWorld &W, 
             ip.sharded = 0;      // (a filtered record travels with weight 0 in partition mode anyway)
             ip.ctr = sh.ctx->d_ctr;
             ip.codec = codec;
-            const PartParams part{t.tiles0, t.cursor0, nparts0, t.spill, t.ctrs + CTR_SPILL, spill_cap};
+            const PartParams part{t.tiles0, t.cursor0, nparts0, t.spill, t.ctrs + CTR_SPILL, spill_cap, region};
             if (job.n) FQD_TRY((launch_partition<K, PW>(sh.ctx, job, codec, ip, part, fused ? (uint32_t)d + 1u : 0u, sh.index_base, sh.tt)));
             return FQD_OK;
         }();
     }
-    lap("partition (local)");
+    lap("partition");
 
     // =====================================================================================================
     // phase 3: fill counters to the tile owners; phase 4: dedupe (+ pass 0, + tiles of pass 1) on the owners
     // =====================================================================================================
     FQD_TRY(alltoall_u32([&](int i) { return T[i].cursor0; }, [&](int i) { return T[i].cnt0; }, nper0));
+    lap("counters a2a");
     for (int i = 0; i < L; i++) {
         Shard &sh = S[i];
         TileRank &t = T[i];
@@ -243,6 +274,7 @@ int run_sharded_tiles(std::vector<Shard> &S, Exchange *ex, const ShardWorld &W, 
             TileSource src{};
             for (int g = 0; g < G; g++) src.buf[g] = reinterpret_cast<const uint32_t *>(peer_ptr(sh, g, t.tiles0));
             src.cnt = t.cnt0; src.G = (uint32_t)G; src.self = (uint32_t)r; src.first_tile = (uint32_t)r * nper0; src.ntiles = nper0;
+            src.region = region; src.peer_ldg = peer_ldg;
             DedupeOut out{sh.local.ukey, sh.local.ucount, sh.local.ufirst, t.ctrs + CTR_UNIQUE, t.oversize, t.ctrs + CTR_OVERSIZE, 0,
                           cap_u, t.ctrs + CTR_UNIQUE_OVER};
             PassParams p0{};
@@ -258,7 +290,7 @@ int run_sharded_tiles(std::vector<Shard> &S, Exchange *ex, const ShardWorld &W, 
                 sink0 = EdgeSink{t.edges, t.ctrs + CTR_EDGES, cap_e, t.ctrs + CTR_EDGE_OVER};
                 NextPass nx{};
                 if (emit_next) {
-                    nx.next = PartParams{t.tilesN, t.cursorN, npartsN, nullptr, nullptr, 0};
+                    nx.next = PartParams{t.tilesN, t.cursorN, npartsN, nullptr, nullptr, 0, region};
                     nx.pass_j = 1;
                     nx.st = block_start(sh.job.max_len, 1u, (uint32_t)d + 1u);
                     nx.bl = block_start(sh.job.max_len, 2u, (uint32_t)d + 1u) - nx.st;
@@ -269,12 +301,12 @@ int run_sharded_tiles(std::vector<Shard> &S, Exchange *ex, const ShardWorld &W, 
             }
             sh.tt.launches++;
             FQD_CUDA(cudaGetLastError());
+            if (i == 0) lap("dedupe tiles");
             FQD_CUDA(cudaMemcpyAsync(t.h_ctrs, t.ctrs, sizeof t.h_ctrs, cudaMemcpyDeviceToHost, s));
             FQD_TRY(fetch_counters(sh.ctx));
             return FQD_OK;
         }();
     }
-    lap("dedupe tiles (peer fetch)");
 
     // ---- agreement 1: status, input errors, unique counts, skew ----
     constexpr int A1 = 24;
@@ -348,6 +380,7 @@ int run_sharded_tiles(std::vector<Shard> &S, Exchange *ex, const ShardWorld &W, 
                 TileSource src{};
                 for (int g = 0; g < G; g++) src.buf[g] = reinterpret_cast<const uint32_t *>(peer_ptr(sh, g, t.tiles0));
                 src.cnt = t.cnt0; src.G = (uint32_t)G; src.self = (uint32_t)r; src.first_tile = (uint32_t)r * nper0; src.ntiles = nper0;
+            src.region = region; src.peer_ldg = peer_ldg;
                 if (n_over)
                     spill_insert_tiles_kernel<K, PW><<<n_over * (uint32_t)G * (TILE_R / 256), 256, 0, s>>>(src, t.oversize, tr, t.ctrs + CTR_CLAIMED);
                 for (int g = 0; g < G; g++)
@@ -399,7 +432,7 @@ int run_sharded_tiles(std::vector<Shard> &S, Exchange *ex, const ShardWorld &W, 
                         sp.pass_j = 1;
                         sp.fix_st = block_start(sh.job.max_len, 1u, (uint32_t)d + 1u);
                         sp.fix_bl = block_start(sh.job.max_len, 2u, (uint32_t)d + 1u) - sp.fix_st;
-                        const PartParams qn{t.tilesN, t.cursorN, npartsN, nullptr, nullptr, 0};
+                        const PartParams qn{t.tilesN, t.cursorN, npartsN, nullptr, nullptr, 0, region};
                         bucket_partition_kernel<K, PW><<<cdiv(ns, 256 * BP_ROWS), 256, 0, s>>>(sp, qn);
                         sh.tt.launches++;
                     }
@@ -409,7 +442,7 @@ int run_sharded_tiles(std::vector<Shard> &S, Exchange *ex, const ShardWorld &W, 
             }();
         }
         for (int i = 0; i < L; i++) arena_release(S[i].ctx, marks[i]);
-        lap("oversize tiles");
+        lap("agree + oversize tiles");
     }
 
     // ---- agreement 2: final unique counts ----
@@ -454,8 +487,8 @@ int run_sharded_tiles(std::vector<Shard> &S, Exchange *ex, const ShardWorld &W, 
             bool inside = true;
             if (need_pass_buffers) {
                 for (int b = 0; b < 2; b++) {
-                    FQD_TRY(arena(sh.ctx, (size_t)npartsP * TILE_R * RW, &t.tilesP[b]));
-                    inside = inside && in_slab(sh, t.tilesP[b], (size_t)npartsP * TILE_R * RW * 4);
+                    FQD_TRY(arena(sh.ctx, (size_t)npartsP * region * RW, &t.tilesP[b]));
+                    inside = inside && in_slab(sh, t.tilesP[b], (size_t)npartsP * region * RW * 4);
                 }
                 FQD_TRY(arena(sh.ctx, (size_t)npartsP, &t.cursorP));
                 FQD_TRY(arena(sh.ctx, (size_t)npartsP, &t.cntP));
@@ -517,7 +550,7 @@ int run_sharded_tiles(std::vector<Shard> &S, Exchange *ex, const ShardWorld &W, 
                     FQD_CUDA(cudaSetDevice(S[i].ctx->device));
                     cudaStream_t s = S[i].ctx->stream;
                     FQD_CUDA(cudaMemsetAsync(T[i].cursorP, 0, (size_t)npartsP * 4, s));
-                    const PartParams qp{T[i].tilesP[j & 1], T[i].cursorP, npartsP, nullptr, nullptr, 0};
+                    const PartParams qp{T[i].tilesP[j & 1], T[i].cursorP, npartsP, nullptr, nullptr, 0, region};
                     if (T[i].U) bucket_partition_kernel<K, PW><<<cdiv(T[i].U, 256 * BP_ROWS), 256, 0, s>>>(pass_params(i), qp);
                     S[i].tt.launches++;
                     FQD_CUDA(cudaGetLastError());
@@ -539,6 +572,7 @@ int run_sharded_tiles(std::vector<Shard> &S, Exchange *ex, const ShardWorld &W, 
                 for (int g = 0; g < G; g++) src.buf[g] = reinterpret_cast<const uint32_t *>(peer_ptr(sh, g, mine));
                 src.cnt = emitted ? t.cntN : t.cntP;
                 src.G = (uint32_t)G; src.self = (uint32_t)r; src.first_tile = (uint32_t)r * nper; src.ntiles = nper;
+                src.region = region; src.peer_ldg = peer_ldg;
                 const EdgeSink sink{t.edges, t.ctrs + CTR_EDGES, cap_e, t.ctrs + CTR_EDGE_OVER};
                 bucket_tile_kernel<K, PW><<<nper, TILE_THREADS, 0, sh.ctx->stream>>>(src, pass_params(i), sink);
                 sh.tt.launches++;
@@ -548,7 +582,7 @@ int run_sharded_tiles(std::vector<Shard> &S, Exchange *ex, const ShardWorld &W, 
         }
         (void)nparts;
     }
-    lap("passes (peer fetch)");
+    lap("forest init + passes");
 
     // =====================================================================================================
     // phase 8: all edges of all ranks into every rank's forests (edge lists read from the peers' HBM)
@@ -565,6 +599,7 @@ int run_sharded_tiles(std::vector<Shard> &S, Exchange *ex, const ShardWorld &W, 
         return allgather_u32([&](int i) { return T[i].gath_in; }, [&](int i) { return T[i].gath + (size_t)slot * 4 * G; }, 4);
     };
     FQD_TRY(gather4(0));
+    lap("edge counts ag");
     for (int i = 0; i < L; i++) {
         if (T[i].rc != FQD_OK) continue;
         T[i].rc = [&]() -> int {
@@ -582,7 +617,7 @@ int run_sharded_tiles(std::vector<Shard> &S, Exchange *ex, const ShardWorld &W, 
             return FQD_OK;
         }();
     }
-    lap("apply edges (peer fetch)");
+    lap("apply edges");
 
     // =====================================================================================================
     // phase 9: what a component's answer needs from several members
@@ -752,7 +787,8 @@ int run_sharded_tiles(std::vector<Shard> &S, Exchange *ex, const ShardWorld &W, 
         if (trace) fprintf(stderr, "[fqd trace] tiles: a pass tile / the edge or candidate list overflowed -> replicated-set plan\n");
         return RC_FALLBACK_REPLICATED;
     }
-    lap("select + totals");
+    lap("select + agree");
+    lap_report();
     for (int i = 0; i < L; i++) {
         Shard &sh = S[i];
         TileRank &t = T[i];
