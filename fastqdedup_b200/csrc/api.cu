@@ -789,7 +789,7 @@ int fqd_cluster_fetch(fqd_context *ctx, uint64_t *first, uint32_t *count, uint64
         FQD_CUDA(cudaMemcpyAsync(selected, ctx->res.selected, (size_t)U, cudaMemcpyDeviceToHost, s));
     }
     struct Scope { fqd_context *c; size_t m; ~Scope() { cudaStreamSynchronize(c->stream); arena_release(c, m); } } scope{ctx, arena_mark(ctx)};
-    if (label && ctx->res.id_mul > 1) {
+    if (label && ctx->res.roots_only) {
         // tile-sharded job: this rank holds its own uniques only; label = root of the cluster in the job-wide id space
         DevBuf root;
         FQD_TRY(root.alloc(ctx, (size_t)U * 4));

@@ -41,9 +41,10 @@ struct fqd_result {
     uint32_t *ucount = nullptr;
     uint32_t *parent_full = nullptr;
     uint8_t *selected = nullptr;
-    // tile-sharded job: the rank's OWN uniques; unique u has the job-wide id u * id_mul + id_add (the forests are
-    // indexed by it)
+    // tile-sharded job: the rank's OWN uniques; unique u sits at slot id_add + u * id_mul of the (job-wide) forests,
+    // and the per-unique view labels clusters by their root slot
     uint32_t id_mul = 1, id_add = 0;
+    bool roots_only = false;
 };
 
 // Job-lifetime device memory: one slab, bump allocation, reset at the start of every job.

@@ -575,7 +575,7 @@ static __global__ void __launch_bounds__(256) bucket_partition_kernel(const __gr
 #pragma unroll
     for (int r = 0; r < BP_ROWS; r++) {
         const uint64_t u = (uint64_t)P.u_lo + ((uint64_t)blockIdx.x * BP_ROWS + r) * 256u + threadIdx.x;
-        go[r] = u < P.U;
+        go[r] = u < (P.U_dev ? min(P.U, *P.U_dev) : P.U);
         if (!go[r]) continue;
         Key<K, PW> key;
         load_key_stream<K, PW>(P.ukey, (uint32_t)u, key);
@@ -675,7 +675,18 @@ struct EdgeSource {
     const uint32_t *n_edges;    // [G * n_stride] edge counters of all ranks (gathered; a local copy)
     uint32_t n_stride;          // counter of rank g: n_edges[g * n_stride]
     uint32_t G, self;
+    uint32_t id_stride;         // slot of id (u * G + rank): rank * id_stride + u, see slot_of_id
 };
+
+// Ids travel as (local id * G + rank): a tile kernel can number its uniques without knowing how many the other
+// ranks have.  The forests and flag arrays are indexed rank-major instead (slot = rank * stride + local id, the
+// stride agreed once the unique counts are known): the edges of one rank's tiles then touch one contiguous
+// block, as they do on one GPU -- interleaved slots would drag every 32-byte sector of the arrays through the
+// caches once per rank.
+__device__ __forceinline__ uint32_t slot_of_id(uint32_t id, uint32_t G, uint32_t stride)
+{
+    return G == 1 ? id : (id % G) * stride + id / G;
+}
 
 // Per-key state of the dissection that edges set (all byte arrays over the job-wide id space; null = not needed).
 struct EdgeFlags {
@@ -698,7 +709,9 @@ static __global__ void __launch_bounds__(256) apply_edges_kernel(const __grid_co
         const uint2 *edges = E.edges[g];
         for (uint32_t i = blockIdx.x * 256u + threadIdx.x; i < n; i += gridDim.x * 256u) {
             const uint2 ed = __ldcs(edges + i);
-            const uint32_t x = ed.x, y = ed.y & EDGE_ID, st = ed.y & EDGE_STATE;
+            const uint32_t st = ed.y & EDGE_STATE;
+            const bool x_mine = ed.x % E.G == E.self, y_mine = (ed.y & EDGE_ID) % E.G == E.self;
+            const uint32_t x = slot_of_id(ed.x, E.G, E.id_stride), y = slot_of_id(ed.y & EDGE_ID, E.G, E.id_stride);
             if (uf_union(parent_full, x, y)) merges++;
             if (st == EDGE_ONE) {
                 if (parent_one) uf_union(parent_one, x, y);
@@ -708,9 +721,9 @@ static __global__ void __launch_bounds__(256) apply_edges_kernel(const __grid_co
             } else if (st == EDGE_DEAD_Y) {
                 F.dead[y] = 1;
             } else if (st == EDGE_DOM_X) {
-                if (x % E.G == E.self) F.dominated[x] = 1;
+                if (x_mine) F.dominated[x] = 1;
             } else if (st == EDGE_DOM_Y) {
-                if (y % E.G == E.self) F.dominated[y] = 1;
+                if (y_mine) F.dominated[y] = 1;
             }
             if (F.any_edge) { F.linked[x] = 1; F.linked[y] = 1; }
         }
@@ -738,9 +751,45 @@ static __global__ void __launch_bounds__(256) deadroot_kernel(uint32_t n_ids, co
     deadroot[uf_find(parent_one, g)] = 1;
 }
 
+// One status block per rank and agreement point, packed on the device (no host round trip before the exchange):
+// the plan's counters and the job counters the ranks have to agree on or add up.
+constexpr int STATUS_WORDS = 24;   // uint64 each
+struct StatusParams {
+    long long rc;
+    const uint32_t *ctrs;          // the plan's counters (sharded_tiles.cuh CTR_*)
+    const DevCounters *ctr;
+    uint32_t cap_u, spill_cap, cap_e, cap_c;
+    unsigned long long *out;
+};
+static __global__ void pack_status_kernel(const __grid_constant__ StatusParams P)
+{
+    if (threadIdx.x != 0) return;
+    const uint32_t *c = P.ctrs;
+    const DevCounters &d = *P.ctr;
+    unsigned long long *o = P.out;
+    o[0] = (unsigned long long)P.rc;
+    o[1] = min(c[2], P.cap_u);
+    o[2] = c[3];
+    o[3] = min(c[0], P.spill_cap);
+    o[4] = (c[1] | c[7] | c[6] | (c[5] > P.cap_e) | (c[8] > P.cap_c)) ? 1ull : 0ull;
+    o[5] = d.phred_err;
+    o[6] = d.n_discarded;
+    o[7] = d.sum_weights;
+    for (int k = 0; k < 8; k++) o[8 + k] = d.unknown[k];
+    unsigned long long cand = d.n_candidates, merges = d.n_merges;
+    for (uint32_t k = 0; k < STAT_SPREAD; k++) { cand += d.cand_spread[k]; merges += d.merge_spread[k]; }
+    o[16] = d.n_selected;
+    o[17] = cand;
+    o[18] = merges;
+    o[19] = d.n_edges;
+    o[20] = d.table_full;
+    for (int k = 21; k < STATUS_WORDS; k++) o[k] = 0;
+}
+
 struct CandParams {
-    uint32_t U;               // this rank's uniques
-    uint32_t G, self;
+    uint32_t U;               // this rank's uniques (an upper bound when U_dev is set)
+    const uint32_t *U_dev;    // the count on the device (the spill path may still be adding to it when the launch is sized)
+    uint32_t G, self, id_stride;
     const uint32_t *ukey, *ucount;
     uint32_t *forest;         // parent_one (directional) / parent_full (highest_count)
     const uint8_t *dead, *linked, *deadroot;
@@ -759,10 +808,11 @@ static __global__ void __launch_bounds__(256) candidates_kernel(const __grid_con
     constexpr int KW = K * PW;
     static_assert(slot_words(KW) == PART_RW, "candidate records are 32 bytes");
     const uint32_t u = blockIdx.x * 256u + threadIdx.x;
+    const uint32_t U = P.U_dev ? min(P.U, *P.U_dev) : P.U;
     bool emit = false;
     uint32_t root = 0, gid = 0, c = 0;
-    if (u < P.U) {
-        gid = u * P.G + P.self;
+    if (u < U) {
+        gid = P.self * P.id_stride + u;   // slot of the key in the forests / flag arrays
         c = P.ucount[u];
         root = gid;
         if (P.method == METHOD_DIRECTIONAL) {
@@ -777,7 +827,7 @@ static __global__ void __launch_bounds__(256) candidates_kernel(const __grid_con
         P.root_of[u] = root;
     }
     const uint32_t pos = block_reserve(emit, P.n_cand);
-    if (u < P.U) P.loc_of[u] = (emit && pos < P.cap) ? ((P.self << 28) | pos) : NO_CLAIM;
+    if (u < U) P.loc_of[u] = (emit && pos < P.cap) ? ((P.self << 28) | pos) : NO_CLAIM;
     if (emit && pos < P.cap) {
         uint32_t e[PART_RW];
 #pragma unroll
@@ -840,7 +890,8 @@ static __global__ void __launch_bounds__(256) best_candidate_kernel(const __grid
 }
 
 struct SelectOwnParams {
-    uint32_t U, G, self;
+    uint32_t U, G, self, id_stride;
+    const uint32_t *U_dev;
     const uint32_t *ucount, *ufirst;
     const uint32_t *root_of, *loc_of, *best;
     const uint8_t *dominated, *dead, *linked, *deadroot, *state;
@@ -856,9 +907,10 @@ struct SelectOwnParams {
 static __global__ void __launch_bounds__(256) select_own_kernel(const __grid_constant__ SelectOwnParams P)
 {
     const uint32_t u = blockIdx.x * 256u + threadIdx.x;
+    const uint32_t U = P.U_dev ? min(P.U, *P.U_dev) : P.U;
     bool sel = false;
-    if (u < P.U) {
-        const uint32_t gid = u * P.G + P.self;
+    if (u < U) {
+        const uint32_t gid = P.self * P.id_stride + u;   // slot of the key in the forests / flag arrays
         const uint32_t c = __ldcs(P.ucount + u);
         if (P.method == METHOD_DIRECTIONAL) {
             if (c >= 2) sel = !P.dominated[gid];
@@ -941,7 +993,10 @@ static __global__ void __launch_bounds__(256) adjacency_copy_kernel(const __grid
     for (uint32_t g = 0; g < E.G; g++) {
         const uint32_t n = min(E.n_edges[(size_t)g * E.n_stride], E.cap[g]);
         const uint32_t off = offsets[g];
-        for (uint32_t i = blockIdx.x * 256u + threadIdx.x; i < n; i += gridDim.x * 256u) dst[off + i] = __ldcs(E.edges[g] + i);
+        for (uint32_t i = blockIdx.x * 256u + threadIdx.x; i < n; i += gridDim.x * 256u) {
+            const uint2 ed = __ldcs(E.edges[g] + i);
+            dst[off + i] = make_uint2(slot_of_id(ed.x, E.G, E.id_stride), slot_of_id(ed.y, E.G, E.id_stride));
+        }
     }
 }
 

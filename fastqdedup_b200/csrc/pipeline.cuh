@@ -693,6 +693,7 @@ struct PassParams {
     // an edge travel in its state bits instead of being written to the flag bytes (partitioned.cuh, EDGE_*)
     uint32_t id_mul = 1, id_add = 0;
     int edge_flags = 0;
+    const uint32_t *U_dev = nullptr;   // when set: the unique count on the device (U is then an upper bound)
     uint32_t nb_mask;
     uint32_t *cnt;          // NB+1 counters -> exclusive offsets after the scan
     uint32_t *rank;         // U*V
@@ -1143,13 +1144,13 @@ static __global__ void __launch_bounds__(256) label_min_kernel(const __grid_cons
     atomicMin(P.minfirst + r, P.ufirst[u]);
 }
 
-// tile-sharded job: root of every own unique in the job-wide id space (the per-unique view of such a job labels a
+// tile-sharded job: root of every own unique in the job-wide slot space (slot of unique u = id_add + u * id_mul) (the per-unique view of such a job labels a
 // cluster by its root; the caller that holds all ranks' views turns roots into smallest-first labels)
 static __global__ void __launch_bounds__(256) root_gid_kernel(uint32_t U, uint32_t id_mul, uint32_t id_add, uint32_t *parent,
                                                               uint32_t *root)
 {
     const uint32_t u = blockIdx.x * 256u + threadIdx.x;
-    if (u < U) root[u] = uf_find(parent, u * id_mul + id_add);
+    if (u < U) root[u] = uf_find(parent, id_add + u * id_mul);
 }
 
 // ---- sharding across GPUs (DESIGN.md "Multi-GPU") ----------------------------------------------
@@ -1250,11 +1251,12 @@ static __global__ void __launch_bounds__(256) gather_nonzero_kernel(uint32_t U, 
                                                                     uint32_t *__restrict__ ucount,
                                                                     uint32_t *__restrict__ ufirst,
                                                                     uint32_t *kept, int keep_zero = 0,
-                                                                    uint32_t cap = 0xFFFFFFFFu, uint32_t *overflow = nullptr)
+                                                                    uint32_t cap = 0xFFFFFFFFu, uint32_t *overflow = nullptr,
+                                                                    const uint32_t *U_dev = nullptr)
 {
     constexpr int KW = K * PW, RW = slot_words(KW);
     const uint32_t u = blockIdx.x * 256u + threadIdx.x;
-    if (u >= U) return;
+    if (u >= U || (U_dev && u >= *U_dev)) return;
     const uint4 *rec = reinterpret_cast<const uint4 *>(table + (size_t)uslot[u] * RW);
     uint32_t w[RW];
 #pragma unroll

@@ -36,8 +36,8 @@ struct TileRank {
     uint32_t *ctrs = nullptr;        // device counters of the plan, see CTR_*
     uint32_t *oversize = nullptr;
     uint32_t *gath_in = nullptr, *gath = nullptr;   // small device-side gathers: [G][4]
-    uint32_t h_ctrs[16] = {};
-    uint32_t U_tiles = 0, U = 0;     // uniques out of the tiles / including the spill path
+    uint32_t *stat_in = nullptr, *stat_all = nullptr;   // status blocks (STATUS_WORDS uint64 per rank)
+    uint32_t U_tiles = 0, U = 0;     // uniques out of the tiles / upper bound including the spill path
     uint32_t *root_of = nullptr, *loc_of = nullptr;
     uint8_t *linked = nullptr;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -154,12 +154,29 @@ int run_sharded_tiles(std::vector<Shard> &S, Exchange *ex, const ShardWorld &W, 
         }
         return sync_all(S);
     };
-    // every rank's status and numbers on every rank; returns the first failing status (the same on all ranks)
-    auto agree = [&](int n, std::vector<std::vector<uint64_t>> &mine, std::vector<uint64_t> &all) -> int {
-        for (int i = 0; i < L; i++) mine[i][0] = (uint64_t)(uint32_t)T[i].rc;
-        FQD_TRY(gather_host_u64(S, ex, G, n, mine, all));
+    // Agreement point: every rank's status block (packed on the device by pack_status_kernel: no host round trip
+    // before the exchange) on every rank -- ONE host synchronisation.  `tail` is enqueued behind the exchange, before
+    // the synchronisation.  Returns the first failing status, the same on all ranks.
+    std::vector<uint64_t> all((size_t)G * STATUS_WORDS, 0);
+    auto agree = [&](auto tail) -> int {
+        for (int i = 0; i < L; i++) {
+            FQD_CUDA(cudaSetDevice(S[i].ctx->device));
+            StatusParams sp{(long long)T[i].rc, T[i].ctrs, S[i].ctx->d_ctr, cap_u, spill_cap, cap_e, cap_c,
+                            reinterpret_cast<unsigned long long *>(T[i].stat_in)};
+            if (!T[i].ctrs || !T[i].stat_in) { set_error("internal: status buffers were not allocated"); return FQD_ERR_NOMEM; }
+            pack_status_kernel<<<1, 32, 0, S[i].ctx->stream>>>(sp);
+            FQD_CUDA(cudaGetLastError());
+        }
+        FQD_TRY(allgather_u32([&](int i) { return T[i].stat_in; }, [&](int i) { return T[i].stat_all; }, (size_t)STATUS_WORDS * 2));
+        for (int i = 0; i < L; i++) {
+            FQD_CUDA(cudaSetDevice(S[i].ctx->device));
+            FQD_TRY(tail(i));
+            if (i == 0)
+                FQD_CUDA(cudaMemcpyAsync(all.data(), T[0].stat_all, (size_t)G * STATUS_WORDS * 8, cudaMemcpyDeviceToHost, S[0].ctx->stream));
+        }
+        FQD_TRY(sync_all(S));
         for (int g = 0; g < G; g++) {
-            const int rc = (int)(uint32_t)all[(size_t)g * n];
+            const int rc = (int)(long long)all[(size_t)g * STATUS_WORDS];
             if (rc != FQD_OK) {
                 bool mine_failed = false;
                 for (int i = 0; i < L; i++) mine_failed |= T[i].rc == rc;
@@ -169,6 +186,7 @@ int run_sharded_tiles(std::vector<Shard> &S, Exchange *ex, const ShardWorld &W, 
         }
         return FQD_OK;
     };
+    auto no_tail = [](int) { return FQD_OK; };
 
     // =====================================================================================================
     // phase 1: buffers
@@ -212,6 +230,8 @@ int run_sharded_tiles(std::vector<Shard> &S, Exchange *ex, const ShardWorld &W, 
             FQD_TRY(arena(ctx, (size_t)nper0, &t.oversize));
             FQD_TRY(arena(ctx, (size_t)4 * G, &t.gath_in));
             FQD_TRY(arena(ctx, (size_t)4 * G * 2, &t.gath));
+            FQD_TRY(arena(ctx, (size_t)STATUS_WORDS * 2, &t.stat_in));
+            FQD_TRY(arena(ctx, (size_t)STATUS_WORDS * 2 * G, &t.stat_all));
             FQD_TRY(arena(ctx, (size_t)cap_u * KW, &sh.local.ukey));
             FQD_TRY(arena(ctx, (size_t)cap_u, &sh.local.ucount));
             FQD_TRY(arena(ctx, (size_t)cap_u, &sh.local.ufirst));
@@ -302,42 +322,28 @@ int run_sharded_tiles(std::vector<Shard> &S, Exchange *ex, const ShardWorld &W, 
             sh.tt.launches++;
             FQD_CUDA(cudaGetLastError());
             if (i == 0) lap("dedupe tiles");
-            FQD_CUDA(cudaMemcpyAsync(t.h_ctrs, t.ctrs, sizeof t.h_ctrs, cudaMemcpyDeviceToHost, s));
-            FQD_TRY(fetch_counters(sh.ctx));
             return FQD_OK;
         }();
     }
 
     // ---- agreement 1: status, input errors, unique counts, skew ----
-    constexpr int A1 = 24;
-    std::vector<uint64_t> all;
     {
-        std::vector<std::vector<uint64_t>> mine(L, std::vector<uint64_t>(A1, 0));
-        for (int i = 0; i < L; i++) {
-            const DevCounters &c = *S[i].ctx->h_ctr;
-            const bool ok = T[i].rc == FQD_OK;
-            mine[i][1] = ok ? T[i].h_ctrs[CTR_UNIQUE] : 0;
-            mine[i][2] = ok ? T[i].h_ctrs[CTR_OVERSIZE] : 0;
-            mine[i][3] = ok ? std::min(T[i].h_ctrs[CTR_SPILL], spill_cap) : 0;
-            mine[i][4] = ok ? (T[i].h_ctrs[CTR_SPILL_OVER] | T[i].h_ctrs[CTR_UNIQUE_OVER] | T[i].h_ctrs[CTR_EDGE_OVER]) : 0;
-            mine[i][5] = ok ? c.phred_err : ~0ull;
-            mine[i][6] = ok ? c.n_discarded : 0;
-            mine[i][7] = ok ? (S[i].job.weights ? c.sum_weights : S[i].job.n - c.n_discarded) : 0;
-            for (int k = 0; k < 8; k++) mine[i][8 + k] = ok ? c.unknown[k] : 0;
-        }
-        const int rc = agree(A1, mine, all);
+        const int rc = agree(no_tail);
         if (rc != FQD_OK) return rc;
     }
     uint64_t n_disc = 0, n_seq = 0, phred = ~0ull, skew = 0, any_over = 0;
     bool any_unknown = false;
-    std::vector<uint32_t> n_spill(G);
+    std::vector<uint32_t> n_spill(G), n_over_of(G), U_tiles_of(G);
     for (int g = 0; g < G; g++) {
-        const uint64_t *v = &all[(size_t)g * A1];
-        any_over += v[2] + v[3];
+        const uint64_t *v = &all[(size_t)g * STATUS_WORDS];
+        U_tiles_of[g] = (uint32_t)v[1];
+        n_over_of[g] = (uint32_t)v[2];
         n_spill[g] = (uint32_t)v[3];
+        any_over += v[2] + v[3];
         skew |= v[4];
         phred = std::min(phred, v[5]);
-        n_disc += v[6]; n_seq += v[7];
+        n_disc += v[6];
+        n_seq += j0.weights ? v[7] : (W.base[g + 1] - W.base[g]) - v[6];
         for (int k = 0; k < 8; k++) { unknown_out[k] |= (uint32_t)v[8 + k]; any_unknown |= v[8 + k] != 0; }
     }
     if (phred != ~0ull) {
@@ -351,7 +357,22 @@ int run_sharded_tiles(std::vector<Shard> &S, Exchange *ex, const ShardWorld &W, 
         if (trace) fprintf(stderr, "[fqd trace] tiles: a spill / unique / edge buffer overflowed -> replicated-set plan\n");
         return RC_FALLBACK_REPLICATED;
     }
-    for (int i = 0; i < L; i++) T[i].U_tiles = T[i].U = T[i].h_ctrs[CTR_UNIQUE];
+    lap("agree");
+    // From here on nothing waits for the host until the final agreement: where a count is still being produced on the
+    // device (the spill path below adds uniques) launches are sized by an upper bound every rank can compute from
+    // the agreed numbers, and the kernels read the count itself.
+    uint64_t spill_total = 0;
+    for (int g = 0; g < G; g++) spill_total += n_spill[g];
+    auto spill_records_of = [&](int g) { return (uint64_t)n_over_of[g] * G * region + spill_total; };   // what rank g's spill path may see
+    uint32_t U_max = 0;
+    uint64_t U_bound_total = 0;
+    std::vector<uint32_t> U_bound_of(G);
+    for (int g = 0; g < G; g++) {
+        U_bound_of[g] = (uint32_t)std::min<uint64_t>(cap_u, U_tiles_of[g] + (any_over ? spill_records_of(g) : 0));
+        U_max = std::max(U_max, U_bound_of[g]);
+        U_bound_total += U_bound_of[g];
+    }
+    for (int i = 0; i < L; i++) { T[i].U_tiles = U_tiles_of[rank_of(i)]; T[i].U = U_bound_of[rank_of(i)]; }
 
     // =====================================================================================================
     // phase 5: oversize tiles (a key family larger than a tile) through the single-table insert on their owner
@@ -368,9 +389,9 @@ int run_sharded_tiles(std::vector<Shard> &S, Exchange *ex, const ShardWorld &W, 
                 FQD_CUDA(cudaSetDevice(sh.ctx->device));
                 cudaStream_t s = sh.ctx->stream;
                 const int r = rank_of(i);
-                const uint32_t n_over = t.h_ctrs[CTR_OVERSIZE];
-                uint64_t n_rec = (uint64_t)n_over * G * TILE_R;
-                for (int g = 0; g < G; g++) n_rec += n_spill[g];
+                const uint32_t n_over = n_over_of[r];
+                const uint64_t n_rec = spill_records_of(r);
+                if (n_rec == 0) return FQD_OK;
                 const uint64_t capacity = n_rec + (n_rec >> 1) + 1024;
                 uint32_t *table, *uslot;
                 FQD_TRY(arena(sh.ctx, capacity * RW, &table));
@@ -380,7 +401,7 @@ int run_sharded_tiles(std::vector<Shard> &S, Exchange *ex, const ShardWorld &W, 
                 TileSource src{};
                 for (int g = 0; g < G; g++) src.buf[g] = reinterpret_cast<const uint32_t *>(peer_ptr(sh, g, t.tiles0));
                 src.cnt = t.cnt0; src.G = (uint32_t)G; src.self = (uint32_t)r; src.first_tile = (uint32_t)r * nper0; src.ntiles = nper0;
-            src.region = region; src.peer_ldg = peer_ldg;
+                src.region = region; src.peer_ldg = peer_ldg;
                 if (n_over)
                     spill_insert_tiles_kernel<K, PW><<<n_over * (uint32_t)G * (TILE_R / 256), 256, 0, s>>>(src, t.oversize, tr, t.ctrs + CTR_CLAIMED);
                 for (int g = 0; g < G; g++)
@@ -388,32 +409,25 @@ int run_sharded_tiles(std::vector<Shard> &S, Exchange *ex, const ShardWorld &W, 
                         spill_insert_owned_kernel<K, PW><<<cdiv(n_spill[g], 256), 256, 0, s>>>(
                             reinterpret_cast<const uint32_t *>(peer_ptr(sh, g, t.spill)), n_spill[g], fused ? (uint32_t)d + 1u : 0u, (uint32_t)d + 1u,
                             nparts0, (uint32_t)r * nper0, nper0, sh.job.max_len, codec.pad_code, sh.job.varlen ? 1 : 0, tr, t.ctrs + CTR_CLAIMED);
+                // (the number of claimed slots stays on the device: the gather is sized by its upper bound)
+                gather_nonzero_kernel<K, PW><<<cdiv(n_rec, 256), 256, 0, s>>>((uint32_t)std::min<uint64_t>(n_rec, 0xFFFFFFF0u), table, uslot,
+                                                                                   sh.local.ukey, sh.local.ucount, sh.local.ufirst,
+                                                                                   t.ctrs + CTR_UNIQUE, 0, cap_u, t.ctrs + CTR_UNIQUE_OVER,
+                                                                                   t.ctrs + CTR_CLAIMED);
                 FQD_CUDA(cudaGetLastError());
-                uint32_t n_claimed = 0;
-                FQD_CUDA(cudaMemcpyAsync(&n_claimed, t.ctrs + CTR_CLAIMED, 4, cudaMemcpyDeviceToHost, s));
-                FQD_CUDA(cudaStreamSynchronize(s));
-                if (n_claimed)
-                    gather_nonzero_kernel<K, PW><<<cdiv(n_claimed, 256), 256, 0, s>>>(n_claimed, table, uslot, sh.local.ukey, sh.local.ucount,
-                                                                                       sh.local.ufirst, t.ctrs + CTR_UNIQUE, 0, cap_u,
-                                                                                       t.ctrs + CTR_UNIQUE_OVER);
-                FQD_CUDA(cudaGetLastError());
-                FQD_CUDA(cudaMemcpyAsync(t.h_ctrs, t.ctrs, sizeof t.h_ctrs, cudaMemcpyDeviceToHost, s));
-                FQD_TRY(fetch_counters(sh.ctx));
-                if (sh.ctx->h_ctr->table_full) { set_error("internal: spill table overflow"); return FQD_ERR_NOMEM; }
                 sh.tt.launches += 2 + G;
-                t.U = std::min(t.h_ctrs[CTR_UNIQUE], cap_u);
                 // the uniques of oversize tiles were not compared inside a tile, and they are not in the tiles of pass 1
                 // yet: pass 0 among themselves (their bucket mates took the same path, on this rank), then emit them
-                if (t.U > t.U_tiles && !t.h_ctrs[CTR_UNIQUE_OVER] && (fused || emit_next)) {
+                if (fused || emit_next) {
                     PassParams sp{};
-                    sp.U = t.U; sp.u_lo = t.U_tiles; sp.ukey = sh.local.ukey; sp.ucount = sh.local.ucount;
+                    sp.U = t.U; sp.U_dev = t.ctrs + CTR_UNIQUE; sp.u_lo = t.U_tiles; sp.ukey = sh.local.ukey; sp.ucount = sh.local.ucount;
                     sp.d = d; sp.edit = 0; sp.varlen = sh.job.varlen ? 1 : 0; sp.method = method;
                     sp.max_len = sh.job.max_len; sp.pad_code = codec.pad_code; sp.V = 1; sp.world = 1;
                     sp.ctr = sh.ctx->d_ctr;
                     sp.edge_flags = 1; sp.id_mul = (uint32_t)G; sp.id_add = (uint32_t)r;
                     for (int k = 0; k < 256; k++) sp.rank_of_code[k] = codec.rank[k];
-                    const uint32_t ns = t.U - t.U_tiles;
-                    if (fused) {
+                    const uint32_t ns = t.U - t.U_tiles;   // (upper bound)
+                    if (fused && ns) {
                         const uint32_t np = tile_partitions(ns);
                         uint32_t *sb, *sc;
                         FQD_TRY(arena(sh.ctx, (size_t)np * TILE_R * RW, &sb));
@@ -428,7 +442,7 @@ int run_sharded_tiles(std::vector<Shard> &S, Exchange *ex, const ShardWorld &W, 
                         bucket_tile_kernel<K, PW><<<np, TILE_THREADS, 0, s>>>(single_source(qp), sp, sink);
                         sh.tt.launches += 2;
                     }
-                    if (emit_next) {
+                    if (emit_next && ns) {
                         sp.pass_j = 1;
                         sp.fix_st = block_start(sh.job.max_len, 1u, (uint32_t)d + 1u);
                         sp.fix_bl = block_start(sh.job.max_len, 2u, (uint32_t)d + 1u) - sp.fix_st;
@@ -442,42 +456,21 @@ int run_sharded_tiles(std::vector<Shard> &S, Exchange *ex, const ShardWorld &W, 
             }();
         }
         for (int i = 0; i < L; i++) arena_release(S[i].ctx, marks[i]);
-        lap("agree + oversize tiles");
+        lap("oversize tiles");
     }
-
-    // ---- agreement 2: final unique counts ----
-    uint64_t U_total = 0;
-    uint32_t U_max = 0;
-    {
-        std::vector<std::vector<uint64_t>> mine(L, std::vector<uint64_t>(3, 0));
-        for (int i = 0; i < L; i++) { mine[i][1] = T[i].U; mine[i][2] = T[i].h_ctrs[CTR_UNIQUE_OVER]; }
-        if (any_over) {
-            const int rc = agree(3, mine, all);
-            if (rc != FQD_OK) return rc;
-            for (int g = 0; g < G; g++) {
-                if (all[(size_t)g * 3 + 2]) return RC_FALLBACK_REPLICATED;
-                U_total += all[(size_t)g * 3 + 1];
-                U_max = std::max<uint32_t>(U_max, (uint32_t)all[(size_t)g * 3 + 1]);
-            }
-        } else {
-            for (int g = 0; g < G; g++) {
-                U_total += all[(size_t)g * A1 + 1];
-                U_max = std::max<uint32_t>(U_max, (uint32_t)all[(size_t)g * A1 + 1]);
-            }
-        }
-    }
-    const uint64_t ids64 = (uint64_t)U_max * G;          // job-wide id space (ranks interleaved; sparse above a rank's count)
-    if (ids64 >= EDGE_ID) { set_error("too many unique keys for the tile-sharded plan (%llu)", (unsigned long long)U_total); return FQD_ERR_UNSUPPORTED; }
+    const uint64_t U_total_bound = U_bound_total;
+    const uint64_t ids64 = (uint64_t)U_max * G;          // job-wide id space; slots are rank-major with stride U_max
+    if (ids64 >= EDGE_ID) { set_error("too many unique keys for the tile-sharded plan (%llu)", (unsigned long long)U_total_bound); return FQD_ERR_UNSUPPORTED; }
     const uint32_t n_ids = (uint32_t)std::max<uint64_t>(ids64, 1);
 
     // =====================================================================================================
     // phase 6: forests and flags over the job-wide id space (every rank holds all of them)
     // =====================================================================================================
-    const int npass_all = (d > 0 && U_total > 1) ? d + 1 : 0;
+    const int npass_all = (d > 0 && U_total_bound > 1) ? d + 1 : 0;
     const int first_pass = fused ? 1 : 0;
-    const bool use_emitted = emit_next && U_total <= guessU;
+    const bool use_emitted = emit_next && U_total_bound <= guessU;
     const bool need_pass_buffers = npass_all > first_pass + (use_emitted ? 1 : 0);
-    const uint32_t nperP = cdiv(tile_partitions(std::max<uint64_t>(U_total, 1)), (uint32_t)G), npartsP = nperP * (uint32_t)G;
+    const uint32_t nperP = cdiv(tile_partitions(std::max<uint64_t>(U_total_bound, 1)), (uint32_t)G), npartsP = nperP * (uint32_t)G;
     for (int i = 0; i < L; i++) {
         Shard &sh = S[i];
         TileRank &t = T[i];
@@ -531,7 +524,7 @@ int run_sharded_tiles(std::vector<Shard> &S, Exchange *ex, const ShardWorld &W, 
         auto pass_params = [&](int i) {
             Shard &sh = S[i];
             PassParams pp{};
-            pp.U = T[i].U; pp.u_lo = 0; pp.ukey = sh.local.ukey; pp.ucount = sh.local.ucount;
+            pp.U = T[i].U; pp.U_dev = T[i].ctrs + CTR_UNIQUE; pp.u_lo = 0; pp.ukey = sh.local.ukey; pp.ucount = sh.local.ucount;
             pp.d = d; pp.edit = 0; pp.varlen = sh.job.varlen ? 1 : 0; pp.method = method;
             pp.max_len = sh.job.max_len; pp.pad_code = codec.pad_code; pp.V = 1; pp.world = 1;
             pp.ctr = sh.ctx->d_ctr;
@@ -608,7 +601,7 @@ int run_sharded_tiles(std::vector<Shard> &S, Exchange *ex, const ShardWorld &W, 
             FQD_CUDA(cudaSetDevice(sh.ctx->device));
             EdgeSource es{};
             for (int g = 0; g < G; g++) { es.edges[g] = reinterpret_cast<const uint2 *>(peer_ptr(sh, g, t.edges)); es.cap[g] = cap_e; }
-            es.n_edges = t.gath; es.n_stride = 4; es.G = (uint32_t)G; es.self = (uint32_t)rank_of(i);
+            es.n_edges = t.gath; es.n_stride = 4; es.G = (uint32_t)G; es.self = (uint32_t)rank_of(i); es.id_stride = U_max;
             EdgeFlags ef{sh.f.dominated, sh.f.dead, t.linked, method == METHOD_HIGHEST ? 1 : 0};
             if (npass_all)
                 apply_edges_kernel<<<sh.ctx->sm_count * 8, 256, 0, sh.ctx->stream>>>(es, sh.f.parent_full, sh.f.parent_one, ef, sh.ctx->d_ctr);
@@ -625,18 +618,14 @@ int run_sharded_tiles(std::vector<Shard> &S, Exchange *ex, const ShardWorld &W, 
     std::vector<uint8_t *> adj_state(L, nullptr);
     if (method == METHOD_ADJACENCY) {
         // (higher, lower) edges of all ranks, fetched once; then the rounds of the single-GPU plan over the id space
-        // the counts are needed on the host (launch sizes of the rounds): exchanged as numbers
-        std::vector<std::vector<uint64_t>> mine(L, std::vector<uint64_t>(2, 0));
-        for (int i = 0; i < L; i++) {
-            if (T[i].rc == FQD_OK && fetch_counters(S[i].ctx) != FQD_OK) T[i].rc = FQD_ERR_CUDA;
-            mine[i][1] = T[i].rc == FQD_OK ? S[i].ctx->h_ctr->n_edges : 0;
-        }
-        const int rc = agree(2, mine, all);
+        // the counts are needed on the host (launch sizes of the rounds): one more agreement point
+        const int rc = agree(no_tail);
         if (rc != FQD_OK) return rc;
         std::vector<uint32_t> off(G + 1, 0);
         for (int g = 0; g < G; g++) {
-            if (all[(size_t)g * 2 + 1] > cap_adj) return RC_FALLBACK_REPLICATED;
-            off[g + 1] = off[g] + (uint32_t)all[(size_t)g * 2 + 1];
+            const uint64_t ne = all[(size_t)g * STATUS_WORDS + 19];
+            if (ne > cap_adj || all[(size_t)g * STATUS_WORDS + 4]) return RC_FALLBACK_REPLICATED;
+            off[g + 1] = off[g] + (uint32_t)ne;
         }
         const uint32_t n_adj = off[G];
         for (int i = 0; i < L; i++) {
@@ -652,7 +641,7 @@ int run_sharded_tiles(std::vector<Shard> &S, Exchange *ex, const ShardWorld &W, 
                 FQD_CUDA(cudaMemcpyAsync(d_off, off.data(), (size_t)(G + 1) * 4, cudaMemcpyHostToDevice, s));
                 EdgeSource es{};
                 for (int g = 0; g < G; g++) { es.edges[g] = reinterpret_cast<const uint2 *>(peer_ptr(sh, g, t.adj)); es.cap[g] = (uint32_t)cap_adj; }
-                es.n_edges = t.gath + 2; es.n_stride = 4; es.G = (uint32_t)G; es.self = (uint32_t)rank_of(i);
+                es.n_edges = t.gath + 2; es.n_stride = 4; es.G = (uint32_t)G; es.self = (uint32_t)rank_of(i); es.id_stride = U_max;
                 if (n_adj) adjacency_copy_kernel<<<sh.ctx->sm_count * 4, 256, 0, s>>>(es, alle, d_off);
                 FQD_CUDA(cudaGetLastError());
                 FQD_CUDA(cudaStreamSynchronize(s));   // `off` is host memory
@@ -690,7 +679,7 @@ int run_sharded_tiles(std::vector<Shard> &S, Exchange *ex, const ShardWorld &W, 
                 if (method == METHOD_DIRECTIONAL)
                     deadroot_kernel<<<cdiv(n_ids, 256), 256, 0, s>>>(n_ids, sh.f.dead, t.linked, sh.f.parent_one, sh.f.deadroot);
                 CandParams cp{};
-                cp.U = t.U; cp.G = (uint32_t)G; cp.self = (uint32_t)rank_of(i);
+                cp.U = t.U; cp.U_dev = t.ctrs + CTR_UNIQUE; cp.G = (uint32_t)G; cp.self = (uint32_t)rank_of(i); cp.id_stride = U_max;
                 cp.ukey = sh.local.ukey; cp.ucount = sh.local.ucount;
                 cp.forest = method == METHOD_DIRECTIONAL ? sh.f.parent_one : sh.f.parent_full;
                 cp.dead = sh.f.dead; cp.linked = t.linked; cp.deadroot = sh.f.deadroot;
@@ -740,7 +729,7 @@ int run_sharded_tiles(std::vector<Shard> &S, Exchange *ex, const ShardWorld &W, 
             FQD_CUDA(cudaSetDevice(sh.ctx->device));
             cudaStream_t s = sh.ctx->stream;
             SelectOwnParams sp{};
-            sp.U = t.U; sp.G = (uint32_t)G; sp.self = (uint32_t)rank_of(i);
+            sp.U = t.U; sp.U_dev = t.ctrs + CTR_UNIQUE; sp.G = (uint32_t)G; sp.self = (uint32_t)rank_of(i); sp.id_stride = U_max;
             sp.ucount = sh.local.ucount; sp.ufirst = sh.local.ufirst;
             sp.root_of = t.root_of; sp.loc_of = t.loc_of; sp.best = sh.f.best;
             sp.dominated = sh.f.dominated; sp.dead = sh.f.dead; sp.linked = t.linked; sp.deadroot = sh.f.deadroot;
@@ -756,35 +745,33 @@ int run_sharded_tiles(std::vector<Shard> &S, Exchange *ex, const ShardWorld &W, 
             if (t.U) select_own_kernel<<<cdiv(t.U, 256), 256, 0, s>>>(sp);
             sh.tt.launches++;
             FQD_CUDA(cudaGetLastError());
-            FQD_CUDA(cudaMemcpyAsync(t.h_ctrs, t.ctrs, sizeof t.h_ctrs, cudaMemcpyDeviceToHost, s));
-            FQD_TRY(fetch_counters(sh.ctx));
             return FQD_OK;
         }();
     }
 
-    // ---- agreement 3 (also the barrier behind the remote keep bits): totals and late overflows ----
-    uint64_t n_sel = 0, n_cand_pairs = 0, merges = 0, late = 0;
+    // ---- final agreement (also the barrier behind the remote keep bits): totals and late overflows; the keep bitmap is
+    //      handed to the caller behind the exchange, ahead of the one host synchronisation ----
     {
-        std::vector<std::vector<uint64_t>> mine(L, std::vector<uint64_t>(6, 0));
-        for (int i = 0; i < L; i++) {
-            if (T[i].rc != FQD_OK) continue;
-            const DevCounters &c = *S[i].ctx->h_ctr;
-            mine[i][1] = c.n_selected;
-            mine[i][2] = c.n_candidates;
-            mine[i][3] = c.n_merges;
-            mine[i][4] = T[i].h_ctrs[CTR_EDGE_OVER] | (T[i].h_ctrs[CTR_EDGES] > cap_e) | (T[i].h_ctrs[CTR_CAND] > cap_c);
-        }
-        const int rc = agree(6, mine, all);
+        const int rc = agree([&](int i) -> int {
+            if (S[i].job.bitmap && S[i].job.n)
+                FQD_CUDA(cudaMemcpyAsync(S[i].job.bitmap, T[i].bitmap, (size_t)cdiv(S[i].job.n, 32) * 4, cudaMemcpyDeviceToDevice,
+                                         S[i].ctx->stream));
+            FQD_CUDA(cudaEventRecord(T[i].e1, S[i].ctx->stream));
+            return FQD_OK;
+        });
         if (rc != FQD_OK) return rc;
-        for (int g = 0; g < G; g++) {
-            n_sel += all[(size_t)g * 6 + 1];
-            n_cand_pairs += all[(size_t)g * 6 + 2];
-            merges = all[(size_t)g * 6 + 3];     // every rank applied every edge: the same number everywhere
-            late |= all[(size_t)g * 6 + 4];
-        }
+    }
+    uint64_t n_sel = 0, n_cand_pairs = 0, merges = 0, late = 0, U_total = 0;
+    for (int g = 0; g < G; g++) {
+        const uint64_t *v = &all[(size_t)g * STATUS_WORDS];
+        U_total += v[1];
+        late |= v[4] | v[20];
+        n_sel += v[16];
+        n_cand_pairs += v[17];
+        merges = v[18];          // every rank applied every edge: the same number everywhere
     }
     if (late) {
-        if (trace) fprintf(stderr, "[fqd trace] tiles: a pass tile / the edge or candidate list overflowed -> replicated-set plan\n");
+        if (trace) fprintf(stderr, "[fqd trace] tiles: a pass tile / the unique, edge or candidate list overflowed -> replicated-set plan\n");
         return RC_FALLBACK_REPLICATED;
     }
     lap("select + agree");
@@ -793,11 +780,7 @@ int run_sharded_tiles(std::vector<Shard> &S, Exchange *ex, const ShardWorld &W, 
         Shard &sh = S[i];
         TileRank &t = T[i];
         FQD_CUDA(cudaSetDevice(sh.ctx->device));
-        cudaStream_t s = sh.ctx->stream;
-        if (sh.job.bitmap && sh.job.n)
-            FQD_CUDA(cudaMemcpyAsync(sh.job.bitmap, t.bitmap, (size_t)cdiv(sh.job.n, 32) * 4, cudaMemcpyDeviceToDevice, s));
-        FQD_CUDA(cudaEventRecord(t.e1, s));
-        FQD_CUDA(cudaStreamSynchronize(s));
+        t.U = (uint32_t)all[(size_t)rank_of(i) * STATUS_WORDS + 1];   // the count itself (so far an upper bound)
         fqd_cluster_stats *st = sh.st;
         st->total_records = N;
         st->discarded_records = n_disc;
@@ -814,8 +797,9 @@ int run_sharded_tiles(std::vector<Shard> &S, Exchange *ex, const ShardWorld &W, 
                          (fused ? FQD_PLAN_PASS0_FUSED : 0u) | (use_emitted && npass_all > 1 ? FQD_PLAN_PASS1_TILES_EMITTED : 0u);
         sh.local.U = t.U;
         publish_result(sh.ctx, sh.local, sh.f, N, n_sel);
-        sh.ctx->res.id_mul = (uint32_t)G;
-        sh.ctx->res.id_add = (uint32_t)rank_of(i);
+        sh.ctx->res.id_mul = 1;                                    // slot of own unique u: rank * stride + u
+        sh.ctx->res.id_add = (uint32_t)rank_of(i) * U_max;
+        sh.ctx->res.roots_only = true;
     }
     return FQD_OK;
     }
