@@ -65,7 +65,8 @@ constexpr uint32_t EDGE_STATE = 7u << EDGE_SHIFT;
 constexpr int MAX_RANKS = 16;
 struct TileSource {
     const uint32_t *buf[MAX_RANKS];   // partition buffers (peer-mapped for the other ranks), regions indexed by GLOBAL tile
-    const uint32_t *cnt;              // [G][ntiles] fill counters of the owned tiles, gathered from all ranks
+    const uint32_t *cnt;              // fill counters of the owned tiles gathered from all ranks: cnt[g * cnt_stride + j]
+    uint32_t cnt_stride;
     uint32_t G, self;
     uint32_t first_tile;              // global index of owned tile 0
     uint32_t ntiles;                  // owned tiles
@@ -125,7 +126,7 @@ __device__ __forceinline__ uint32_t stage_tile(uint32_t *recs, uint32_t *tab, ui
     uint32_t total = 0, mine = 0, before = 0, local = 0;
     bool over = false;
     for (uint32_t g = 0; g < S.G; g++) {
-        const uint32_t c = S.cnt[(size_t)g * S.ntiles + j];
+        const uint32_t c = S.cnt[(size_t)g * S.cnt_stride + j];
         if (g == S.self) local = c;
         over |= c > S.region;               // the rank's own region overflowed (the surplus is in its spill buffer)
         if (g < tid) before += c;
@@ -161,7 +162,7 @@ __device__ __forceinline__ uint32_t stage_tile(uint32_t *recs, uint32_t *tab, ui
         // the peers' fragments by plain 16-byte loads, four in flight per thread
         uint32_t off = 0;
         for (uint32_t g = 0; g < S.G; g++) {
-            const uint32_t c = S.cnt[(size_t)g * S.ntiles + j];
+            const uint32_t c = S.cnt[(size_t)g * S.cnt_stride + j];
             if (g != S.self && c) {
                 const uint4 *src = reinterpret_cast<const uint4 *>(S.buf[g] + (size_t)(S.first_tile + j) * S.region * PART_RW);
                 uint4 *dst = reinterpret_cast<uint4 *>(recs + (size_t)off * PART_RW);
@@ -674,6 +675,8 @@ struct EdgeSource {
     uint32_t cap[MAX_RANKS];
     const uint32_t *n_edges;    // [G * n_stride] edge counters of all ranks (gathered; a local copy)
     uint32_t n_stride;          // counter of rank g: n_edges[g * n_stride]
+    const uint32_t *first;      // optional: the lists are read from first[g * first_stride] on (what an earlier launch,
+    uint32_t first_stride;      // overlapped with the next pass, has already applied)
     uint32_t G, self;
     uint32_t id_stride;         // slot of id (u * G + rank): rank * id_stride + u, see slot_of_id
 };
@@ -688,44 +691,60 @@ __device__ __forceinline__ uint32_t slot_of_id(uint32_t id, uint32_t G, uint32_t
     return G == 1 ? id : (id % G) * stride + id / G;
 }
 
-// Per-key state of the dissection that edges set (all byte arrays over the job-wide id space; null = not needed).
+// Per-key state of the dissection that edges set: byte arrays over THIS RANK'S uniques (index = local unique id; on
+// one GPU that is the id itself).  A rank applies every edge of every rank to its forests, but only the flags of its
+// own keys: what the other members of a component contribute reaches it through the candidate lists.
 struct EdgeFlags {
-    uint8_t *dominated;   // directional: written for this rank's own ids only
-    uint8_t *dead;        // directional: every rank keeps all of them (a dead member kills its whole count-1 component)
+    uint8_t *dominated;   // directional
+    uint8_t *dead;        // directional: the count-1 key touches a key with count >= 2
     uint8_t *linked;      // the key has an edge of the kind the dissection reduces over (directional: count-1 edges;
                           // highest_count: any edge) -- keys without one are their own component and need no exchange
     int any_edge;         // highest_count: `linked` for every edge
 };
+
+constexpr int APPLY_UNROLL = 4;   // edges a thread fetches (from a peer's HBM) before it hooks them
 
 static __global__ void __launch_bounds__(256) apply_edges_kernel(const __grid_constant__ EdgeSource E, uint32_t *parent_full,
                                                                  uint32_t *parent_one, const __grid_constant__ EdgeFlags F,
                                                                  DevCounters *ctr)
 {
     uint32_t merges = 0;
-    // (prefetching the next edge's parents into the L2 while hooking the current one was measured slower)
+    const uint32_t stride = gridDim.x * 256u;
     for (uint32_t k = 0; k < E.G; k++) {
         const uint32_t g = (k + blockIdx.x) % E.G;   // blocks start on different peers: all NVLink ports busy at once
         const uint32_t n = min(E.n_edges[(size_t)g * E.n_stride], E.cap[g]);
+        const uint32_t lo = E.first ? min(E.first[(size_t)g * E.first_stride], n) : 0u;
         const uint2 *edges = E.edges[g];
-        for (uint32_t i = blockIdx.x * 256u + threadIdx.x; i < n; i += gridDim.x * 256u) {
-            const uint2 ed = __ldcs(edges + i);
-            const uint32_t st = ed.y & EDGE_STATE;
-            const bool x_mine = ed.x % E.G == E.self, y_mine = (ed.y & EDGE_ID) % E.G == E.self;
-            const uint32_t x = slot_of_id(ed.x, E.G, E.id_stride), y = slot_of_id(ed.y & EDGE_ID, E.G, E.id_stride);
-            if (uf_union(parent_full, x, y)) merges++;
-            if (st == EDGE_ONE) {
-                if (parent_one) uf_union(parent_one, x, y);
-                if (F.linked) { F.linked[x] = 1; F.linked[y] = 1; }
-            } else if (st == EDGE_DEAD_X) {
-                F.dead[x] = 1;
-            } else if (st == EDGE_DEAD_Y) {
-                F.dead[y] = 1;
-            } else if (st == EDGE_DOM_X) {
-                if (x_mine) F.dominated[x] = 1;
-            } else if (st == EDGE_DOM_Y) {
-                if (y_mine) F.dominated[y] = 1;
+        for (uint32_t i0 = lo + blockIdx.x * 256u + threadIdx.x; i0 < n; i0 += APPLY_UNROLL * stride) {
+            uint2 batch[APPLY_UNROLL];
+#pragma unroll
+            for (int u = 0; u < APPLY_UNROLL; u++)
+                if (i0 + u * stride < n) batch[u] = __ldcs(edges + i0 + u * stride);
+#pragma unroll
+            for (int u = 0; u < APPLY_UNROLL; u++) {
+                if (i0 + u * stride >= n) break;
+                const uint2 ed = batch[u];
+                const uint32_t st = ed.y & EDGE_STATE, idx = ed.x, idy = ed.y & EDGE_ID;
+                const uint32_t x = slot_of_id(idx, E.G, E.id_stride), y = slot_of_id(idy, E.G, E.id_stride);
+                if (uf_union(parent_full, x, y)) merges++;
+                if (st == EDGE_ONE && parent_one) uf_union(parent_one, x, y);
+                if (st == EDGE_NONE && !F.any_edge) continue;
+                // flags of this rank's own keys (local id = id / G)
+                const bool x_mine = idx % E.G == E.self, y_mine = idy % E.G == E.self;
+                const uint32_t ux = idx / E.G, uy = idy / E.G;
+                if (st == EDGE_ONE || F.any_edge) {
+                    if (F.linked && x_mine) F.linked[ux] = 1;
+                    if (F.linked && y_mine) F.linked[uy] = 1;
+                } else if (st == EDGE_DEAD_X) {
+                    if (x_mine) F.dead[ux] = 1;
+                } else if (st == EDGE_DEAD_Y) {
+                    if (y_mine) F.dead[uy] = 1;
+                } else if (st == EDGE_DOM_X) {
+                    if (x_mine) F.dominated[ux] = 1;
+                } else if (st == EDGE_DOM_Y) {
+                    if (y_mine) F.dominated[uy] = 1;
+                }
             }
-            if (F.any_edge) { F.linked[x] = 1; F.linked[y] = 1; }
         }
     }
     for (int o = 16; o; o >>= 1) merges += __shfl_xor_sync(WARP_FULL, merges, o);
@@ -734,22 +753,12 @@ static __global__ void __launch_bounds__(256) apply_edges_kernel(const __grid_co
 
 // ---- dissection of a tile-sharded job ---------------------------------------------------------------
 //
-// Every rank holds the whole forests (it applied all edges) but only ITS keys.  Flags and roots are enough
-// for most keys; where a component's answer depends on the keys of several members (the largest key of a
-// count-1 component, the largest (count, key) of a cluster) the members that matter become CANDIDATES --
-// {key, count, id} records in each rank's candidate list -- and every rank reduces all candidate lists
-// (read from the peers' HBM) into best[root].
-
-// directional: a dead member makes its count-1 component dead (replicated: all ids)
-static __global__ void __launch_bounds__(256) deadroot_kernel(uint32_t n_ids, const uint8_t *__restrict__ dead,
-                                                              const uint8_t *__restrict__ linked, uint32_t *parent_one,
-                                                              uint8_t *deadroot)
-{
-    const uint32_t g = blockIdx.x * 256u + threadIdx.x;
-    if (g >= n_ids || !dead[g]) return;
-    if (!linked[g]) return;   // its own component: select_own_kernel reads dead[] directly
-    deadroot[uf_find(parent_one, g)] = 1;
-}
+// Every rank holds the whole forests (it applied all edges) but only ITS keys and their flags.  Flags and roots
+// are enough for most keys; where a component's answer depends on several members (the largest key of a count-1
+// component and whether any member is dead; the largest (count, key) of a cluster) the members that matter
+// become CANDIDATES -- {key, count, id} records in each rank's candidate list -- and every rank reduces all
+// candidate lists (read from the peers' HBM) into best[root] / deadroot[root].  A dead member travels as a record
+// with count 0.
 
 // One status block per rank and agreement point, packed on the device (no host round trip before the exchange):
 // the plan's counters and the job counters the ranks have to agree on or add up.
@@ -792,7 +801,7 @@ struct CandParams {
     uint32_t G, self, id_stride;
     const uint32_t *ukey, *ucount;
     uint32_t *forest;         // parent_one (directional) / parent_full (highest_count)
-    const uint8_t *dead, *linked, *deadroot;
+    const uint8_t *dead, *linked;   // per own unique
     uint32_t *root_of;        // per own unique: root of its component in `forest`
     uint32_t *loc_of;         // per own unique: (self << 28 | index) of its candidate record, or NO_CLAIM
     uint32_t *cand;           // candidate records {key[KW], count, id} of PART_RW words
@@ -812,17 +821,13 @@ static __global__ void __launch_bounds__(256) candidates_kernel(const __grid_con
     bool emit = false;
     uint32_t root = 0, gid = 0, c = 0;
     if (u < U) {
-        gid = P.self * P.id_stride + u;   // slot of the key in the forests / flag arrays
+        gid = P.self * P.id_stride + u;   // slot of the key in the forests
         c = P.ucount[u];
         root = gid;
-        if (P.method == METHOD_DIRECTIONAL) {
-            if (c == 1 && P.linked[gid] && !P.dead[gid]) {
-                root = uf_find(P.forest, gid);
-                emit = !P.deadroot[root];
-            }
-        } else if (P.linked[gid]) {
+        if (P.linked[u] && (P.method != METHOD_DIRECTIONAL || c == 1)) {
             root = uf_find(P.forest, gid);
             emit = true;
+            if (P.method == METHOD_DIRECTIONAL && P.dead[u]) c = 0;   // a dead member: kills the component, never wins it
         }
         P.root_of[u] = root;
     }
@@ -851,6 +856,7 @@ struct BestParams {
     uint32_t n_stride;
     uint32_t G;
     uint32_t *best;           // per root: (rank << 28 | index) of the best candidate so far; NO_CLAIM = none
+    uint8_t *deadroot;        // per root: a member of the count-1 component is dead (directional)
     uint8_t rank_of_code[256];
 };
 
@@ -867,6 +873,7 @@ static __global__ void __launch_bounds__(256) best_candidate_kernel(const __grid
             uint32_t e[PART_RW];
             load_rec_stream(P.cand[g] + (size_t)i * PART_RW, e);
             const uint32_t r = __ldcs(P.cand_root[g] + i);
+            if (e[KW] == 0) { P.deadroot[r] = 1; continue; }   // (only directional jobs send count 0)
             const uint32_t me = (g << 28) | i;
             Key<K, PW> km;
 #pragma unroll
@@ -894,16 +901,18 @@ struct SelectOwnParams {
     const uint32_t *U_dev;
     const uint32_t *ucount, *ufirst;
     const uint32_t *root_of, *loc_of, *best;
-    const uint8_t *dominated, *dead, *linked, *deadroot, *state;
+    const uint8_t *dominated, *dead, *linked;   // per own unique
+    const uint8_t *deadroot, *state;            // per slot
     uint8_t *selected;        // per own unique
-    uint32_t *bitmap[MAX_RANKS];       // keep bitmaps of all ranks (peer memory): bit (f - base[q]) of rank q
-    uint32_t base[MAX_RANKS + 1];      // record index ranges of the ranks
+    uint32_t *bitmap;         // this rank's keep bits over ALL records of the job (bit = global record index - bit_base)
+    uint32_t bit_base;
     int method;
     DevCounters *ctr;
 };
 
-// The keys of this rank decide; the keep bit of a selected key goes to the rank that holds its first record
-// (reference pass 2, __init__.py:201-206) with one remote atomic OR.
+// The keys of this rank decide.  The keep bit of a selected key belongs to the rank that holds the key's first
+// record (reference pass 2, __init__.py:201-206): every rank marks its selected keys in a bitmap over the records
+// of the whole job, and merge_bitmaps_kernel on each rank ORs together the peers' slices of its own records.
 static __global__ void __launch_bounds__(256) select_own_kernel(const __grid_constant__ SelectOwnParams P)
 {
     const uint32_t u = blockIdx.x * 256u + threadIdx.x;
@@ -913,25 +922,64 @@ static __global__ void __launch_bounds__(256) select_own_kernel(const __grid_con
         const uint32_t gid = P.self * P.id_stride + u;   // slot of the key in the forests / flag arrays
         const uint32_t c = __ldcs(P.ucount + u);
         if (P.method == METHOD_DIRECTIONAL) {
-            if (c >= 2) sel = !P.dominated[gid];
-            else if (P.dead[gid]) sel = false;
-            else if (!P.linked[gid]) sel = true;
+            if (c >= 2) sel = !P.dominated[u];
+            else if (P.dead[u]) sel = false;
+            else if (!P.linked[u]) sel = true;
             else sel = !P.deadroot[P.root_of[u]] && P.best[P.root_of[u]] == P.loc_of[u];
         } else if (P.method == METHOD_HIGHEST) {
-            sel = !P.linked[gid] || P.best[P.root_of[u]] == P.loc_of[u];
+            sel = !P.linked[u] || P.best[P.root_of[u]] == P.loc_of[u];
         } else {
             sel = P.state[gid] == 1;
         }
         P.selected[u] = sel ? 1 : 0;
         if (sel) {
-            const uint32_t f = __ldcs(P.ufirst + u);
-            uint32_t q = 0;
-            while (q + 1 < P.G && f >= P.base[q + 1]) q++;
-            const uint32_t t = f - P.base[q];
-            atomicOr(P.bitmap[q] + (t >> 5), 1u << (t & 31));
+            const uint32_t t = __ldcs(P.ufirst + u) - P.bit_base;
+            atomicOr(P.bitmap + (t >> 5), 1u << (t & 31));
         }
     }
     block_add(sel ? 1u : 0u, &P.ctr->n_selected);
+}
+
+// Send buffer of the counter exchange: G blocks of (nper fill counters of the receiver's tiles, this rank's current
+// edge count) -- the receiver learns, for free, how far every list is complete at this point of the job.
+static __global__ void __launch_bounds__(256) pack_counters_kernel(const uint32_t *__restrict__ cursor, uint32_t nper, uint32_t G,
+                                                                   const uint32_t *__restrict__ extra, uint32_t *__restrict__ out)
+{
+    const uint32_t i = blockIdx.x * 256u + threadIdx.x, block = nper + 1;
+    if (i >= G * block) return;
+    const uint32_t g = i / block, j = i % block;
+    out[i] = j < nper ? cursor[(size_t)g * nper + j] : *extra;
+}
+
+static __global__ void copy_strided_kernel(uint32_t *dst, const uint32_t *src, uint32_t stride, uint32_t n)
+{
+    if (threadIdx.x < n) dst[threadIdx.x] = src[(size_t)threadIdx.x * stride];
+}
+
+// Keep bitmap of this rank's records [lo, lo + n): OR of that bit range of every rank's job-wide bitmap (fetched
+// from the peers' HBM); output bit t = job bit (lo - bit_base + t).
+struct MergeParams {
+    const uint32_t *src[MAX_RANKS];
+    uint32_t G;
+    uint32_t bit_lo;      // lo - bit_base
+    uint32_t n;           // records of this rank
+    uint32_t src_words;   // words of a job-wide bitmap
+    uint32_t *dst;
+};
+static __global__ void __launch_bounds__(256) merge_bitmaps_kernel(const __grid_constant__ MergeParams P)
+{
+    const uint32_t w = blockIdx.x * 256u + threadIdx.x, nw = (P.n + 31) / 32;
+    if (w >= nw) return;
+    const uint32_t k = (P.bit_lo >> 5) + w, sh = P.bit_lo & 31u;
+    uint32_t acc = 0;
+    for (uint32_t g = 0; g < P.G; g++) {
+        const uint32_t lo = __ldcs(P.src[g] + k);
+        const uint32_t hi = (sh && k + 1 < P.src_words) ? __ldcs(P.src[g] + k + 1) : 0u;
+        acc |= sh ? ((lo >> sh) | (hi << (32u - sh))) : lo;
+    }
+    const uint32_t rem = P.n - 32u * w;
+    if (rem < 32u) acc &= (1u << rem) - 1u;
+    P.dst[w] = acc;
 }
 
 // Oversize tiles of a sharded job: the fragments of the listed owned tiles (all ranks' regions) go through the
@@ -945,7 +993,7 @@ static __global__ void __launch_bounds__(256) spill_insert_tiles_kernel(const __
     constexpr uint32_t BPP = TILE_R / 256;
     const uint32_t j = list[blockIdx.x / (S.G * BPP)], g = (blockIdx.x / BPP) % S.G;
     const uint32_t i = (blockIdx.x % BPP) * 256u + threadIdx.x;
-    const uint32_t n = min(S.cnt[(size_t)g * S.ntiles + j], S.region);
+    const uint32_t n = min(S.cnt[(size_t)g * S.cnt_stride + j], S.region);
     uint32_t claimed = NO_CLAIM;
     if (i < n) {
         uint32_t e[PART_RW];

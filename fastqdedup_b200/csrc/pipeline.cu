@@ -84,7 +84,7 @@ size_t tile_plan_bytes(uint64_t n_total, uint64_t n_max, int world, int d, int m
     b += (n_max + (1u << 16)) * 8;                                               // edge list
     if (method == METHOD_ADJACENCY) b += (2 * n_max + (1u << 16)) * 8 + (2 * n_total + (1u << 16)) * 8;
     b += cap_u * (rec + 4);                                                      // candidate list
-    b += n_max / 8 + 4096;                                                       // keep bitmap
+    b += n_total / 8 + 4096;                                                     // keep bits over the records of the whole job
     const uint64_t ids = cap_u * G;                                              // job-wide id space
     b += ids * (4 + 4 + 4 + 4 + 5) + cap_u * 16;                                 // forests, best, flags, per-own-unique state
     b += (cap_u / 2) * rec * 3;                                                  // spill table of the oversize tiles (rarely large)

@@ -189,7 +189,7 @@ inline TileSource single_source(const PartParams &q)
 {
     TileSource S{};
     S.buf[0] = q.buf;
-    S.cnt = q.cursor;
+    S.cnt = q.cursor; S.cnt_stride = q.nparts;
     S.G = 1; S.self = 0; S.first_tile = 0; S.ntiles = q.nparts; S.region = q.region;
     return S;
 }

@@ -37,6 +37,8 @@ struct TileRank {
     uint32_t *oversize = nullptr;
     uint32_t *gath_in = nullptr, *gath = nullptr;   // small device-side gathers: [G][4]
     uint32_t *stat_in = nullptr, *stat_all = nullptr;   // status blocks (STATUS_WORDS uint64 per rank)
+    uint32_t *a2a_send = nullptr;                   // counter exchange: G blocks of (nper counters, edge count)
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;   // the first edge application runs beside the next pass
     uint32_t U_tiles = 0, U = 0;     // uniques out of the tiles / upper bound including the spill path
     uint32_t *root_of = nullptr, *loc_of = nullptr;
     uint8_t *linked = nullptr;
@@ -95,7 +97,12 @@ int run_sharded_tiles(std::vector<Shard> &S, Exchange *ex, const ShardWorld &W, 
     std::vector<TileRank> T(L);
     struct Cleanup {
         std::vector<TileRank> &T;
-        ~Cleanup() { for (auto &t : T) { if (t.e0) cudaEventDestroy(t.e0); if (t.e1) cudaEventDestroy(t.e1); } }
+        ~Cleanup()
+        {
+            for (auto &t : T)
+                for (cudaEvent_t e : {t.e0, t.e1, t.ev_fork, t.ev_join})
+                    if (e) cudaEventDestroy(e);
+        }
     } cleanup{T};
 
     // ---- sizes every rank derives from the agreed numbers (so that the shared buffers sit at the same offsets) ----
@@ -115,7 +122,7 @@ int run_sharded_tiles(std::vector<Shard> &S, Exchange *ex, const ShardWorld &W, 
     const uint32_t cap_e = (uint32_t)std::min<uint64_t>(EDGE_ID, W.n_max + (1u << 16));
     const uint32_t cap_c = std::min<uint32_t>(cap_u, (1u << 28) - 1);
     const uint64_t cap_adj = method == METHOD_ADJACENCY ? 2 * W.n_max + (1u << 16) : 0;
-    const uint32_t bm_words = (uint32_t)((W.n_max + 31) / 32 + 1);
+    const uint32_t bm_words = (uint32_t)((N + 31) / 32 + 2);   // every rank marks its selected keys over the records of the whole job
 
     // peer view of a pointer into this rank's slab
     auto in_slab = [&](const Shard &sh, const void *p, size_t bytes) {
@@ -127,18 +134,27 @@ int run_sharded_tiles(std::vector<Shard> &S, Exchange *ex, const ShardWorld &W, 
     };
 
     // ---- exchanges ----
-    // all-to-all of equal blocks of `words` uint32: block r of rank g -> block g of rank r
-    auto alltoall_u32 = [&](auto src_of, auto dst_of, size_t words) -> int {
+    // Counter exchange (all-to-all): rank g sends rank r the fill counters of r's tiles in g's buffer plus g's current
+    // edge count; received as cnt[g * (nper + 1) + j].  It is also the barrier between a fill phase and the tile kernels.
+    auto exchange_counters = [&](auto cursor_of, auto cnt_of, uint32_t nper) -> int {
+        const size_t words = (size_t)nper + 1;
+        for (int i = 0; i < L; i++) {
+            if (T[i].rc != FQD_OK || !T[i].a2a_send) continue;
+            FQD_CUDA(cudaSetDevice(S[i].ctx->device));
+            pack_counters_kernel<<<cdiv(words * G, 256), 256, 0, S[i].ctx->stream>>>(cursor_of(i), nper, (uint32_t)G, T[i].ctrs + CTR_EDGES,
+                                                                                      T[i].a2a_send);
+            FQD_CUDA(cudaGetLastError());
+        }
         if (ex) {
             std::vector<size_t> off(G), bytes(G, words * 4);
             for (int g = 0; g < G; g++) off[g] = (size_t)g * words * 4;
-            return ex->alltoallv(src_of(0), off.data(), bytes.data(), dst_of(0), off.data(), bytes.data(), S[0].ctx->stream);
+            return ex->alltoallv(T[0].a2a_send, off.data(), bytes.data(), cnt_of(0), off.data(), bytes.data(), S[0].ctx->stream);
         }
         FQD_TRY(sync_all(S));
         for (int r = 0; r < G; r++) {
             FQD_CUDA(cudaSetDevice(S[r].ctx->device));
             for (int g = 0; g < G; g++)
-                FQD_CUDA(cudaMemcpyAsync(dst_of(r) + (size_t)g * words, src_of(g) + (size_t)r * words, words * 4, cudaMemcpyDefault,
+                FQD_CUDA(cudaMemcpyAsync(cnt_of(r) + (size_t)g * words, T[g].a2a_send + (size_t)r * words, words * 4, cudaMemcpyDefault,
                                          S[r].ctx->stream));
         }
         return sync_all(S);
@@ -221,14 +237,17 @@ int run_sharded_tiles(std::vector<Shard> &S, Exchange *ex, const ShardWorld &W, 
             FQD_TRY(shared(&t.cand_root, (size_t)cap_c));
             FQD_TRY(shared(&t.bitmap, (size_t)bm_words));
             FQD_TRY(arena(ctx, (size_t)nparts0, &t.cursor0));
-            FQD_TRY(arena(ctx, (size_t)nparts0, &t.cnt0));
+            FQD_TRY(arena(ctx, (size_t)nparts0 + G, &t.cnt0));
+            FQD_TRY(arena(ctx, (size_t)std::max(nparts0, npartsN) + G, &t.a2a_send));
+            FQD_CUDA(cudaEventCreateWithFlags(&t.ev_fork, cudaEventDisableTiming));
+            FQD_CUDA(cudaEventCreateWithFlags(&t.ev_join, cudaEventDisableTiming));
             if (emit_next) {
                 FQD_TRY(arena(ctx, (size_t)npartsN, &t.cursorN));
-                FQD_TRY(arena(ctx, (size_t)npartsN, &t.cntN));
+                FQD_TRY(arena(ctx, (size_t)npartsN + G, &t.cntN));
             }
             FQD_TRY(arena(ctx, (size_t)CTR_WORDS, &t.ctrs));
             FQD_TRY(arena(ctx, (size_t)nper0, &t.oversize));
-            FQD_TRY(arena(ctx, (size_t)4 * G, &t.gath_in));
+            FQD_TRY(arena(ctx, (size_t)4 + 2 * G, &t.gath_in));   // [0..3] this rank's numbers, [4..] edge counts at the fork
             FQD_TRY(arena(ctx, (size_t)4 * G * 2, &t.gath));
             FQD_TRY(arena(ctx, (size_t)STATUS_WORDS * 2, &t.stat_in));
             FQD_TRY(arena(ctx, (size_t)STATUS_WORDS * 2 * G, &t.stat_all));
@@ -238,7 +257,6 @@ int run_sharded_tiles(std::vector<Shard> &S, Exchange *ex, const ShardWorld &W, 
             FQD_CUDA(cudaMemsetAsync(t.cursor0, 0, (size_t)nparts0 * 4, s));
             if (emit_next) FQD_CUDA(cudaMemsetAsync(t.cursorN, 0, (size_t)npartsN * 4, s));
             FQD_CUDA(cudaMemsetAsync(t.ctrs, 0, CTR_WORDS * 4, s));
-            FQD_CUDA(cudaMemsetAsync(t.bitmap, 0, (size_t)bm_words * 4, s));
             // the slab estimate was too small: this rank's (zeroed) counters keep the peers' tile kernels harmless
             // until the ranks have agreed to hand the job over
             return inside ? FQD_OK : RC_FALLBACK_REPLICATED;
@@ -281,7 +299,7 @@ int run_sharded_tiles(std::vector<Shard> &S, Exchange *ex, const ShardWorld &W, 
     // =====================================================================================================
     // phase 3: fill counters to the tile owners; phase 4: dedupe (+ pass 0, + tiles of pass 1) on the owners
     // =====================================================================================================
-    FQD_TRY(alltoall_u32([&](int i) { return T[i].cursor0; }, [&](int i) { return T[i].cnt0; }, nper0));
+    FQD_TRY(exchange_counters([&](int i) { return T[i].cursor0; }, [&](int i) { return T[i].cnt0; }, nper0));
     lap("counters a2a");
     for (int i = 0; i < L; i++) {
         Shard &sh = S[i];
@@ -291,9 +309,10 @@ int run_sharded_tiles(std::vector<Shard> &S, Exchange *ex, const ShardWorld &W, 
             FQD_CUDA(cudaSetDevice(sh.ctx->device));
             cudaStream_t s = sh.ctx->stream;
             const int r = rank_of(i);
+            FQD_CUDA(cudaMemsetAsync(t.bitmap, 0, (size_t)bm_words * 4, s));   // (every rank has entered this job by now)
             TileSource src{};
             for (int g = 0; g < G; g++) src.buf[g] = reinterpret_cast<const uint32_t *>(peer_ptr(sh, g, t.tiles0));
-            src.cnt = t.cnt0; src.G = (uint32_t)G; src.self = (uint32_t)r; src.first_tile = (uint32_t)r * nper0; src.ntiles = nper0;
+            src.cnt = t.cnt0; src.cnt_stride = nper0 + 1; src.G = (uint32_t)G; src.self = (uint32_t)r; src.first_tile = (uint32_t)r * nper0; src.ntiles = nper0;
             src.region = region; src.peer_ldg = peer_ldg;
             DedupeOut out{sh.local.ukey, sh.local.ucount, sh.local.ufirst, t.ctrs + CTR_UNIQUE, t.oversize, t.ctrs + CTR_OVERSIZE, 0,
                           cap_u, t.ctrs + CTR_UNIQUE_OVER};
@@ -400,7 +419,7 @@ int run_sharded_tiles(std::vector<Shard> &S, Exchange *ex, const ShardWorld &W, 
                 const TableRef tr{table, capacity, uslot, sh.ctx->d_ctr};
                 TileSource src{};
                 for (int g = 0; g < G; g++) src.buf[g] = reinterpret_cast<const uint32_t *>(peer_ptr(sh, g, t.tiles0));
-                src.cnt = t.cnt0; src.G = (uint32_t)G; src.self = (uint32_t)r; src.first_tile = (uint32_t)r * nper0; src.ntiles = nper0;
+                src.cnt = t.cnt0; src.cnt_stride = nper0 + 1; src.G = (uint32_t)G; src.self = (uint32_t)r; src.first_tile = (uint32_t)r * nper0; src.ntiles = nper0;
                 src.region = region; src.peer_ldg = peer_ldg;
                 if (n_over)
                     spill_insert_tiles_kernel<K, PW><<<n_over * (uint32_t)G * (TILE_R / 256), 256, 0, s>>>(src, t.oversize, tr, t.ctrs + CTR_CLAIMED);
@@ -484,7 +503,8 @@ int run_sharded_tiles(std::vector<Shard> &S, Exchange *ex, const ShardWorld &W, 
                     inside = inside && in_slab(sh, t.tilesP[b], (size_t)npartsP * region * RW * 4);
                 }
                 FQD_TRY(arena(sh.ctx, (size_t)npartsP, &t.cursorP));
-                FQD_TRY(arena(sh.ctx, (size_t)npartsP, &t.cntP));
+                FQD_TRY(arena(sh.ctx, (size_t)npartsP + G, &t.cntP));
+                if (npartsP > std::max(nparts0, npartsN)) FQD_TRY(arena(sh.ctx, (size_t)npartsP + G, &t.a2a_send));
             }
             if (!inside) return RC_FALLBACK_REPLICATED;
             Forest &f = sh.f;
@@ -492,20 +512,21 @@ int run_sharded_tiles(std::vector<Shard> &S, Exchange *ex, const ShardWorld &W, 
             FQD_TRY(arena(sh.ctx, (size_t)std::max<uint32_t>(t.U, 1), &f.selected));
             FQD_TRY(arena(sh.ctx, (size_t)std::max<uint32_t>(t.U, 1), &t.root_of));
             FQD_TRY(arena(sh.ctx, (size_t)std::max<uint32_t>(t.U, 1), &t.loc_of));
+            const size_t own = std::max<uint32_t>(t.U, 1);   // flags: this rank's own keys only
             if (method == METHOD_DIRECTIONAL) {
                 FQD_TRY(arena(sh.ctx, (size_t)n_ids, &f.parent_one));
-                FQD_TRY(arena(sh.ctx, (size_t)n_ids, &f.dominated));
-                FQD_TRY(arena(sh.ctx, (size_t)n_ids, &f.dead));
+                FQD_TRY(arena(sh.ctx, own, &f.dominated));
+                FQD_TRY(arena(sh.ctx, own, &f.dead));
                 FQD_TRY(arena(sh.ctx, (size_t)n_ids, &f.deadroot));
-                FQD_CUDA(cudaMemsetAsync(f.dominated, 0, n_ids, s));
-                FQD_CUDA(cudaMemsetAsync(f.dead, 0, n_ids, s));
+                FQD_CUDA(cudaMemsetAsync(f.dominated, 0, own, s));
+                FQD_CUDA(cudaMemsetAsync(f.dead, 0, own, s));
                 FQD_CUDA(cudaMemsetAsync(f.deadroot, 0, n_ids, s));
             }
             if (method != METHOD_ADJACENCY) {
                 FQD_TRY(arena(sh.ctx, (size_t)n_ids, &f.best));
-                FQD_TRY(arena(sh.ctx, (size_t)n_ids, &t.linked));
+                FQD_TRY(arena(sh.ctx, own, &t.linked));
                 FQD_CUDA(cudaMemsetAsync(f.best, 0xFF, (size_t)n_ids * 4, s));
-                FQD_CUDA(cudaMemsetAsync(t.linked, 0, n_ids, s));
+                FQD_CUDA(cudaMemsetAsync(t.linked, 0, own, s));
             }
             init_forest_kernel<<<cdiv(n_ids, 256), 256, 0, s>>>(n_ids, f.parent_full, f.parent_one, nullptr);
             sh.tt.launches++;
@@ -518,6 +539,10 @@ int run_sharded_tiles(std::vector<Shard> &S, Exchange *ex, const ShardWorld &W, 
     // =====================================================================================================
     // phase 7: the remaining pigeonhole passes, tile by tile on the tile owners
     // =====================================================================================================
+    // fused jobs: the edges of pass 0 are applied while pass 1 runs (both are latency-bound, they overlap well)
+    const bool overlap_apply = fused && npass_all > first_pass && !getenv("FQD_NO_APPLY_OVERLAP");
+    std::vector<const uint32_t *> early_first(L, nullptr);
+    uint32_t early_stride = 0;
     for (int j = first_pass; j < npass_all; j++) {
         const bool emitted = use_emitted && j == 1;
         const uint32_t nper = emitted ? nperN : nperP, nparts = emitted ? npartsN : npartsP;
@@ -551,8 +576,8 @@ int run_sharded_tiles(std::vector<Shard> &S, Exchange *ex, const ShardWorld &W, 
                 }();
             }
         }
-        FQD_TRY(alltoall_u32([&](int i) { return emitted ? T[i].cursorN : T[i].cursorP; },
-                             [&](int i) { return emitted ? T[i].cntN : T[i].cntP; }, nper));
+        FQD_TRY(exchange_counters([&](int i) { return emitted ? T[i].cursorN : T[i].cursorP; },
+                                  [&](int i) { return emitted ? T[i].cntN : T[i].cntP; }, nper));
         for (int i = 0; i < L; i++) {
             if (T[i].rc != FQD_OK) continue;
             T[i].rc = [&]() -> int {
@@ -560,10 +585,31 @@ int run_sharded_tiles(std::vector<Shard> &S, Exchange *ex, const ShardWorld &W, 
                 TileRank &t = T[i];
                 FQD_CUDA(cudaSetDevice(sh.ctx->device));
                 const int r = rank_of(i);
+                if (j == first_pass && overlap_apply) {
+                    // every rank's edges of the passes so far (pass 0, done inside the dedupe tiles) are complete, and the
+                    // exchange just told how many there are: hook them on a second stream while this pass runs
+                    const uint32_t *cnt = emitted ? t.cntN : t.cntP;
+                    // (the counter block is reused by later passes: keep the G numbers)
+                    copy_strided_kernel<<<1, 32, 0, sh.ctx->stream>>>(t.gath_in + 4, cnt + nper, nper + 1, (uint32_t)G);
+                    FQD_CUDA(cudaGetLastError());
+                    FQD_CUDA(cudaEventRecord(t.ev_fork, sh.ctx->stream));
+                    FQD_CUDA(cudaStreamWaitEvent(sh.ctx->copy_stream, t.ev_fork, 0));
+                    EdgeSource es{};
+                    for (int g = 0; g < G; g++) { es.edges[g] = reinterpret_cast<const uint2 *>(peer_ptr(sh, g, t.edges)); es.cap[g] = cap_e; }
+                    es.n_edges = t.gath_in + 4; es.n_stride = 1; es.G = (uint32_t)G; es.self = (uint32_t)r; es.id_stride = U_max;
+                    EdgeFlags ef{sh.f.dominated, sh.f.dead, t.linked, method == METHOD_HIGHEST ? 1 : 0};
+                    apply_edges_kernel<<<sh.ctx->sm_count * 4, 256, 0, sh.ctx->copy_stream>>>(es, sh.f.parent_full, sh.f.parent_one, ef,
+                                                                                           sh.ctx->d_ctr);
+                    FQD_CUDA(cudaGetLastError());
+                    FQD_CUDA(cudaEventRecord(t.ev_join, sh.ctx->copy_stream));
+                    sh.tt.launches++;
+                    early_first[i] = t.gath_in + 4;
+                    early_stride = 1;
+                }
                 TileSource src{};
                 const uint32_t *mine = emitted ? t.tilesN : t.tilesP[j & 1];
                 for (int g = 0; g < G; g++) src.buf[g] = reinterpret_cast<const uint32_t *>(peer_ptr(sh, g, mine));
-                src.cnt = emitted ? t.cntN : t.cntP;
+                src.cnt = emitted ? t.cntN : t.cntP; src.cnt_stride = nper + 1;
                 src.G = (uint32_t)G; src.self = (uint32_t)r; src.first_tile = (uint32_t)r * nper; src.ntiles = nper;
                 src.region = region; src.peer_ldg = peer_ldg;
                 const EdgeSink sink{t.edges, t.ctrs + CTR_EDGES, cap_e, t.ctrs + CTR_EDGE_OVER};
@@ -602,9 +648,11 @@ int run_sharded_tiles(std::vector<Shard> &S, Exchange *ex, const ShardWorld &W, 
             EdgeSource es{};
             for (int g = 0; g < G; g++) { es.edges[g] = reinterpret_cast<const uint2 *>(peer_ptr(sh, g, t.edges)); es.cap[g] = cap_e; }
             es.n_edges = t.gath; es.n_stride = 4; es.G = (uint32_t)G; es.self = (uint32_t)rank_of(i); es.id_stride = U_max;
+            es.first = early_first[i]; es.first_stride = early_stride;   // (what the overlapped launch has taken care of)
             EdgeFlags ef{sh.f.dominated, sh.f.dead, t.linked, method == METHOD_HIGHEST ? 1 : 0};
             if (npass_all)
                 apply_edges_kernel<<<sh.ctx->sm_count * 8, 256, 0, sh.ctx->stream>>>(es, sh.f.parent_full, sh.f.parent_one, ef, sh.ctx->d_ctr);
+            if (early_first[i]) FQD_CUDA(cudaStreamWaitEvent(sh.ctx->stream, t.ev_join, 0));
             sh.tt.launches++;
             FQD_CUDA(cudaGetLastError());
             return FQD_OK;
@@ -676,18 +724,16 @@ int run_sharded_tiles(std::vector<Shard> &S, Exchange *ex, const ShardWorld &W, 
                 TileRank &t = T[i];
                 FQD_CUDA(cudaSetDevice(sh.ctx->device));
                 cudaStream_t s = sh.ctx->stream;
-                if (method == METHOD_DIRECTIONAL)
-                    deadroot_kernel<<<cdiv(n_ids, 256), 256, 0, s>>>(n_ids, sh.f.dead, t.linked, sh.f.parent_one, sh.f.deadroot);
                 CandParams cp{};
                 cp.U = t.U; cp.U_dev = t.ctrs + CTR_UNIQUE; cp.G = (uint32_t)G; cp.self = (uint32_t)rank_of(i); cp.id_stride = U_max;
                 cp.ukey = sh.local.ukey; cp.ucount = sh.local.ucount;
                 cp.forest = method == METHOD_DIRECTIONAL ? sh.f.parent_one : sh.f.parent_full;
-                cp.dead = sh.f.dead; cp.linked = t.linked; cp.deadroot = sh.f.deadroot;
+                cp.dead = sh.f.dead; cp.linked = t.linked;
                 cp.root_of = t.root_of; cp.loc_of = t.loc_of;
                 cp.cand = t.cand; cp.cand_root = t.cand_root; cp.n_cand = t.ctrs + CTR_CAND; cp.cap = cap_c;
                 cp.method = method;
                 if (t.U) candidates_kernel<K, PW><<<cdiv(t.U, 256), 256, 0, s>>>(cp);
-                sh.tt.launches += 2;
+                sh.tt.launches++;
                 FQD_CUDA(cudaGetLastError());
                 return FQD_OK;
             }();
@@ -707,6 +753,7 @@ int run_sharded_tiles(std::vector<Shard> &S, Exchange *ex, const ShardWorld &W, 
                 }
                 bp.n_cand = t.gath + (size_t)4 * G + 1; bp.n_stride = 4; bp.G = (uint32_t)G;
                 bp.best = sh.f.best;
+                bp.deadroot = sh.f.deadroot;
                 for (int k = 0; k < 256; k++) bp.rank_of_code[k] = codec.rank[k];
                 best_candidate_kernel<K, PW><<<sh.ctx->sm_count * 4, 256, 0, sh.ctx->stream>>>(bp);
                 sh.tt.launches++;
@@ -720,7 +767,6 @@ int run_sharded_tiles(std::vector<Shard> &S, Exchange *ex, const ShardWorld &W, 
     // =====================================================================================================
     // phase 10: the keys of a rank decide; keep bits go to the rank that holds the record
     // =====================================================================================================
-    if (!ex) FQD_TRY(sync_all(S));   // (virtual ranks: every bitmap was zeroed long ago, every forest is complete)
     for (int i = 0; i < L; i++) {
         if (T[i].rc != FQD_OK) continue;
         T[i].rc = [&]() -> int {
@@ -735,11 +781,7 @@ int run_sharded_tiles(std::vector<Shard> &S, Exchange *ex, const ShardWorld &W, 
             sp.dominated = sh.f.dominated; sp.dead = sh.f.dead; sp.linked = t.linked; sp.deadroot = sh.f.deadroot;
             sp.state = adj_state[i];
             sp.selected = sh.f.selected;
-            for (int g = 0; g < G; g++) {
-                sp.bitmap[g] = reinterpret_cast<uint32_t *>(peer_ptr(sh, g, t.bitmap));
-                sp.base[g] = (uint32_t)W.base[g];
-            }
-            sp.base[G] = (uint32_t)W.base[G];
+            sp.bitmap = t.bitmap; sp.bit_base = (uint32_t)W.base[0];
             sp.method = method; sp.ctr = sh.ctx->d_ctr;
             FQD_CUDA(cudaMemsetAsync(&sh.ctx->d_ctr->n_selected, 0, 4, s));
             if (t.U) select_own_kernel<<<cdiv(t.U, 256), 256, 0, s>>>(sp);
@@ -753,13 +795,26 @@ int run_sharded_tiles(std::vector<Shard> &S, Exchange *ex, const ShardWorld &W, 
     //      handed to the caller behind the exchange, ahead of the one host synchronisation ----
     {
         const int rc = agree([&](int i) -> int {
-            if (S[i].job.bitmap && S[i].job.n)
-                FQD_CUDA(cudaMemcpyAsync(S[i].job.bitmap, T[i].bitmap, (size_t)cdiv(S[i].job.n, 32) * 4, cudaMemcpyDeviceToDevice,
-                                         S[i].ctx->stream));
+            // behind the exchange every rank's bitmap is complete: OR the peers' slices of this rank's records together
+            if (S[i].job.bitmap && S[i].job.n) {
+                MergeParams mp{};
+                for (int g = 0; g < G; g++) mp.src[g] = reinterpret_cast<const uint32_t *>(peer_ptr(S[i], g, T[i].bitmap));
+                mp.G = (uint32_t)G;
+                mp.bit_lo = (uint32_t)(W.base[rank_of(i)] - W.base[0]);
+                mp.n = (uint32_t)S[i].job.n;
+                mp.src_words = bm_words;
+                mp.dst = S[i].job.bitmap;
+                merge_bitmaps_kernel<<<cdiv(cdiv(S[i].job.n, 32), 256), 256, 0, S[i].ctx->stream>>>(mp);
+                FQD_CUDA(cudaGetLastError());
+                S[i].tt.launches++;
+            }
             FQD_CUDA(cudaEventRecord(T[i].e1, S[i].ctx->stream));
             return FQD_OK;
         });
         if (rc != FQD_OK) return rc;
+        // nobody may reuse its arena (the next job, of any kind) while a peer still merges: one more rendezvous, on the
+        // streams only
+        FQD_TRY(allgather_u32([&](int i) { return T[i].gath_in; }, [&](int i) { return T[i].gath; }, 1));
     }
     uint64_t n_sel = 0, n_cand_pairs = 0, merges = 0, late = 0, U_total = 0;
     for (int g = 0; g < G; g++) {
