@@ -524,7 +524,9 @@ def run_ours(args, rank, world, local_rank):
                          "streaming_passes": tiled_passes}}
 
     # ---- CPU baseline on a bounded sample of the same workload ----
-    sample = min(n, env_int("FQD_CPU_SAMPLE", 4_000_000))
+    # about 15-25 s of single-core reference work, whatever the configuration
+    us_read = REF_US_PER_READ.get(cfg.name, 3.5) * (6.0 if cfg.use_edit_distance and cfg.max_distance >= 2 else 1.0)
+    sample = min(n, env_int("FQD_CPU_SAMPLE", 0) or int(min(4_000_000, max(250_000, 14.0 / (us_read * 1e-6)))))
     uniq_s, secs, split, kind = time_reference(
         cfg, host_keys.array[:sample], None if host_quals is None else host_quals.array[:sample])
     cpu = {"value": uniq_s / secs, "unit": UNIT, "cores": 1, "kind": kind,

@@ -702,8 +702,8 @@ struct EdgeFlags {
     int any_edge;         // highest_count: `linked` for every edge
 };
 
-constexpr int APPLY_UNROLL = 4;   // edges a thread fetches (from a peer's HBM) before it hooks them
-
+// APPLY_UNROLL: edges a thread fetches (from a peer's HBM) before it hooks them
+template <int APPLY_UNROLL = 1>
 static __global__ void __launch_bounds__(256) apply_edges_kernel(const __grid_constant__ EdgeSource E, uint32_t *parent_full,
                                                                  uint32_t *parent_one, const __grid_constant__ EdgeFlags F,
                                                                  DevCounters *ctr)

@@ -639,7 +639,7 @@ int stage_passes(fqd_context *ctx, const DeviceJob &job, const Codec &codec, con
             }
             FQD_CUDA(cudaEventRecord(cev[2 * j], s));
             bucket_tile_kernel<K, PW><<<qp.nparts, TILE_THREADS, 0, s>>>(single_source(qp), pp, sink);
-            apply_edges_kernel<<<ctx->sm_count * 8, 256, 0, s>>>(single_edges(sink.edges, sink.n_edges, sink.cap), f.parent_full,
+            apply_edges_kernel<1><<<ctx->sm_count * 8, 256, 0, s>>>(single_edges(sink.edges, sink.n_edges, sink.cap), f.parent_full,
                                                                 f.parent_one, EdgeFlags{}, ctx->d_ctr);
             FQD_CUDA(cudaEventRecord(cev[2 * j + 1], s));
             FQD_CUDA(cudaGetLastError());
@@ -823,7 +823,7 @@ int run_typed(fqd_context *ctx, const DeviceJob &job, const Codec &codec, fqd_cl
     FQD_CUDA(cudaEventRecord(ev[6], s));
     int first_pass = 0;
     if (fp.done && U > 1) {
-        apply_edges_kernel<<<ctx->sm_count * 8, 256, 0, s>>>(single_edges(fp.edges, fp.aux, fp.edge_cap), f.parent_full, f.parent_one,
+        apply_edges_kernel<1><<<ctx->sm_count * 8, 256, 0, s>>>(single_edges(fp.edges, fp.aux, fp.edge_cap), f.parent_full, f.parent_one,
                                                             EdgeFlags{}, ctx->d_ctr);
         tt.launches++;
         tt.pass0_fused = true;

@@ -48,7 +48,7 @@ def main():
         env = dict(VARIANTS.get(name.split("=")[0], {}))
         if "=" in name:
             env.update(kv.split(":") for kv in name.split("=", 1)[1].split(","))
-        for k in ("FQD_PEER_LDG", "FQD_SHARD_FULL_REGIONS", "FQD_SHARD_REPLICATED", "FQD_TRACE"):
+        for k in [k for k in os.environ if k.startswith("FQD_")]:
             os.environ.pop(k, None)
         os.environ.update(env)
         times = []
