@@ -17,7 +17,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libfqd_b200.so")
 
 FQD_OK = 0
-ERR_ARG, ERR_PHRED, ERR_CUDA, ERR_NOMEM, ERR_LOOKUP, ERR_UNSUPPORTED, ERR_NCCL = range(1, 8)
+ERR_ARG, ERR_PHRED, ERR_CUDA, ERR_NOMEM, ERR_LOOKUP, ERR_UNSUPPORTED, ERR_NCCL, ERR_FASTQ, ERR_IO = range(1, 10)
 MEM_HOST, MEM_DEVICE = 0, 1
 METHODS = {"highest_count": 0, "adjacency": 1, "directional": 2}
 
@@ -37,6 +37,26 @@ class FqdPhredError(ValueError):
         super().__init__(msg)
         self.record = record
         self.char = char
+
+
+class FqdFastqError(Exception):
+    """Malformed FASTQ input / inputs not in sync (the frontend re-raises it as dnaio's FastqFormatError)."""
+
+
+class Slice(Structure):
+    """include/fqd_b200.h fqd_slice: a Python slice object, has_x == 0 meaning None."""
+    _fields_ = [("start", ctypes.c_int64), ("stop", ctypes.c_int64), ("step", ctypes.c_int64),
+                ("has_start", c_uint8), ("has_stop", c_uint8), ("has_step", c_uint8), ("reserved", c_uint8 * 5)]
+
+    @classmethod
+    def from_python(cls, slc):
+        out = cls()
+        for name in ("start", "stop", "step"):
+            v = getattr(slc, name)
+            if v is not None:
+                setattr(out, name, int(v))
+                setattr(out, "has_" + name, 1)
+        return out
 
 
 class ClusterJob(Structure):
@@ -84,6 +104,8 @@ EXPORTS = [
     "fqd_nccl_unique_id", "fqd_comm_create", "fqd_comm_destroy", "fqd_cluster_sharded",
     "fqd_cluster_sharded_local",
     "fqd_average_error_rate", "fqd_within_distance", "fqd_int_peak",
+    "fqd_fastq_scan_open", "fqd_fastq_scan_records", "fqd_fastq_scan_keys", "fqd_fastq_scan_quals",
+    "fqd_fastq_scan_free", "fqd_fastq_emit",
     "fqd_trie_new", "fqd_trie_free", "fqd_trie_add_sequence", "fqd_trie_contains_sequence",
     "fqd_trie_pop_cluster", "fqd_trie_cluster_item", "fqd_trie_number_of_sequences",
     "fqd_trie_alphabet", "fqd_trie_memory_size", "fqd_trie_raw_stats",
@@ -132,6 +154,15 @@ def load():
                                            c_void_p, POINTER(c_uint64), POINTER(c_uint32)]
     lib.fqd_within_distance.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                         c_uint64, c_int32, c_int32, c_void_p]
+    lib.fqd_fastq_scan_open.argtypes = [POINTER(c_char_p), c_int, POINTER(Slice), c_int, c_int, POINTER(c_void_p)]
+    lib.fqd_fastq_scan_records.argtypes = [c_void_p]
+    lib.fqd_fastq_scan_records.restype = c_uint64
+    lib.fqd_fastq_scan_keys.argtypes = [c_void_p, POINTER(c_void_p), POINTER(c_void_p), POINTER(c_uint32)]
+    lib.fqd_fastq_scan_quals.argtypes = [c_void_p, POINTER(c_void_p), POINTER(c_void_p), POINTER(c_uint32)]
+    lib.fqd_fastq_scan_free.argtypes = [c_void_p]
+    lib.fqd_fastq_scan_free.restype = None
+    lib.fqd_fastq_emit.argtypes = [POINTER(c_char_p), POINTER(c_char_p), c_int, c_void_p, c_uint64, c_int,
+                                   POINTER(c_uint64)]
     _lib = lib
     return lib
 
@@ -153,7 +184,75 @@ def check(rc, stats=None):
         raise NotImplementedError(msg)
     if rc == ERR_CUDA:
         raise FqdCudaError(msg)
+    if rc == ERR_FASTQ:
+        raise FqdFastqError(msg)
+    if rc == ERR_IO:
+        raise OSError(msg)
     raise FqdError(msg)
+
+
+class FastqScan:
+    """Pass 1 over the input files in native code (``fqd_fastq_scan_open``): per record tuple the key (and quality)
+    rows ``deduplicate_cluster`` builds, as numpy views on the library's buffers."""
+
+    def __init__(self, paths, slices=None, want_quals=False, threads=0):
+        self.lib = load()
+        n = len(paths)
+        c_paths = (c_char_p * n)(*[os.fsencode(p) for p in paths])
+        c_slices = None
+        if slices:
+            c_slices = (Slice * n)(*[Slice.from_python(s) for s in slices])
+        h = c_void_p()
+        check(self.lib.fqd_fastq_scan_open(c_paths, n, c_slices, int(bool(want_quals)), int(threads), byref(h)))
+        self.handle = h
+        self.n_records = int(self.lib.fqd_fastq_scan_records(h))
+        self.keys = self._rows(self.lib.fqd_fastq_scan_keys)
+        self.quals = self._rows(self.lib.fqd_fastq_scan_quals) if want_quals else None
+
+    def _rows(self, getter):
+        data, off, stride = c_void_p(), c_void_p(), c_uint32()
+        check(getter(self.handle, byref(data), byref(off), byref(stride)))
+        n = self.n_records
+        if off.value:
+            offsets = np.ctypeslib.as_array(ctypes.cast(off, POINTER(c_uint64)), shape=(n + 1,))
+            nbytes = int(offsets[n]) if n else 0
+            flat = np.ctypeslib.as_array(ctypes.cast(data, POINTER(c_uint8)), shape=(max(nbytes, 1),))
+            return flat, offsets
+        width = int(stride.value)
+        if n == 0 or width == 0:
+            return np.zeros(1, dtype=np.uint8), np.zeros(n + 1, dtype=np.uint64)
+        return np.ctypeslib.as_array(ctypes.cast(data, POINTER(c_uint8)), shape=(n, width))
+
+    def close(self):
+        if self.handle:
+            self.keys = self.quals = None
+            self.lib.fqd_fastq_scan_free(self.handle)
+            self.handle = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def fastq_emit(in_paths, out_paths, keep_bitmap, n_records, threads=0):
+    """Pass 2 in native code (``fqd_fastq_emit``): writes the record tuples whose bit is set; returns their number."""
+    lib = load()
+    n = len(in_paths)
+    c_in = (c_char_p * n)(*[os.fsencode(p) for p in in_paths])
+    c_out = (c_char_p * n)(*[os.fsencode(p) for p in out_paths])
+    words = np.ascontiguousarray(keep_bitmap, dtype=np.uint32)
+    written = c_uint64()
+    check(lib.fqd_fastq_emit(c_in, c_out, n, words.ctypes.data if len(words) else None, int(n_records), int(threads),
+                             byref(written)))
+    return int(written.value)
 
 
 class Context:

@@ -62,15 +62,25 @@ def _nvcc(item):
     return obj, r.stderr
 
 
+def _gxx(src):
+    """Host-only C++ (the native FASTQ passes): plain g++."""
+    obj = os.path.join(OBJ, os.path.splitext(src)[0] + ".o")
+    srcp = os.path.join(CSRC, src)
+    if _stale(obj, [srcp, os.path.join(CSRC, "..", "..", "include", "fqd_b200.h")]):
+        subprocess.run(["g++", "-O3", "-std=c++17", "-fPIC", "-pthread", "-Wall", "-Wno-stringop-overflow", "-c", srcp, "-o", obj], check=True)
+    return obj
+
+
 def build_library(verbose=False):
     os.makedirs(OBJ, exist_ok=True)
     sources = [s for s in CU_SOURCES if os.path.exists(os.path.join(CSRC, s[0]))]
     with concurrent.futures.ThreadPoolExecutor(max_workers=min(len(sources), os.cpu_count() or 4)) as ex:
         objs = [o for o, _ in ex.map(_nvcc, sources)]
+    objs.append(_gxx("fastq_native.cpp"))
     if _stale(LIB, objs):
         # static cudart (nvcc's default), deliberately: the library must not depend on WHICH libcudart.so.12
         # the host process has mapped (a torch process brings the 12.8 runtime, this toolkit is 12.9)
-        cmd = ["nvcc", "-shared", "-o", LIB + ".tmp"] + objs
+        cmd = ["nvcc", "-shared", "-o", LIB + ".tmp"] + objs + ["-lz", "-lpthread"]
         subprocess.run(cmd, check=True)
         os.replace(LIB + ".tmp", LIB)   # never a half-written library in the tree
     if verbose:

@@ -251,15 +251,63 @@ size_t fqd_trie_alphabet(const fqd_trie *t, uint8_t *buf, size_t cap)
     return n;
 }
 
-// The new path has no trie nodes.  memory_size reports the bytes of the staged sequences
-// (+8 per entry, the reference's leaf header) and raw_stats a well-formed all-leaf layer 0,
-// so that trie_stats (reference __init__.py:133-157, -v only) keeps working.
+// The new path has no trie nodes, but the node layout of the reference's trie is a function of the key set alone
+// (one level per character, a key that is alone below a node is a leaf holding its suffix, a node has as many
+// child slots as the largest alphabet index below it + 1: TrieNode_AddSequence, _triemodule.c:222-288).  raw_stats
+// (:929-964) and memory_size (:909-913) therefore report exactly what the reference's trie over the same sequences
+// holds when freshly built, so trie_stats (__init__.py:133-157, -v) prints the reference's table.
+}  // extern "C"
+
+namespace {
+
+struct TrieShape {
+    const fqd_trie *t;
+    std::vector<const std::string *> keys;   // byte-lexicographic
+    uint64_t *stats;                         // rows of row_len counters, may be null
+    size_t row_len, rows;
+    uint64_t bytes = 0;
+
+    void node(size_t lo, size_t hi, size_t depth)
+    {
+        if (hi - lo == 1) {   // a leaf: header + the rest of the key (TrieNode_GetMemorySize, :553-570)
+            bytes += 8 + (keys[lo]->size() - depth);
+            if (stats && depth < rows) stats[depth * row_len] += 1;
+            return;
+        }
+        // keys equal to the prefix itself (at most one, first in the range) count at this node and have no child
+        size_t i = lo;
+        if (keys[i]->size() == depth) i++;
+        uint32_t slots = 0;
+        for (size_t k = i; k < hi; k++) slots = std::max<uint32_t>(slots, (uint32_t)t->to_index[(uint8_t)(*keys[k])[depth]] + 1u);
+        bytes += 8 + 8ull * slots;
+        if (stats && depth < rows && slots < row_len) stats[depth * row_len + slots] += 1;
+        while (i < hi) {
+            const char c = (*keys[i])[depth];
+            size_t j = i + 1;
+            while (j < hi && (*keys[j])[depth] == c) j++;
+            node(i, j, depth + 1);
+            i = j;
+        }
+    }
+};
+
+uint64_t trie_shape(const fqd_trie *t, uint64_t *stats, size_t row_len, size_t rows)
+{
+    TrieShape sh{t, {}, stats, row_len, rows};
+    sh.keys.reserve(t->present.size());
+    for (const auto &kv : t->present) sh.keys.push_back(&kv.first);
+    if (!sh.keys.empty()) sh.node(0, sh.keys.size(), 0);
+    return sh.bytes;
+}
+
+}  // namespace
+
+extern "C" {
+
 uint64_t fqd_trie_memory_size(const fqd_trie *t)
 {
     if (!t) return 0;
-    uint64_t b = 0;
-    for (const auto &kv : t->present) b += 8 + kv.first.size();
-    return b;
+    return trie_shape(t, nullptr, 0, 0);
 }
 
 size_t fqd_trie_raw_stats(const fqd_trie *t, uint64_t *buf, size_t cap, size_t *row_len)
@@ -267,10 +315,9 @@ size_t fqd_trie_raw_stats(const fqd_trie *t, uint64_t *buf, size_t cap, size_t *
     if (!t) return 0;
     const size_t rl = t->alphabet.size() + 1, rows = (size_t)t->max_sequence_size + 1;
     if (row_len) *row_len = rl;
-    if (buf) {
-        const size_t total = std::min(cap, rl * rows);
-        memset(buf, 0, total * sizeof(uint64_t));
-        if (total) buf[0] = t->present.size();
+    if (buf && cap >= rl * rows) {
+        memset(buf, 0, rl * rows * sizeof(uint64_t));
+        trie_shape(t, buf, rl, rows);
     }
     return rows;
 }

@@ -24,7 +24,7 @@ from typing import Callable, Dict, Iterable, Iterator, List, Optional, Tuple
 
 import numpy as np
 
-from . import fastq_io
+from . import _native, fastq_io
 from ._trie import Trie
 from .clustering import cluster_keys
 
@@ -160,6 +160,27 @@ def filter_fastq_files_on_bitmap(input_files: List[str], output_files: List[str]
                     out.write(record.fastq_bytes())
 
 
+def structure_stats(result) -> str:
+    """The ``-v`` report of the structure that replaces the trie (the reference prints ``trie_stats`` here,
+    ``:260-264``): the packed unique-key table, the shared-memory tiles and the pigeonhole passes of the job."""
+    st = result.stats
+    n, u = result.total_records, result.number_of_uniques
+    key_bytes = 4 * st["key_words"]
+    flags = st["plan_flags"]
+    lines = [
+        f"unique keys       {u:>12}  ({st['key_bits']} bit planes x {st['key_words'] // max(st['key_bits'], 1)} words"
+        f" = {key_bytes} B packed key + 4 B count + 4 B first index = {(key_bytes + 8) * u / 1024 ** 3:.2} GiB)",
+        f"records           {n:>12}  ({result.discarded_records} discarded by the quality filter)",
+        f"exact dedupe      {'shared-memory tiles of 512 records, ~60 % full' if flags & 1 else 'one open-addressing table in HBM'}",
+        f"pigeonhole passes {st['n_passes']:>12}  "
+        f"({'tiles' if flags & 2 else 'counting sort by block hash'}{', pass 0 inside the dedupe tiles' if flags & 4 else ''})",
+        f"candidate pairs   {st['candidate_pairs']:>12}  ({st['candidate_pairs'] / max(u, 1):.2f} per unique key, all verified)",
+        f"clusters          {result.number_of_clusters:>12}",
+        f"kernel launches   {st['launches']:>12}  ({st['ms_total']:.2f} ms on the device)",
+    ]
+    return "\n".join(lines) + "\n"
+
+
 def deduplicate_cluster(
     input_files: List[str],
     output_files: List[str],
@@ -177,52 +198,56 @@ def deduplicate_cluster(
         raise ValueError(f"Amount of check lengths ({len(check_slices)}) "
                          f"must be equal to the amount of input files "
                          f"({len(input_files)}). ")
-    joinfunc = joinfunc_from_check_slices(check_slices) if check_slices else "".join
     filter_on_quality = max_average_error_rate < 1.0
     timer = Timer()
     logger = logging.getLogger("fastqdedup")
 
-    # pass 1 (host): collect the key and quality slices of every record tuple
-    key_buf = bytearray()
-    qual_buf = bytearray()
-    key_off = [0]
-    qual_off = [0]
-    for record_tuple in fastq_files_to_records(input_files):
-        if filter_on_quality:
-            qual_buf += joinfunc(r.qualities for r in record_tuple
-                                 if r.qualities is not None).encode("latin-1")
-            qual_off.append(len(qual_buf))
-        key_buf += joinfunc(r.sequence for r in record_tuple).encode("latin-1")
-        key_off.append(len(key_buf))
-    keys = (np.frombuffer(bytes(key_buf), dtype=np.uint8), np.asarray(key_off, dtype=np.uint64))
-    quals = None
-    if filter_on_quality:
-        quals = (np.frombuffer(bytes(qual_buf), dtype=np.uint8),
-                 np.asarray(qual_off, dtype=np.uint64))
-
-    method = _METHOD_OF_FUNC.get(cluster_dissection_func)
-    if method is not None:
-        # the batched GPU job: filter + exact dedupe + neighbour search + dissection
-        result = cluster_keys(keys, quals, max_distance, use_edit_distance, method,
-                              max_average_error_rate, want_uniques=False)
-        if filter_on_quality:
-            logger.info(
-                f"{result.discarded_records} records out of {result.total_records} "
-                f"records had an error rate higher than {max_average_error_rate} "
-                f"and were discarded.")
-        logger.info(f"Processed {result.number_of_sequences} sequences. "
-                    f"({timer.get_difference()})")
-        logger.info(f"Found {result.number_selected} distinct reads "
-                    f"in {result.number_of_clusters} clusters."
-                    f"({timer.get_difference()})")
-        keep = result.keep_mask()
-    else:
-        keep = _deduplicate_with_callable(keys, quals, max_distance, max_average_error_rate,
-                                          cluster_dissection_func, use_edit_distance,
-                                          filter_on_quality, logger, timer)
-    filter_fastq_files_on_bitmap(input_files, output_files, keep)
+    # pass 1 (host, native: csrc/fastq_native.cpp): reader + parser threads per file, mates check, the key and
+    # quality slices of every record tuple written straight into the buffers of the GPU job
+    try:
+        scan = _native.FastqScan(input_files, check_slices or None, want_quals=filter_on_quality)
+    except _native.FqdFastqError as e:
+        raise fastq_io.FastqFormatError(str(e), line=None) from None
+    with scan:
+        keys, quals = scan.keys, scan.quals
+        n_records = scan.n_records
+        method = _METHOD_OF_FUNC.get(cluster_dissection_func)
+        if method is not None:
+            # the batched GPU job: filter + exact dedupe + neighbour search + dissection
+            result = cluster_keys(keys, quals, max_distance, use_edit_distance, method,
+                                  max_average_error_rate, want_uniques=False)
+            if filter_on_quality:
+                logger.info(
+                    f"{result.discarded_records} records out of {result.total_records} "
+                    f"records had an error rate higher than {max_average_error_rate} "
+                    f"and were discarded.")
+            logger.info(f"Processed {result.number_of_sequences} sequences. "
+                        f"({timer.get_difference()})")
+            if logger.level <= logging.DEBUG:
+                logger.debug("\n" + structure_stats(result))
+            logger.info(f"Found {result.number_selected} distinct reads "
+                        f"in {result.number_of_clusters} clusters."
+                        f"({timer.get_difference()})")
+            bitmap = result.keep_bitmap
+        else:
+            keep = _deduplicate_with_callable(_as_ragged(keys), None if quals is None else _as_ragged(quals),
+                                              max_distance, max_average_error_rate,
+                                              cluster_dissection_func, use_edit_distance,
+                                              filter_on_quality, logger, timer)
+            words = np.packbits(keep, bitorder="little")
+            bitmap = np.concatenate([words, np.zeros((-len(words)) % 4, dtype=np.uint8)]).view(np.uint32)
+    # pass 2 (host, native): the record tuples whose bit is set; .gz outputs compressed by the worker threads
+    _native.fastq_emit(input_files, output_files, bitmap, n_records)
     logger.info(f"Filtered FASTQ files based on distinct reads from each cluster. "
                 f"({timer.get_difference()}) ")
+
+
+def _as_ragged(rows):
+    """(flat, offsets) view of the scan's rows (2-D when every row has the same length)."""
+    if isinstance(rows, tuple):
+        return rows
+    n, width = rows.shape
+    return rows.reshape(-1), np.arange(n + 1, dtype=np.uint64) * np.uint64(width)
 
 
 def _deduplicate_with_callable(keys, quals, max_distance, max_average_error_rate, func,

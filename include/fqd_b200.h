@@ -31,6 +31,9 @@ extern "C" {
                                   (src/fastqdedup/_triemodule.c:794-797)                 */
 #define FQD_ERR_UNSUPPORTED 6  /* key longer / alphabet larger than this build supports  */
 #define FQD_ERR_NCCL 7
+#define FQD_ERR_FASTQ 8        /* dnaio.FastqFormatError: malformed record, inputs not in sync
+                                  (src/fastqdedup/__init__.py:181-185)                     */
+#define FQD_ERR_IO 9           /* OSError: a file cannot be opened / read / written         */
 
 #define FQD_METHOD_HIGHEST_COUNT 0 /* cluster_dissection_highest_count, __init__.py:94-102 */
 #define FQD_METHOD_ADJACENCY 1     /* cluster_dissection_adjacency,     __init__.py:105-122 */
@@ -209,6 +212,43 @@ int fqd_average_error_rate(fqd_context *ctx, const uint8_t *phred, const uint64_
 int fqd_within_distance(fqd_context *ctx, const uint8_t *a, const uint64_t *a_offsets,
                         const uint8_t *b, const uint64_t *b_offsets, uint64_t n_pairs,
                         int32_t max_distance, int32_t use_edit_distance, uint8_t *out);
+
+/* ------------------------------------------------------------------------------------
+ * The two FASTQ passes around the job, native (host threads + zlib; no GPU involved).
+ * ------------------------------------------------------------------------------------ */
+
+/* A Python slice object (the --check-lengths of one input file, length_string_to_slices,
+ * src/fastqdedup/__init__.py:364-375): has_x == 0 means None. */
+typedef struct {
+    int64_t start, stop, step;
+    uint8_t has_start, has_stop, has_step;
+    uint8_t reserved[5];
+} fqd_slice;
+
+typedef struct fqd_fastq_scan fqd_fastq_scan;
+
+/* Pass 1 (fastq_files_to_records + joinfunc_from_check_slices, __init__.py:170-186, :160-167, and the key /
+ * quality construction of deduplicate_cluster, :243-251): reads the n_files FASTQ files (plain or gzip) in lock
+ * step, stops at the shortest, checks that the records of a tuple are mates (FQD_ERR_FASTQ "FASTQ files not in
+ * sync: <names> are not mates.") and builds, per record tuple, key = concatenation over the files of
+ * sequence[slice of that file] and, with want_quals, the same slices of the quality strings.  slices == NULL: whole
+ * sequences.  threads <= 0: one per core (at most 16), besides a reader and a parser thread per file. */
+int fqd_fastq_scan_open(const char *const *paths, int n_files, const fqd_slice *slices, int want_quals, int threads,
+                        fqd_fastq_scan **out);
+uint64_t fqd_fastq_scan_records(const fqd_fastq_scan *scan);
+/* The rows, in the form fqd_cluster_job takes (memory_space HOST): *offsets != NULL: ragged rows
+ * keys[offsets[t] .. offsets[t+1]); else every row has *stride bytes.  Owned by the scan. */
+int fqd_fastq_scan_keys(const fqd_fastq_scan *scan, const uint8_t **keys, const uint64_t **offsets, uint32_t *stride);
+int fqd_fastq_scan_quals(const fqd_fastq_scan *scan, const uint8_t **quals, const uint64_t **offsets, uint32_t *stride);
+void fqd_fastq_scan_free(fqd_fastq_scan *scan);
+
+/* Pass 2 (filter_fastq_files_on_set, __init__.py:189-206): re-reads the inputs and writes record tuple t of every
+ * file to the matching output file iff bit t of keep_bitmap (fqd_cluster) is set, as "@name\nseq\n+\nqual\n"
+ * (dnaio's fastq_bytes()).  Outputs ending in .gz are compressed at level 1 (__init__.py:197-198) by the worker
+ * threads, one gzip member per block, written in order: the compression is off the serial path and the
+ * decompressed bytes are the reference's. */
+int fqd_fastq_emit(const char *const *in_paths, const char *const *out_paths, int n_files, const uint32_t *keep_bitmap,
+                   uint64_t n_records, int threads, uint64_t *n_written);
 
 /* Measurement aid (not on the product path): the integer-issue peak of the
  * context's GPU in thread-level operations per second, from dependent-free instruction streams --

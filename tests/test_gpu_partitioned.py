@@ -202,3 +202,26 @@ def test_streaming_plan_with_record_multiplicities(gpu_ctx, oracle):
         sel_got = sorted(strings[i] for i in got.selected_first.tolist())
         sel_want = sorted(expanded[i] for i in want["selected_first"].tolist())
         assert sel_got == sel_want
+
+
+def test_more_oversize_partitions_than_a_launch_grid_has_rows(gpu_ctx):
+    """~58 M records of ~96 k keys with 600 copies each: every occupied 512-record tile is oversize, and there are
+    more than 65535 of them -- what gridDim.y could hold when the spill launch still put the partition index there.
+    Checked against the known answer (keys built so that no two are within distance 1: every key its own cluster,
+    all selected, first occurrence = its index in the first round) instead of the oracle."""
+    os.environ["FQD_TILE_FILL_PCT"] = "90"
+    try:
+        n_keys, copies, half = 96_000, 600, 10
+        digits = ((np.arange(n_keys)[:, None] >> (2 * np.arange(half)[None, :])) & 3).astype(np.uint8)
+        base = np.frombuffer(b"ACGT", dtype=np.uint8)[np.concatenate([digits, digits], axis=1)]   # two keys differ in >= 2 symbols
+        keys = np.tile(base, (copies, 1))
+        got = cluster_keys(keys, None, 1, False, "directional", 1.0, context=gpu_ctx, want_uniques=True)
+    finally:
+        del os.environ["FQD_TILE_FILL_PCT"]
+    n = n_keys * copies
+    assert got.total_records == n and got.number_of_uniques == n_keys
+    assert got.number_of_clusters == n_keys and got.number_selected == n_keys
+    assert np.array_equal(got.first, np.arange(n_keys, dtype=np.uint64))
+    assert np.all(got.count == copies) and np.all(got.selected)
+    assert np.array_equal(np.nonzero(got.keep_mask())[0], np.arange(n_keys))
+    assert got.stats["plan_flags"] & 1

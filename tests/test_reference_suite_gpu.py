@@ -281,3 +281,22 @@ def test_dissection_yield_order_equals_reference(pkg, reference):
             for d, e in ((1, False), (2, False), (1, True)):
                 assert list(pkg.CLUSTER_DISSECTION_METHODS[name](cluster, d, e)) == \
                     list(reference.CLUSTER_DISSECTION_METHODS[name](cluster, d, e)), (name, d, e)
+
+
+def test_trie_stats_report_equals_reference(pkg, reference):
+    """raw_stats / memory_size (-v report, reference __init__.py:133-157): the shim has no nodes, it derives the node
+    layout the reference's trie holds for the same sequences."""
+    import random
+    rng = random.Random(5)
+    for alphabet, lo, hi, n in (("ACGTN", 4, 12, 400), ("ACGTN", 1, 6, 300), ("", 2, 9, 200), ("acgtRYKM", 3, 10, 250)):
+        letters = alphabet or "ACGT"
+        seqs = ["".join(rng.choice(letters) for _ in range(rng.randint(lo, hi))) for _ in range(n)]
+        seqs += seqs[: n // 5] + [s[: len(s) // 2] for s in seqs[: n // 10] if len(s) > 1]     # duplicates, proper prefixes
+        ours, ref = pkg.Trie(alphabet=alphabet), reference.Trie(alphabet=alphabet)
+        for s in seqs:
+            ours.add_sequence(s)
+            ref.add_sequence(s)
+        assert ours.alphabet == ref.alphabet
+        assert ours.raw_stats() == ref.raw_stats()
+        assert ours.memory_size() == ref.memory_size()
+        assert pkg.trie_stats(ours) == reference.trie_stats(ref)
