@@ -105,7 +105,7 @@ EXPORTS = [
     "fqd_cluster_sharded_local",
     "fqd_average_error_rate", "fqd_within_distance", "fqd_int_peak",
     "fqd_fastq_scan_open", "fqd_fastq_scan_records", "fqd_fastq_scan_keys", "fqd_fastq_scan_quals",
-    "fqd_fastq_scan_free", "fqd_fastq_emit",
+    "fqd_fastq_scan_free", "fqd_fastq_emit", "fqd_pack_keys",
     "fqd_trie_new", "fqd_trie_free", "fqd_trie_add_sequence", "fqd_trie_contains_sequence",
     "fqd_trie_pop_cluster", "fqd_trie_cluster_item", "fqd_trie_number_of_sequences",
     "fqd_trie_alphabet", "fqd_trie_memory_size", "fqd_trie_raw_stats",
@@ -163,6 +163,7 @@ def load():
     lib.fqd_fastq_scan_free.restype = None
     lib.fqd_fastq_emit.argtypes = [POINTER(c_char_p), POINTER(c_char_p), c_int, c_void_p, c_uint64, c_int,
                                    POINTER(c_uint64)]
+    lib.fqd_pack_keys.argtypes = [c_void_p, c_uint64, c_uint32, c_uint32, c_void_p, POINTER(c_uint64)]
     _lib = lib
     return lib
 

@@ -77,6 +77,7 @@ def build_library(verbose=False):
     with concurrent.futures.ThreadPoolExecutor(max_workers=min(len(sources), os.cpu_count() or 4)) as ex:
         objs = [o for o, _ in ex.map(_nvcc, sources)]
     objs.append(_gxx("fastq_native.cpp"))
+    objs.append(_gxx("host_pack.cpp"))
     if _stale(LIB, objs):
         # static cudart (nvcc's default), deliberately: the library must not depend on WHICH libcudart.so.12
         # the host process has mapped (a torch process brings the 12.8 runtime, this toolkit is 12.9)

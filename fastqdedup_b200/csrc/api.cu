@@ -227,6 +227,10 @@ void fqd_context_destroy(fqd_context *ctx)
     if (ctx->d_ctr) cudaFree(ctx->d_ctr);
     if (ctx->h_ctr) cudaFreeHost(ctx->h_ctr);
     for (auto &ev : ctx->chunk_events) cudaEventDestroy(ev);
+    for (int k = 0; k < 2; k++) {
+        if (ctx->pack_stage[k]) cudaFreeHost(ctx->pack_stage[k]);
+        if (ctx->pack_ev[k]) cudaEventDestroy(ctx->pack_ev[k]);
+    }
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -378,6 +382,8 @@ int resolve_job(fqd_context *ctx, const fqd_cluster_job *job, uint32_t *keep_bit
                 FQD_TRY(dev_alloc(ctx, key_bytes, &p));
                 dj.keys = static_cast<const uint8_t *>(p);
                 dj.host_keys = job->keys;
+                dj.host_pack = !job->key_lengths && job->key_length == job->key_stride && (job->key_length & 3u) == 0 &&
+                               job->key_length <= 64 && !getenv("FQD_NO_HOST_PACK");
             } else {
                 FQD_TRY(up(job->keys, key_bytes, (const void **)&dj.keys));
             }

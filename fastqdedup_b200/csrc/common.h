@@ -72,6 +72,10 @@ struct fqd_context {
     fqd::DevCounters *d_ctr = nullptr;
     fqd::DevCounters *h_ctr = nullptr;   // pinned
     cudaEvent_t ev[12] = {};
+    // pinned staging of the host packer (two chunks of packed rows in flight) and the events that free a slot
+    void *pack_stage[2] = {nullptr, nullptr};
+    size_t pack_stage_bytes = 0;
+    cudaEvent_t pack_ev[2] = {nullptr, nullptr};
     fqd_result res;
     int sm_count = 148;
 };
@@ -138,12 +142,14 @@ struct DeviceJob {
     // them chunk by chunk on the copy stream and ingests each chunk as soon as it has landed
     // (keys / quals above are the device destinations)
     const uint8_t *host_keys = nullptr;
+    bool host_pack = false;       // ... and the keys may cross PCIe packed (host_pack.cpp): fixed-length rows of <= 64 symbols
     const uint8_t *host_quals = nullptr;
     uint32_t *bitmap = nullptr;   // device, (n+31)/32 words, zeroed by the pipeline; may be null
 };
 
 constexpr int RC_RETRY_ALPHABET = -100;   // internal: unknown bytes were seen, grow the alphabet
 constexpr int RC_FALLBACK_REPLICATED = -102;   // internal: the tile-sharded plan gave up (skew), run the replicated-set plan
+constexpr int RC_PACK_INVALID = -103;          // internal: the host packer met a byte outside ACGTN, take the ASCII path
 constexpr int RC_NOT_IN_GROUP = -101;     // internal: the (K, PW) instantiation lives in another instance group
 
 // What every rank of a sharded job knows about the others before the plan starts (agreed in
@@ -186,6 +192,10 @@ inline uint32_t tile_partitions(uint64_t n)
     const uint64_t parts = (n * 100 + (uint64_t)TILE_R * pct - 1) / ((uint64_t)TILE_R * pct);
     return (uint32_t)(parts < 1 ? 1 : parts);
 }
+
+// host_pack.cpp
+uint32_t packed_row_words(uint32_t key_length);
+uint64_t pack_keys_parallel(const uint8_t *src, uint64_t n, uint32_t L, uint32_t stride, uint32_t *dst);
 
 // largest key (in symbols) this build can pack for a given number of code bits
 uint32_t max_supported_length(int bits);

@@ -1,0 +1,228 @@
+// host_pack.cpp -- packing ACGTN keys on the host, so that the host -> device copy of a job carries 3 bits per
+// symbol instead of 8 ("pack keys in C straight from the parser's buffers").
+//
+// With the clustering at a few milliseconds, a job that starts from host buffers is bound by the PCIe copy of its
+// keys (100 M x 36 bytes: 65 of 71 ms).  A packed row is the key's three code-bit planes back to back -- plane p
+// (bit p+1 of every ASCII byte: A 0, C 1, T 2, G 3, N 7, the code of key.cuh) in bits [p*L, (p+1)*L) -- in
+// ceil(3L / 32) 32-bit words: 16 bytes for 36 symbols.  partition_packed_kernel (partitioned.cuh) unpacks it into
+// the plane-major key with a handful of funnel shifts.
+//
+// The packer is one AVX-512 step per row (masked 64-byte load, one VPTESTMB per plane gives the plane as a mask
+// register, one VPERMB table look-up validates all bytes at once) with a scalar fallback, run by a small pool of
+// threads over the rows of a chunk.  No CUDA here.
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <atomic>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+#if defined(__x86_64__)
+#include <immintrin.h>
+#endif
+
+#include "../../include/fqd_b200.h"
+
+namespace fqd {
+
+void set_error(const char *fmt, ...);
+
+namespace {
+
+inline void put_bits(uint64_t (&out)[4], uint64_t v, uint32_t at)
+{
+    const uint32_t w = at >> 6, sh = at & 63u;
+    out[w] |= v << sh;
+    if (sh) out[w + 1] |= v >> (64u - sh);
+}
+
+// scalar: returns false at the first byte that is not one of ACGTN
+inline bool pack_row_scalar(const uint8_t *row, uint32_t L, uint32_t row_words, uint32_t *dst)
+{
+    uint64_t plane[3] = {0, 0, 0};
+    for (uint32_t i = 0; i < L; i++) {
+        const uint8_t c = row[i];
+        if (c != 'A' && c != 'C' && c != 'G' && c != 'T' && c != 'N') return false;
+        const uint64_t code = (c >> 1) & 7u;
+        plane[0] |= (code & 1u) << i;
+        plane[1] |= ((code >> 1) & 1u) << i;
+        plane[2] |= ((code >> 2) & 1u) << i;
+    }
+    uint64_t out[4] = {0, 0, 0, 0};
+    put_bits(out, plane[0], 0);
+    put_bits(out, plane[1], L);
+    put_bits(out, plane[2], 2 * L);
+    memcpy(dst, out, (size_t)row_words * 4);
+    return true;
+}
+
+#if defined(__x86_64__)
+__attribute__((target("avx512f,avx512bw,avx512vbmi,bmi2")))
+size_t pack_rows_avx512(const uint8_t *src, size_t n, uint32_t L, uint32_t stride, uint32_t *dst, uint32_t row_words)
+{
+    // table: index = byte & 63; the five letters map to themselves, everything else to 0xFF (never equal to the byte)
+    alignas(64) uint8_t lut[64];
+    memset(lut, 0xFF, sizeof lut);
+    lut['A' & 63] = 'A'; lut['C' & 63] = 'C'; lut['G' & 63] = 'G'; lut['T' & 63] = 'T'; lut['N' & 63] = 'N';
+    const __m512i table = _mm512_load_si512(lut);
+    const __m512i b1 = _mm512_set1_epi8(0x02), b2 = _mm512_set1_epi8(0x04), b3 = _mm512_set1_epi8(0x08);
+    const __mmask64 lanes = L >= 64 ? ~0ull : ((1ull << L) - 1ull);
+    for (size_t r = 0; r < n; r++) {
+        const __m512i v = _mm512_maskz_loadu_epi8(lanes, src + r * stride);
+        const __mmask64 ok = _mm512_mask_cmpeq_epi8_mask(lanes, _mm512_permutexvar_epi8(v, table), v);
+        if (ok != lanes) return r;
+        const uint64_t p0 = _mm512_test_epi8_mask(v, b1), p1 = _mm512_test_epi8_mask(v, b2), p2 = _mm512_test_epi8_mask(v, b3);
+        uint64_t out[4] = {0, 0, 0, 0};
+        put_bits(out, p0, 0);
+        put_bits(out, p1, L);
+        put_bits(out, p2, 2 * L);
+        memcpy(dst + r * row_words, out, (size_t)row_words * 4);
+    }
+    return n;
+}
+#endif
+
+size_t pack_rows(const uint8_t *src, size_t n, uint32_t L, uint32_t stride, uint32_t *dst, uint32_t row_words)
+{
+#if defined(__x86_64__)
+    static const bool fast = __builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512bw") &&
+                             __builtin_cpu_supports("avx512vbmi");
+    if (fast) return pack_rows_avx512(src, n, L, stride, dst, row_words);
+#endif
+    for (size_t r = 0; r < n; r++)
+        if (!pack_row_scalar(src + r * stride, L, row_words, dst + r * row_words)) return r;
+    return n;
+}
+
+// A few persistent worker threads: a parallel-for over row ranges.
+class Pool {
+public:
+    explicit Pool(int threads)
+    {
+        for (int i = 0; i < threads; i++) workers_.emplace_back([this] { loop(); });
+    }
+    ~Pool()
+    {
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            stop_ = true;
+        }
+        wake_.notify_all();
+        for (auto &t : workers_) t.join();
+    }
+    int size() const { return (int)workers_.size(); }
+    // runs fn(part) for part in [0, parts) on the workers and the caller; returns when all are done
+    void run(int parts, const std::function<void(int)> &fn)
+    {
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            fn_ = &fn;
+            next_ = 0;
+            parts_ = parts;
+            pending_ = parts;
+            generation_++;
+        }
+        wake_.notify_all();
+        work();
+        std::unique_lock<std::mutex> lk(mu_);
+        done_.wait(lk, [&] { return pending_ == 0; });
+        fn_ = nullptr;
+    }
+
+private:
+    void work()
+    {
+        for (;;) {
+            int part;
+            const std::function<void(int)> *fn;
+            {
+                std::lock_guard<std::mutex> lk(mu_);
+                if (!fn_ || next_ >= parts_) return;
+                part = next_++;
+                fn = fn_;
+            }
+            (*fn)(part);
+            std::lock_guard<std::mutex> lk(mu_);
+            if (--pending_ == 0) done_.notify_all();
+        }
+    }
+    void loop()
+    {
+        uint64_t seen = 0;
+        for (;;) {
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                wake_.wait(lk, [&] { return stop_ || generation_ != seen; });
+                if (stop_) return;
+                seen = generation_;
+            }
+            work();
+        }
+    }
+    std::mutex mu_;
+    std::condition_variable wake_, done_;
+    std::vector<std::thread> workers_;
+    const std::function<void(int)> *fn_ = nullptr;
+    int next_ = 0, parts_ = 0, pending_ = 0;
+    uint64_t generation_ = 0;
+    bool stop_ = false;
+};
+
+Pool &pool()
+{
+    static Pool p([] {
+        const unsigned hc = std::thread::hardware_concurrency();
+        const char *e = getenv("FQD_PACK_THREADS");
+        const int want = e && *e ? atoi(e) : (int)(hc ? hc : 4u);
+        return std::max(1, std::min(want, 64)) - 1;   // the calling thread works too
+    }());
+    return p;
+}
+
+}  // namespace
+
+uint32_t packed_row_words(uint32_t key_length) { return (3u * key_length + 31u) / 32u; }
+
+// rows [0, n) of `src` (L bytes each, `stride` apart) -> packed rows; returns the index of the first row holding a byte
+// outside ACGTN, or n
+uint64_t pack_keys_parallel(const uint8_t *src, uint64_t n, uint32_t L, uint32_t stride, uint32_t *dst)
+{
+    const uint32_t rw = packed_row_words(L);
+    Pool &p = pool();
+    const int parts = (int)std::min<uint64_t>((uint64_t)(p.size() + 1) * 4, std::max<uint64_t>(1, n / 4096));
+    std::atomic<uint64_t> bad{n};
+    const std::function<void(int)> fn = [&](int part) {
+        const uint64_t lo = n * (uint64_t)part / parts, hi = n * (uint64_t)(part + 1) / parts;
+        const size_t r = pack_rows(src + lo * stride, (size_t)(hi - lo), L, stride, dst + lo * rw, rw);
+        if (r != hi - lo) {
+            uint64_t cur = bad.load(), mine = lo + r;
+            while (mine < cur && !bad.compare_exchange_weak(cur, mine)) {}
+        }
+    };
+    p.run(parts, fn);
+    return bad.load();
+}
+
+}  // namespace fqd
+
+extern "C" int fqd_pack_keys(const uint8_t *keys, uint64_t n_records, uint32_t key_length, uint32_t key_stride, uint32_t *packed,
+                             uint64_t *bad_record)
+{
+    if ((!keys || !packed) && n_records) { fqd::set_error("fqd_pack_keys: null buffer"); return FQD_ERR_ARG; }
+    if (key_length == 0 || key_length > 64 || key_length > key_stride) {
+        fqd::set_error("fqd_pack_keys: key_length must be 1..64 and <= key_stride");
+        return FQD_ERR_ARG;
+    }
+    const uint64_t bad = fqd::pack_keys_parallel(keys, n_records, key_length, key_stride, packed);
+    if (bad_record) *bad_record = bad;
+    if (bad != n_records) {
+        fqd::set_error("fqd_pack_keys: record %llu holds a byte outside ACGTN (packed rows cannot carry it)", (unsigned long long)bad);
+        return FQD_ERR_UNSUPPORTED;
+    }
+    return FQD_OK;
+}

@@ -201,6 +201,64 @@ inline EdgeSource single_edges(const uint2 *edges, const uint32_t *n_edges, uint
     return E;
 }
 
+// HOST jobs with fixed-length ACGTN rows: the host packs chunk i+1 (threads, AVX-512) while chunk i crosses PCIe at
+// 3 bits per symbol and the partition kernel unpacks the chunk before that.  RC_PACK_INVALID: a byte outside ACGTN
+// (the caller clears the partition buffers and takes the ASCII path, which reports it).
+template <int PW, int NW>
+int launch_packed_chunks(fqd_context *ctx, const DeviceJob &job, const IngestParams &pp, uint32_t index_base, StageTimes &tt)
+{
+    cudaStream_t s = ctx->stream;
+    const uint64_t n = job.n;
+    const uint32_t L = job.key_len, rw = packed_row_words(L);
+    const uint64_t chunk = 4u << 20;   // records; a multiple of every block tile
+    const size_t nchunks = (size_t)((n + chunk - 1) / chunk);
+    const size_t stage_bytes = (size_t)std::min<uint64_t>(chunk, n) * rw * 4;
+    if (ctx->pack_stage_bytes < stage_bytes) {
+        for (int k = 0; k < 2; k++) {
+            if (ctx->pack_stage[k]) FQD_CUDA(cudaFreeHost(ctx->pack_stage[k]));
+            ctx->pack_stage[k] = nullptr;
+        }
+        ctx->pack_stage_bytes = 0;
+        for (int k = 0; k < 2; k++) FQD_CUDA(cudaHostAlloc(&ctx->pack_stage[k], (size_t)chunk * rw * 4, cudaHostAllocDefault));
+        ctx->pack_stage_bytes = (size_t)chunk * rw * 4;
+    }
+    for (int k = 0; k < 2; k++)
+        if (!ctx->pack_ev[k]) FQD_CUDA(cudaEventCreateWithFlags(&ctx->pack_ev[k], cudaEventDisableTiming));
+    while (ctx->chunk_events.size() < nchunks) {
+        cudaEvent_t e;
+        FQD_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        ctx->chunk_events.push_back(e);
+    }
+    FQD_CUDA(cudaEventRecord(ctx->ev[9], s));
+    FQD_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev[9], 0));   // buffers are allocated / idle
+    FQD_CUDA(cudaEventRecord(ctx->ev[10], ctx->copy_stream));
+    uint8_t *dev = const_cast<uint8_t *>(job.keys);                   // (the ASCII buffer is large enough for the packed rows)
+    for (size_t i = 0; i < nchunks; i++) {
+        const uint64_t c0 = i * chunk, cn = std::min<uint64_t>(chunk, n - c0);
+        const int slot = (int)(i & 1);
+        if (i >= 2) FQD_CUDA(cudaEventSynchronize(ctx->pack_ev[slot]));   // the copy out of this slot is done
+        uint32_t *stage = static_cast<uint32_t *>(ctx->pack_stage[slot]);
+        if (pack_keys_parallel(job.host_keys + c0 * job.key_stride, cn, L, job.key_stride, stage) != cn) {
+            FQD_CUDA(cudaStreamSynchronize(ctx->copy_stream));
+            return RC_PACK_INVALID;
+        }
+        FQD_CUDA(cudaMemcpyAsync(dev + c0 * rw * 4, stage, cn * rw * 4, cudaMemcpyHostToDevice, ctx->copy_stream));
+        FQD_CUDA(cudaEventRecord(ctx->pack_ev[slot], ctx->copy_stream));
+        FQD_CUDA(cudaEventRecord(ctx->chunk_events[i], ctx->copy_stream));
+        FQD_CUDA(cudaStreamWaitEvent(s, ctx->chunk_events[i], 0));
+        IngestParams cp = pp;
+        cp.n = cn;
+        cp.keys = dev + c0 * rw * 4;
+        cp.index_base = index_base + (uint32_t)c0;
+        partition_packed_kernel<PW, NW><<<cdiv(cn, 256 * LEAN_ROWS), 256, 0, s>>>(cp);
+        tt.launches++;
+    }
+    FQD_CUDA(cudaGetLastError());
+    FQD_CUDA(cudaEventRecord(ctx->ev[11], ctx->copy_stream));
+    tt.streamed = true;
+    return FQD_OK;
+}
+
 // The partition pass of the streaming plan over the job's records: filter + pack + hash, every record appended to
 // the tile of its hash (of pigeonhole block 0 of `part_blocks` when > 0, of the whole key otherwise).
 template <int K, int PW>
@@ -231,6 +289,22 @@ int launch_partition(fqd_context *ctx, const DeviceJob &job, const Codec &codec,
             job.key_stride == job.key_len && job.key_len == job.max_len && (job.key_len & 3u) == 0 &&
             !getenv("FQD_NO_SWAR") && !getenv("FQD_NO_LEAN"))
             lean_nw = (int)(job.key_len >> 2);
+    }
+    if constexpr (K == 3 && slot_words(K * PW) == PART_RW) {
+        if (lean_nw && job.host_keys && job.host_pack && job.n) {
+            int rc = RC_PACK_INVALID;
+            if (lean_nw == 3) rc = launch_packed_chunks<PW, 3>(ctx, job, pp, index_base, tt);
+            else if (lean_nw == 6) rc = launch_packed_chunks<PW, 6>(ctx, job, pp, index_base, tt);
+            if constexpr (PW >= 2) {
+                if (lean_nw == 9) rc = launch_packed_chunks<PW, 9>(ctx, job, pp, index_base, tt);
+                else if (lean_nw == 12) rc = launch_packed_chunks<PW, 12>(ctx, job, pp, index_base, tt);
+            }
+            if (rc == FQD_OK) return FQD_OK;
+            if (rc != RC_PACK_INVALID) return rc;
+            // forget what the packed chunks appended, then the ASCII path (it names the unknown bytes)
+            FQD_CUDA(cudaMemsetAsync(part.cursor, 0, (size_t)part.nparts * 4, s));
+            if (part.spill_cnt) FQD_CUDA(cudaMemsetAsync(part.spill_cnt, 0, 8, s));
+        }
     }
     FQD_TRY(for_each_input_chunk(ctx, job, pp, index_base, nullptr, tt, [&](const IngestParams &cp) {
         if constexpr (K == 3 && slot_words(K * PW) == PART_RW) {

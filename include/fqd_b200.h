@@ -250,6 +250,15 @@ void fqd_fastq_scan_free(fqd_fastq_scan *scan);
 int fqd_fastq_emit(const char *const *in_paths, const char *const *out_paths, int n_files, const uint32_t *keep_bitmap,
                    uint64_t n_records, int threads, uint64_t *n_written);
 
+/* Host-side key packing (joinfunc_from_check_slices' output, __init__.py:160-167, 3 bits per symbol instead of 8):
+ * rows of key_length (<= 64) bytes over ACGTN, key_stride apart -> rows of ceil(3 * key_length / 32) uint32 words,
+ * the three code-bit planes of the key back to back (plane p = bit p+1 of every ASCII byte, in bits
+ * [p * key_length, (p+1) * key_length)).  Multithreaded (FQD_PACK_THREADS, default: all cores), AVX-512 when the CPU
+ * has it.  fqd_cluster uses the same packer internally for HOST jobs with fixed-length keys, chunk by chunk ahead of
+ * the PCIe copy.  FQD_ERR_UNSUPPORTED + *bad_record when a byte is outside ACGTN. */
+int fqd_pack_keys(const uint8_t *keys, uint64_t n_records, uint32_t key_length, uint32_t key_stride, uint32_t *packed,
+                  uint64_t *bad_record);
+
 /* Measurement aid (not on the product path): the integer-issue peak of the
  * context's GPU in thread-level operations per second, from dependent-free instruction streams --
  * LOP3 alone, POPC alone, and the 4 LOP3 : 1 POPC mix of the XOR+POPC Hamming compare that replaces

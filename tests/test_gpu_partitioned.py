@@ -205,13 +205,14 @@ def test_streaming_plan_with_record_multiplicities(gpu_ctx, oracle):
 
 
 def test_more_oversize_partitions_than_a_launch_grid_has_rows(gpu_ctx):
-    """~58 M records of ~96 k keys with 600 copies each: every occupied 512-record tile is oversize, and there are
-    more than 65535 of them -- what gridDim.y could hold when the spill launch still put the partition index there.
-    Checked against the known answer (keys built so that no two are within distance 1: every key its own cluster,
-    all selected, first occurrence = its index in the first round) instead of the oracle."""
-    os.environ["FQD_TILE_FILL_PCT"] = "90"
+    """57 M records of 110 k keys with 520 copies each over ~560 k sparsely filled tiles: every occupied 512-record
+    tile is oversize -- about 100 k of them, more than the 65535 gridDim.y could hold when the spill launch still put
+    the partition index there -- while the surplus (8 records of most keys) stays well inside the spill buffer, so the
+    streaming plan has to see it through.  Checked against the known answer (keys built so that no two are within
+    distance 1: every key its own cluster, all selected, first occurrence = its index in the first round)."""
+    os.environ["FQD_TILE_FILL_PCT"] = "20"
     try:
-        n_keys, copies, half = 96_000, 600, 10
+        n_keys, copies, half = 110_000, 520, 10
         digits = ((np.arange(n_keys)[:, None] >> (2 * np.arange(half)[None, :])) & 3).astype(np.uint8)
         base = np.frombuffer(b"ACGT", dtype=np.uint8)[np.concatenate([digits, digits], axis=1)]   # two keys differ in >= 2 symbols
         keys = np.tile(base, (copies, 1))
