@@ -429,7 +429,8 @@ def run_ours(args, rank, world, local_rank):
     for _ in range(e2e_steps):
         est = ctx.cluster(job, host_bitmap.ptr)
     e2e_s = (time.perf_counter() - e0) / e2e_steps
-    h2d = n * L * (2 if host_quals is not None else 1)
+    host_in = n * L * (2 if host_quals is not None else 1)    # what the caller hands over
+    h2d = int(est.h2d_bytes)                                   # what the library copied over PCIe (keys packed on the host)
     d2h = bitmap_words * 4
     # the e2e result is the same set as the device-resident one
     dev_bitmap = ctx.download(d_bitmap, bitmap_words * 4, np.uint32)
@@ -545,7 +546,9 @@ def run_ours(args, rank, world, local_rank):
         "wall_ms_per_step": 1e3 * wall / args.steps,
         "e2e": {"value": U / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * e2e_s,
-                "steps": e2e_steps, "h2d_ms": est.ms_h2d},
+                "steps": e2e_steps, "h2d_ms": est.ms_h2d, "host_input_bytes_per_step": int(host_in),
+                "host_packing": "keys packed to 3 bits/symbol by the library's host threads inside the timed region"
+                                if h2d < host_in else "none"},
         "gpu_launches": int(sum(s.launches for s in stats)),
         "clocks": clocks,
         "roofline": roofline,
@@ -639,7 +642,7 @@ def run_ours_sharded(args, cfg, rank, world, local_rank, dist):
     gathered = [None] * world if rank == 0 else None
     dist.gather_object((dev_bitmap[:words].copy(), nloc), gathered, dst=0)
     launches = int(sum(s.launches for s in stats))
-    lt = torch.tensor([launches], dtype=torch.int64, device=f"cuda:{local_rank}")
+    lt = torch.tensor([launches, int(est.h2d_bytes)], dtype=torch.int64, device=f"cuda:{local_rank}")
     dist.all_reduce(lt)
     if rank == 0:
         total_b, _ = algorithmic_bytes(cfg, n, st.number_of_sequences, U, st.n_passes,
@@ -655,9 +658,10 @@ def run_ours_sharded(args, cfg, rank, world, local_rank, dist):
             "keep_bitmap_sha256_32": bitmap_digest(gathered),
             "plan": "tile-sharded (peer-memory tile fetch)" if st.plan_flags & 16 else "replicated unique set",
             "wall_ms_per_step": 1e3 * wall / args.steps,
-            "e2e": {"value": U / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(n * L * (2 if host_quals is not None else 1)),
-                    "d2h_bytes_per_step": int(((n + 31) // 32) * 4), "ms_per_step": 1e3 * e2e_s, "steps": e2e_steps},
-            "gpu_launches": int(lt.item()),
+            "e2e": {"value": U / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(lt[1].item()),
+                    "d2h_bytes_per_step": int(((n + 31) // 32) * 4), "ms_per_step": 1e3 * e2e_s, "steps": e2e_steps,
+                    "host_input_bytes_per_step": int(n * L * (2 if host_quals is not None else 1))},
+            "gpu_launches": int(lt[0].item()),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "whole sharded job (per-kernel split: see the 1-GPU line)",
                          "achieved": total_b / (ms_per_step / 1e3) / 1e9, "peak": peak * world, "unit": "GB/s",

@@ -88,7 +88,7 @@ class ClusterStats(Structure):
         ("ms_compare", c_float), ("ms_ingest_kernel", c_float), ("ms_table_clear", c_float),
         ("ms_bucket_build", c_float), ("launches", c_uint32), ("plan_flags", c_uint32),
         ("ms_partition_kernel", c_float), ("ms_dedupe_kernel", c_float),
-        ("own_uniques", c_uint64),
+        ("own_uniques", c_uint64), ("h2d_bytes", c_uint64),
     ]
 
     def as_dict(self):

@@ -348,6 +348,7 @@ int resolve_job(fqd_context *ctx, const fqd_cluster_job *job, uint32_t *keep_bit
     cudaStream_t s = ctx->stream;
     const uint64_t n = job->n_records;
     DeviceJob &dj = r.dj;
+    ctx->h2d_bytes = 0;
     dj.n = n;
     dj.d = job->max_distance; dj.edit = job->use_edit_distance ? 1 : 0; dj.method = job->method;
     dj.max_err = job->max_average_error_rate;
@@ -364,6 +365,7 @@ int resolve_job(fqd_context *ctx, const fqd_cluster_job *job, uint32_t *keep_bit
             void *p = nullptr;
             FQD_TRY(dev_alloc(ctx, bytes ? bytes : 16, &p));
             if (bytes) FQD_CUDA(cudaMemcpyAsync(p, src, bytes, cudaMemcpyHostToDevice, s));
+            ctx->h2d_bytes += bytes;
             *dst = p;
             return FQD_OK;
         };
@@ -461,6 +463,7 @@ int finish_job(fqd_context *ctx, Resolved &r, fqd_cluster_stats *stats)
     if (r.host_bitmap && r.bitmap_words)
         FQD_CUDA(cudaMemcpyAsync(r.host_bitmap, r.dj.bitmap, r.bitmap_words * 4, cudaMemcpyDeviceToHost, s));
     FQD_CUDA(cudaStreamSynchronize(s));
+    stats->h2d_bytes = ctx->h2d_bytes;
     if (r.h0) {
         float t = 0.f;
         cudaEventElapsedTime(&t, r.h0, r.h1);

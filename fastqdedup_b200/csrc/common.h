@@ -77,6 +77,7 @@ struct fqd_context {
     size_t pack_stage_bytes = 0;
     cudaEvent_t pack_ev[2] = {nullptr, nullptr};
     fqd_result res;
+    uint64_t h2d_bytes = 0;      // input bytes the current job has copied host -> device
     int sm_count = 148;
 };
 

@@ -62,10 +62,87 @@ inline bool pack_row_scalar(const uint8_t *row, uint32_t L, uint32_t row_words, 
 }
 
 #if defined(__x86_64__)
-__attribute__((target("avx512f,avx512bw,avx512vbmi,bmi2")))
-size_t pack_rows_avx512(const uint8_t *src, size_t n, uint32_t L, uint32_t stride, uint32_t *dst, uint32_t row_words)
+#define FQD_AVX512 __attribute__((target("avx512f,avx512bw,avx512vbmi,bmi2")))
+
+// one row: planes as mask registers, validity of every byte by one table look-up
+template <uint32_t L>
+FQD_AVX512 inline __mmask64 row_planes(const uint8_t *row, __m512i table, __m512i b1, __m512i b2, __m512i b3, uint64_t &p0, uint64_t &p1,
+                                       uint64_t &p2)
 {
+    constexpr __mmask64 lanes = L >= 64 ? ~0ull : ((1ull << L) - 1ull);
+    const __m512i v = _mm512_maskz_loadu_epi8(lanes, row);
+    p0 = _mm512_test_epi8_mask(v, b1);
+    p1 = _mm512_test_epi8_mask(v, b2);
+    p2 = _mm512_test_epi8_mask(v, b3);
+    return _mm512_mask_cmpneq_epi8_mask(lanes, _mm512_permutexvar_epi8(v, table), v);   // bytes that are not ACGTN
+}
+
+// the three planes of one row -> its packed words (straight-line code for the key lengths of the configs)
+template <uint32_t L>
+FQD_AVX512 inline void store_row(uint32_t *dst, uint64_t p0, uint64_t p1, uint64_t p2)
+{
+    constexpr uint32_t RW = (3u * L + 31u) / 32u;
+    uint64_t out[4] = {0, 0, 0, 0};
+    put_bits(out, p0, 0);
+    put_bits(out, p1, L);
+    put_bits(out, p2, 2 * L);
+    if constexpr (RW % 2 == 0) {
+#pragma GCC unroll 4
+        for (uint32_t i = 0; i < RW / 2; i++) memcpy(dst + 2 * i, &out[i], 8);
+    } else {
+#pragma GCC unroll 4
+        for (uint32_t i = 0; i < RW / 2; i++) memcpy(dst + 2 * i, &out[i], 8);
+        const uint32_t last = (uint32_t)out[RW / 2];
+        memcpy(dst + RW - 1, &last, 4);
+    }
+}
+
+template <uint32_t L>
+FQD_AVX512 size_t pack_rows_avx512_fixed(const uint8_t *src, size_t n, uint32_t stride, uint32_t *dst)
+{
+    constexpr uint32_t RW = (3u * L + 31u) / 32u;
     // table: index = byte & 63; the five letters map to themselves, everything else to 0xFF (never equal to the byte)
+    alignas(64) uint8_t lut[64];
+    memset(lut, 0xFF, sizeof lut);
+    lut['A' & 63] = 'A'; lut['C' & 63] = 'C'; lut['G' & 63] = 'G'; lut['T' & 63] = 'T'; lut['N' & 63] = 'N';
+    const __m512i table = _mm512_load_si512(lut);
+    const __m512i b1 = _mm512_set1_epi8(0x02), b2 = _mm512_set1_epi8(0x04), b3 = _mm512_set1_epi8(0x08);
+    constexpr size_t BLOCK = 64;   // rows validated together (the first bad row is only looked for when there is one)
+    for (size_t r0 = 0; r0 < n; r0 += BLOCK) {
+        const size_t r1 = r0 + BLOCK < n ? r0 + BLOCK : n;
+        __mmask64 bad = 0;
+        size_t r = r0;
+        for (; r + 2 <= r1; r += 2) {   // two rows per step: their loads and mask moves overlap
+            uint64_t a0, a1, a2, c0, c1, c2;
+            bad |= row_planes<L>(src + r * stride, table, b1, b2, b3, a0, a1, a2);
+            bad |= row_planes<L>(src + (r + 1) * stride, table, b1, b2, b3, c0, c1, c2);
+            store_row<L>(dst + r * RW, a0, a1, a2);
+            store_row<L>(dst + (r + 1) * RW, c0, c1, c2);
+        }
+        for (; r < r1; r++) {
+            uint64_t a0, a1, a2;
+            bad |= row_planes<L>(src + r * stride, table, b1, b2, b3, a0, a1, a2);
+            store_row<L>(dst + r * RW, a0, a1, a2);
+        }
+        if (bad) {
+            for (r = r0; r < r1; r++) {
+                uint64_t a0, a1, a2;
+                if (row_planes<L>(src + r * stride, table, b1, b2, b3, a0, a1, a2)) return r;
+            }
+        }
+    }
+    return n;
+}
+
+FQD_AVX512 size_t pack_rows_avx512(const uint8_t *src, size_t n, uint32_t L, uint32_t stride, uint32_t *dst, uint32_t row_words)
+{
+    switch (L) {
+    case 12: return pack_rows_avx512_fixed<12>(src, n, stride, dst);
+    case 24: return pack_rows_avx512_fixed<24>(src, n, stride, dst);
+    case 36: return pack_rows_avx512_fixed<36>(src, n, stride, dst);
+    case 48: return pack_rows_avx512_fixed<48>(src, n, stride, dst);
+    default: break;
+    }
     alignas(64) uint8_t lut[64];
     memset(lut, 0xFF, sizeof lut);
     lut['A' & 63] = 'A'; lut['C' & 63] = 'C'; lut['G' & 63] = 'G'; lut['T' & 63] = 'T'; lut['N' & 63] = 'N';

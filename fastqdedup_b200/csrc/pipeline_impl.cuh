@@ -155,6 +155,7 @@ int for_each_input_chunk(fqd_context *ctx, const DeviceJob &job, IngestParams ip
             FQD_CUDA(cudaMemcpyAsync(const_cast<uint8_t *>(job.quals) + c0 * job.qual_stride,
                                      job.host_quals + c0 * job.qual_stride, cn * job.qual_stride,
                                      cudaMemcpyHostToDevice, ctx->copy_stream));
+        ctx->h2d_bytes += cn * job.key_stride + (job.host_quals ? cn * job.qual_stride : 0);
         FQD_CUDA(cudaEventRecord(ctx->chunk_events[i], ctx->copy_stream));
         FQD_CUDA(cudaStreamWaitEvent(s, ctx->chunk_events[i], 0));
         IngestParams cp = ip;
@@ -243,6 +244,7 @@ int launch_packed_chunks(fqd_context *ctx, const DeviceJob &job, const IngestPar
             return RC_PACK_INVALID;
         }
         FQD_CUDA(cudaMemcpyAsync(dev + c0 * rw * 4, stage, cn * rw * 4, cudaMemcpyHostToDevice, ctx->copy_stream));
+        ctx->h2d_bytes += cn * rw * 4;
         FQD_CUDA(cudaEventRecord(ctx->pack_ev[slot], ctx->copy_stream));
         FQD_CUDA(cudaEventRecord(ctx->chunk_events[i], ctx->copy_stream));
         FQD_CUDA(cudaStreamWaitEvent(s, ctx->chunk_events[i], 0));

@@ -135,6 +135,8 @@ typedef struct {
     float ms_partition_kernel;     /* partitioned dedupe: filter + pack + partition pass */
     float ms_dedupe_kernel;        /* partitioned dedupe: the shared-memory tile kernel (dedupe + fused pass 0) */
     uint64_t own_uniques;          /* tile-sharded job: unique keys this rank owns (what fqd_cluster_fetch returns) */
+    uint64_t h2d_bytes;            /* HOST jobs: input bytes copied host -> device (keys packed on the host cross at
+                                      3 bits per symbol) */
 } fqd_cluster_stats;
 
 #define FQD_PLAN_DEDUPE_PARTITIONED 1u /* exact dedupe: partition by hash, tables in shared-memory tiles */
