@@ -387,6 +387,50 @@ FQD_HD uint32_t block_start(uint32_t len, uint32_t j, uint32_t nblocks)
     return (len * j) / nblocks;   // len <= 320 symbols, j <= nblocks <= len: 32-bit arithmetic (a 64-bit divide costs ~100 instructions)
 }
 
+// 32 plane bits for the symbol positions pos .. pos+31 where pos may be negative (positions before the key read as 0).
+template <int K, int PW>
+FQD_HD uint32_t plane_bits32_signed(const Key<K, PW> &a, int p, int pos)
+{
+    if (pos >= 0) return plane_bits32(a, p, (uint32_t)pos);
+    if (pos <= -32) return 0u;
+    return a.w[p * PW] << (uint32_t)(-pos);
+}
+
+// bits k of a 32-bit word whose symbol position base + k lies in [0, len)
+FQD_HD uint32_t range_mask32(int base, int len)
+{
+    const int lo = base < 0 ? -base : 0, hi = len - base;   // k in [lo, hi)
+    if (hi <= lo || lo >= 32) return 0u;
+    const uint32_t upto = hi >= 32 ? 0xFFFFFFFFu : ((1u << hi) - 1u);
+    return upto & ~((1u << lo) - 1u);
+}
+
+// A cheap NECESSARY condition for "Levenshtein distance <= d" (shifted Hamming filter): in an alignment with at most
+// d edits every symbol of `a` that is not substituted or deleted matches the symbol of `b` on one of the diagonals
+// -d .. d, so the positions of `a` that mismatch on ALL those diagonals number at most d.  Bit-plane XORs under 2d+1
+// shifts, AND, POPC: ~60 integer operations for a 24-symbol key at d = 2, against ~400 for the Myers verify it
+// guards -- and random candidates of a pigeonhole bucket almost never pass it.  Never rejects a true neighbour.
+template <int K, int PW>
+FQD_HD bool shifted_hamming_maybe_within(const Key<K, PW> &a, uint32_t la, const Key<K, PW> &b, uint32_t lb, int d)
+{
+    int count = 0;
+#pragma unroll
+    for (int c = 0; c < PW; c++) {
+        if ((uint32_t)(32 * c) >= la) break;
+        uint32_t acc = 0xFFFFFFFFu;
+        for (int s = -d; s <= d; s++) {
+            uint32_t diff = 0;
+#pragma unroll
+            for (int p = 0; p < K; p++) diff |= a.w[p * PW + c] ^ plane_bits32_signed(b, p, 32 * c + s);
+            acc &= diff | ~range_mask32(32 * c + s, (int)lb);   // no partner on this diagonal = a mismatch
+        }
+        acc &= range_mask32(32 * c, (int)la);
+        count += popc32(acc);
+        if (count > d) return false;
+    }
+    return true;
+}
+
 // ---------------------------------------------------------------------------------------
 // Levenshtein predicate (reference distances.h:33-87 == "edit distance <= d") by Myers'
 // bit-vector algorithm in Hyyro's global-distance form, NW64 64-bit words per column

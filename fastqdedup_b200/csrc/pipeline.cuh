@@ -839,7 +839,10 @@ static __global__ void __launch_bounds__(256) compare_kernel(const __grid_consta
                         bool ok;
                         if (P.edit) {
                             const uint32_t lj = P.varlen ? key_length(kj, P.pad_code, P.max_len) : P.max_len;
-                            ok = myers_within<K, PW>(ki, li, kj, lj, P.d);
+                            // (almost every candidate of a block bucket is a chance hit: the shifted-Hamming filter
+                            // turns it away for a seventh of the cost of the verify)
+                            ok = (P.d > 4 || shifted_hamming_maybe_within<K, PW>(ki, li, kj, lj, P.d)) &&
+                                 myers_within<K, PW>(ki, li, kj, lj, P.d);
                         } else {
                             ok = hamming_within<K, PW>(ki, kj, P.d, P.varlen != 0, P.pad_code);
                         }

@@ -12,7 +12,7 @@ SRC = os.path.join(ROOT, "tests", "probe", "key_probe.cpp")
 OUT = os.path.join(ROOT, "tests", "probe", "build", "key_probe.so")
 
 OPS = dict(hamming=0, myers=1, less=2, equal=3, length=4, blockeq=5, hash=6, symbol=7, swar=8, fixed=9,
-           block0eq=10, hash32=11)
+           block0eq=10, hash32=11, shd=12)
 
 
 @pytest.fixture(scope="module")
@@ -175,3 +175,29 @@ def test_partition_hash_depends_on_the_leading_block_only(probe):
         assert probe(3, 2, "block0eq", b"ACGTN", False, a, bytes(c), 36, p2=18) == 0
         h = probe(3, 2, "hash32", b"ACGTN", False, a, a, 36)
         assert seen.setdefault(h, a) == a      # 2000 keys, 32 bits: a collision would be a bug, not bad luck
+
+
+@pytest.mark.parametrize("K,PW,alphabet,L", CASES)
+def test_shifted_hamming_filter_never_rejects_a_neighbour(probe, oracle, K, PW, alphabet, L):
+    """The prefilter of the Levenshtein verify is a necessary condition: whatever is within the distance passes it
+    (mutated pairs, all lengths, PAD in play); and it does turn most random pairs away."""
+    rng = np.random.default_rng(K * 1000 + PW * 10 + L)
+    rejected = total = 0
+    for it in range(2500):
+        la = L if it % 3 else int(rng.integers(0, L + 1))
+        a = bytes(rng.choice(list(alphabet), size=la).astype(np.uint8))
+        d = int(rng.integers(0, 5))
+        if it % 5 == 0:
+            b = bytes(rng.choice(list(alphabet), size=int(rng.integers(max(0, la - 2), min(L, la + 2) + 1))).astype(np.uint8))
+        else:
+            b = mutate(rng, a, alphabet, int(rng.integers(0, d + 2)), indel=True)[:L]
+        for varlen in ((True, False) if len(a) == len(b) else (True,)):
+            maxlen = L if varlen else len(a)
+            passed = probe(K, PW, "shd", alphabet, varlen, a, b, maxlen, d)
+            if oracle.within_distance(a, b, d, True):
+                assert passed == 1, (a, b, d, varlen)
+            elif it % 5 == 0 and la >= 12 and d <= 2:
+                total += 1
+                rejected += passed == 0
+    if total > 50 and len(alphabet) <= 10:
+        assert rejected > 0.7 * total, (rejected, total)
