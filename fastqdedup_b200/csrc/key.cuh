@@ -151,32 +151,42 @@ FQD_HD uint32_t funnel_l(uint32_t lo, uint32_t hi, uint32_t s) { return __funnel
 FQD_HD uint32_t funnel_l(uint32_t lo, uint32_t hi, uint32_t s) { return s ? (hi << s) | (lo >> (32u - s)) : hi; }
 #endif
 
-// SWAR packing for the ACGTN alphabet: four ASCII bytes per 32-bit word, no table.  The code
-// of a letter is bits 1..3 of its byte; the remaining bits are a function of those three for
-// exactly the five letters, which is how a foreign byte is detected (returns false; the caller
-// then reports the bytes one by one through the table path).  `words` must be 4-byte aligned.
+// SWAR packing for the ACGTN alphabet: four ASCII bytes per 32-bit word, no table in memory.  The
+// code of a letter is bits 1..3 of its byte (A 0, C 1, T 2, G 3, N 7).  `words` must be 4-byte aligned.
+//
+// Validity: the four codes are gathered into the four selector nibbles of a byte permute (PRMT), which
+// looks the ASCII byte each code stands for up in an 8-byte register table; a byte that differs from its
+// own code's letter is foreign (codes 4..6 map to 0xFF, whose own code is 7, so they never match).  Five
+// instructions and one accumulate per word; a foreign byte makes the caller report the key's bytes one
+// by one through the table path.
 //
 // Per word and plane: mask the four code bits where they sit (bit 8k+1+p), one multiply moves
 // them to the top nibble (bits 28..31; the cross terms land on distinct lower bits or overflow,
 // so no carry reaches the nibble) and one funnel shift appends that nibble to the plane word --
 // three instructions.  Words are visited from the last to the first so nibble j ends at bit 4j.
+#if defined(__CUDA_ARCH__)
+FQD_HD uint32_t byte_perm(uint32_t a, uint32_t b, uint32_t s) { return __byte_perm(a, b, s); }
+#else
+FQD_HD uint32_t byte_perm(uint32_t a, uint32_t b, uint32_t s)
+{
+    const uint64_t v = ((uint64_t)b << 32) | a;
+    uint32_t r = 0;
+    for (int k = 0; k < 4; k++) r |= (uint32_t)((v >> (8u * ((s >> (4 * k)) & 7u))) & 0xFFu) << (8 * k);
+    return r;
+}
+#endif
+
 struct SwarCheck {
-    uint32_t bad = 0, any = 0, all = 0xFFFFFFFFu;
-    // bits 7..5 of every byte must read 010; `bad` is evaluated at bit 1 of every byte
-    FQD_HD bool ok() const { return ((bad & 0x02020202u) | (any & 0xA0A0A0A0u) | (~all & 0x40404040u)) == 0; }
+    uint32_t bad = 0;
+    FQD_HD bool ok() const { return bad == 0; }
 };
 
 // four symbols: validity + the three plane nibbles appended to p0/p1/p2
 FQD_HD void swar_step(uint32_t w, SwarCheck &c, uint32_t &p0, uint32_t &p1, uint32_t &p2)
 {
-    // validity at bit 1 of every byte: c0 = bit 1, c1 = bit 2, c2 = bit 3
-    const uint32_t s1 = w >> 1, s2 = w >> 2, s3 = w >> 3, sl = w << 1;
-    const uint32_t is_t = ~w & s1 & ~s2;            // code 2
-    const uint32_t t_or_n = s1 & ~(w ^ s2);         // code 2 or 7
-    const uint32_t inval = s2 & ~(w & s1);          // codes 4, 5, 6
-    c.bad |= inval | (is_t ^ s3) | ~(sl ^ t_or_n);  // bit 4 == is_t, bit 0 == !(T or N)
-    c.any |= w;
-    c.all &= w;
+    const uint32_t codes = (w >> 1) & 0x07070707u;                        // one code per byte
+    const uint32_t sel = byte_perm(codes | (codes >> 4), 0u, 0x4420u);    // nibble k = code of byte k
+    c.bad |= byte_perm(0x47544341u, 0x4EFFFFFFu, sel) ^ w;                // "ACTG", 0xFF x3, 'N'
     p0 = funnel_l((w & 0x02020202u) * 0x08102040u, p0, 4);
     p1 = funnel_l((w & 0x04040404u) * 0x04081020u, p1, 4);
     p2 = funnel_l((w & 0x08080808u) * 0x02040810u, p2, 4);
@@ -501,6 +511,114 @@ FQD_HD bool myers_within(const Key<K, PW> &a, uint32_t la, const Key<K, PW> &b, 
         if (score - (int)(lb - 1 - j) > max_distance) return false;
     }
     return score <= max_distance;
+}
+
+// ---------------------------------------------------------------------------------------
+// The same predicate for keys of up to 63 symbols and small d by furthest-reaching diagonals (Landau-Vishkin /
+// Ukkonen), entirely in registers and without a data-dependent loop: a GPU warp runs it in lockstep, where the
+// column loop of Myers' algorithm with its early exit leaves most lanes of a warp idle (config 4, d = 2: a quarter
+// of the random candidates of a bucket pass the shifted-Hamming filter, and the verify behind it took 23 of 24 ms).
+//
+// D_k (bit i) = a[i] differs from b[i + k], or one of the two does not exist.  fr[e][k] = the furthest row i such
+// that a[0, i) and b[0, i + k) are within e edits; a diagonal is extended over a run of matches by counting the
+// trailing zeros of D_k >> i.  fr[e][k] = extend(max(fr[e-1][k] + 1, fr[e-1][k-1], fr[e-1][k+1] + 1)), and the
+// distance is <= d iff some fr[e <= d][lb - la] reaches la.  2d+1 masks and (d+1)^2 extensions: ~200 integer
+// operations for d = 2.
+// ---------------------------------------------------------------------------------------
+template <typename W, int K, int PW>
+FQD_HD W plane_word(const Key<K, PW> &a, int p)
+{
+    static_assert(PW <= 2, "plane_word: keys of up to 64 symbols");
+    if constexpr (sizeof(W) == 4) {
+        return a.w[p * PW];                      // (callers: every symbol lies in the first word)
+    } else {
+        uint64_t v = a.w[p * PW];
+        if constexpr (PW == 2) v |= (uint64_t)a.w[p * PW + 1] << 32;
+        return v;
+    }
+}
+
+#if defined(__CUDA_ARCH__)
+FQD_HD int ctz_word(uint64_t x) { return __ffsll((long long)x) - 1; }   // x != 0
+FQD_HD int ctz_word(uint32_t x) { return __ffs((int)x) - 1; }
+#else
+FQD_HD int ctz_word(uint64_t x) { return __builtin_ctzll(x); }
+FQD_HD int ctz_word(uint32_t x) { return __builtin_ctz(x); }
+#endif
+
+constexpr int LV_MAX_D = 3;
+
+// W = uint32_t for keys of up to 31 symbols (half the instructions of the 64-bit form), uint64_t up to 63
+template <typename W, int K, int PW, int D>
+FQD_HD bool lv_within_d(const Key<K, PW> &a, uint32_t la, const Key<K, PW> &b, uint32_t lb)
+{
+    // la, lb < bits of W; |la - lb| <= D checked by the caller
+    constexpr W ONE = 1, TOP = ONE << (sizeof(W) * 8 - 1);
+    const W ma = (ONE << la) - ONE, mb = (ONE << lb) - ONE;
+    W A[K], B[K];
+#pragma unroll
+    for (int p = 0; p < K; p++) { A[p] = plane_word<W, K, PW>(a, p); B[p] = plane_word<W, K, PW>(b, p); }
+    W Dk[2 * D + 1];   // Dk[k + D]
+#pragma unroll
+    for (int k = -D; k <= D; k++) {
+        W diff = 0;
+#pragma unroll
+        for (int p = 0; p < K; p++) diff |= A[p] ^ (k >= 0 ? (W)(B[p] >> k) : (W)(B[p] << -k));
+        const W have_b = k >= 0 ? (W)(mb >> k) : (W)(mb << -k);   // rows i with 0 <= i + k < lb
+        Dk[k + D] = diff | ~have_b | ~ma | TOP;                     // top bit: a run always ends
+    }
+    const int target = (int)lb - (int)la + D;                      // index of the diagonal the alignment must end on
+    int fr[2 * D + 1];
+#pragma unroll
+    for (int k = 0; k <= 2 * D; k++) fr[k] = -64;                  // unreachable
+    fr[D] = ctz_word(Dk[D]);
+    bool ok = target == D && fr[D] >= (int)la;
+#pragma unroll
+    for (int e = 1; e <= D; e++) {
+        int nx[2 * D + 1];
+#pragma unroll
+        for (int k = 0; k <= 2 * D; k++) nx[k] = fr[k];
+#pragma unroll
+        for (int k = D - e; k <= D + e; k++) {
+            int t = fr[k] + 1;                                      // substitution
+            if (k > 0 && fr[k - 1] > t) t = fr[k - 1];              // a symbol of b inserted
+            if (k < 2 * D && fr[k + 1] + 1 > t) t = fr[k + 1] + 1;  // a symbol of a deleted
+            // rows beyond either string do not exist: row <= la, column row + (k - D) <= lb
+            const int lim_b = (int)lb - (k - D), lim = (int)la < lim_b ? (int)la : lim_b;
+            if (t > lim) t = lim;
+            if (t >= 0) t += ctz_word((W)(Dk[k] >> t));             // extend over the run of matches
+            else t = -64;
+            nx[k] = t;
+        }
+#pragma unroll
+        for (int k = 0; k <= 2 * D; k++) fr[k] = nx[k];
+#pragma unroll
+        for (int k = D - e; k <= D + e; k++) ok = ok || (k == target && fr[k] >= (int)la);
+    }
+    return ok;
+}
+
+template <typename W, int K, int PW>
+FQD_HD bool lv_within(const Key<K, PW> &a, uint32_t la, const Key<K, PW> &b, uint32_t lb, int max_distance)
+{
+    if (max_distance == 1) return lv_within_d<W, K, PW, 1>(a, la, b, lb);
+    if (max_distance == 2) return lv_within_d<W, K, PW, 2>(a, la, b, lb);
+    return lv_within_d<W, K, PW, 3>(a, la, b, lb);
+}
+
+// edit distance <= max_distance; the fast form when the keys fit (else Myers)
+template <int K, int PW>
+FQD_HD bool edit_within(const Key<K, PW> &a, uint32_t la, const Key<K, PW> &b, uint32_t lb, int max_distance)
+{
+    if constexpr (PW <= 2) {
+        if (la <= 63u && lb <= 63u && la > 0 && lb > 0 && max_distance >= 1 && max_distance <= LV_MAX_D) {
+            const uint32_t diff = la > lb ? la - lb : lb - la;
+            if (diff > (uint32_t)max_distance) return false;
+            if (la <= 31u && lb <= 31u) return lv_within<uint32_t, K, PW>(a, la, b, lb, max_distance);
+            return lv_within<uint64_t, K, PW>(a, la, b, lb, max_distance);
+        }
+    }
+    return myers_within<K, PW>(a, la, b, lb, max_distance);
 }
 
 }  // namespace fqd

@@ -197,6 +197,15 @@ __device__ __forceinline__ uint32_t stage_tile(uint32_t *recs, uint32_t *tab, ui
 // multiplicities: everything the general ingest_kernel decides at run time is known here, which
 // removes a third of its instructions (the pass is instruction-bound: ~1.7 G warp instructions
 // for 100 M records).  Same record format, same partition function.
+//
+// What bounds it (ncu, profiles/r02_ncu_full_cfg5_summary.json): every record costs one cursor atomic and one 32-byte
+// store to its own tile, i.e. two warp instructions with 32 distinct sectors each, and the nine shared-memory loads
+// of a row queue behind them in the same load/store pipe (mio_throttle + short_scoreboard = 36 % of the stall
+// samples, the atomics' round trip 25 %).  Measured and dropped in round 2: a persistent variant (two staging
+// buffers, the bulk copy of chunk i+2 in flight while chunk i is packed, 64-bit shared loads, the stores of a chunk
+// issued behind the atomics of the next one): 2.83 ms against 2.25 ms -- its 62 registers halve the resident warps
+// and the load/store pipe, not latency, is the limit; 12 % fewer instructions (validity by byte permute) changed
+// nothing either.
 constexpr int LEAN_ROWS = 2;   // records per thread: both cursor atomics are in flight before the first store needs its position
 
 template <int PW, int NW>

@@ -810,6 +810,20 @@ __device__ __forceinline__ void process_edge(const PassParams &P, uint32_t ui, u
     }
 }
 
+// "Levenshtein distance <= d" of two candidates of a bucket.  Keys of up to 63 symbols at d <= 3 take the
+// furthest-reaching-diagonals form (key.cuh lv_within_d): exact, ~200 integer operations at d = 2 and no
+// data-dependent loop, so a warp verifies 32 candidates in lockstep.  Longer keys: Myers' bit-vector algorithm
+// behind the shifted-Hamming filter (almost every candidate of a block bucket is a chance hit; the filter turns
+// most of them away for a seventh of the cost of the verify).
+template <int K, int PW>
+__device__ __forceinline__ bool verify_edit(const Key<K, PW> &ki, uint32_t li, const Key<K, PW> &kj, uint32_t lj, int d)
+{
+    if constexpr (PW <= 2) {
+        if (d <= LV_MAX_D && li <= 63u && lj <= 63u) return edit_within<K, PW>(ki, li, kj, lj, d);
+    }
+    return (d > 4 || shifted_hamming_maybe_within<K, PW>(ki, li, kj, lj, d)) && myers_within<K, PW>(ki, li, kj, lj, d);
+}
+
 template <int K, int PW>
 static __global__ void __launch_bounds__(256) compare_kernel(const __grid_constant__ PassParams P)
 {
@@ -839,10 +853,7 @@ static __global__ void __launch_bounds__(256) compare_kernel(const __grid_consta
                         bool ok;
                         if (P.edit) {
                             const uint32_t lj = P.varlen ? key_length(kj, P.pad_code, P.max_len) : P.max_len;
-                            // (almost every candidate of a block bucket is a chance hit: the shifted-Hamming filter
-                            // turns it away for a seventh of the cost of the verify)
-                            ok = (P.d > 4 || shifted_hamming_maybe_within<K, PW>(ki, li, kj, lj, P.d)) &&
-                                 myers_within<K, PW>(ki, li, kj, lj, P.d);
+                            ok = verify_edit<K, PW>(ki, li, kj, lj, P.d);
                         } else {
                             ok = hamming_within<K, PW>(ki, kj, P.d, P.varlen != 0, P.pad_code);
                         }
@@ -859,6 +870,93 @@ static __global__ void __launch_bounds__(256) compare_kernel(const __grid_consta
         cand += __shfl_xor_sync(0xFFFFFFFFu, cand, o);
     }
     if ((threadIdx.x & 31) == 0) {
+        if (merges) atomicAdd(&P.ctr->n_merges, merges);
+        if (cand) atomicAdd(&P.ctr->n_candidates, (unsigned long long)cand);
+    }
+}
+
+// The same compare as dense tiles (the default for the Levenshtein passes; FQD_COMPARE_V1=1 selects the kernel above).
+// Short pigeonhole blocks make big buckets -- config 4 at d = 2 has 8-symbol blocks, ~73 entries per bucket and 2e8
+// candidate pairs -- and the one-thread-per-entry walk above then spends its time on a dependent key load per
+// candidate and on warps whose lanes walk ranges of different lengths (31 ms for 1.6 M keys).  Here one warp owns 32
+// consecutive entries (rows).  It streams the entries behind them in chunks of 32 columns: every lane fetches ONE
+// column (entry + key, the only random loads: one per entry and chunk instead of one per candidate) into the warp's
+// shared-memory tile, then all lanes test their row against column t, t = 0..31, read by broadcast.  A row is done
+// at the ENT_LAST mark of its bucket; the warp stops when all its rows are.  Bucket boundaries only bound the work:
+// a pair is reported iff the verify passes, so whatever else lies in a tile is harmless.
+template <int KW> __host__ __device__ constexpr int dense_warps() { return KW <= 12 ? 8 : 4; }
+
+template <int K, int PW>
+static __global__ void __launch_bounds__(dense_warps<K * PW>() * 32) compare_dense_kernel(const __grid_constant__ PassParams P)
+{
+    constexpr int KW = K * PW, WARPS = dense_warps<KW>(), CW = (KW + 2) | 1;   // odd stride: conflict-free column writes
+    __shared__ uint32_t col[WARPS][32][CW];
+    const uint32_t lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
+    const uint32_t E = P.cnt[P.nb_mask + 1];   // cnt[NB] = number of entries after the scan
+    const uint32_t row0 = (blockIdx.x * WARPS + wid) * 32u;
+    uint32_t merges = 0, cand = 0;
+    if (row0 < E) {   // (warp-uniform)
+        const uint32_t i = row0 + lane;
+        const uint2 e = i < E ? P.entries[i] : make_uint2(0u, ENT_LAST);
+        const uint32_t ui = e.y & ENT_UID;
+        bool ended = (e.y & ENT_LAST) != 0;    // nothing follows the last entry of a bucket
+        Key<K, PW> ki;
+#pragma unroll
+        for (int w = 0; w < KW; w++) ki.w[w] = 0;
+        if (i < E) load_key<K, PW>(P.ukey, ui, ki);
+        const uint32_t li = P.varlen ? key_length(ki, P.pad_code, P.max_len) : P.max_len;
+        uint32_t (*tile)[CW] = col[wid];
+        for (uint32_t c0 = row0; __any_sync(WARP_FULL, !ended); c0 += 32u) {
+            __syncwarp();
+            if (c0 == row0) {
+#pragma unroll
+                for (int w = 0; w < KW; w++) tile[lane][w] = ki.w[w];
+                tile[lane][KW] = e.x;
+                tile[lane][KW + 1] = e.y;
+            } else {
+                const uint32_t j = c0 + lane;
+                const uint2 f = j < E ? P.entries[j] : make_uint2(0u, ENT_LAST);   // past the end: stops every row
+                Key<K, PW> kf;
+#pragma unroll
+                for (int w = 0; w < KW; w++) kf.w[w] = 0;
+                if (j < E) load_key<K, PW>(P.ukey, f.y & ENT_UID, kf);
+#pragma unroll
+                for (int w = 0; w < KW; w++) tile[lane][w] = kf.w[w];
+                tile[lane][KW] = f.x;
+                tile[lane][KW + 1] = f.y;
+            }
+            __syncwarp();
+#pragma unroll 2
+            for (uint32_t t = 0; t < 32u; t++) {
+                const uint32_t fx = tile[t][KW], fy = tile[t][KW + 1];
+                const bool live = !ended && c0 + t > i;
+                if (live && fx == e.x && (fy & ENT_UID) != ui && ((e.y | fy) & ENT_BUILD)) {
+                    Key<K, PW> kj;
+#pragma unroll
+                    for (int w = 0; w < KW; w++) kj.w[w] = tile[t][w];
+                    cand++;
+                    bool ok;
+                    if (P.edit) {
+                        const uint32_t lj = P.varlen ? key_length(kj, P.pad_code, P.max_len) : P.max_len;
+                        ok = verify_edit<K, PW>(ki, li, kj, lj, P.d);
+                    } else {
+                        ok = hamming_within<K, PW>(ki, kj, P.d, P.varlen != 0, P.pad_code);
+                    }
+                    if (ok) {
+                        const uint32_t uj = fy & ENT_UID;
+                        process_edge<K, PW>(P, ui, uj, P.ucount[ui], P.ucount[uj], ki, kj, merges);
+                    }
+                }
+                if (live && (fy & ENT_LAST)) ended = true;
+                if (!__any_sync(WARP_FULL, !ended)) break;
+            }
+        }
+    }
+    for (int o = 16; o; o >>= 1) {
+        merges += __shfl_xor_sync(WARP_FULL, merges, o);
+        cand += __shfl_xor_sync(WARP_FULL, cand, o);
+    }
+    if (lane == 0) {
         if (merges) atomicAdd(&P.ctr->n_merges, merges);
         if (cand) atomicAdd(&P.ctr->n_candidates, (unsigned long long)cand);
     }

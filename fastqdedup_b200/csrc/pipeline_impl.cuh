@@ -8,6 +8,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <cmath>
 #include <type_traits>
 #include <vector>
 
@@ -205,8 +206,15 @@ inline EdgeSource single_edges(const uint2 *edges, const uint32_t *n_edges, uint
 // HOST jobs with fixed-length ACGTN rows: the host packs chunk i+1 (threads, AVX-512) while chunk i crosses PCIe at
 // 3 bits per symbol and the partition kernel unpacks the chunk before that.  RC_PACK_INVALID: a byte outside ACGTN
 // (the caller clears the partition buffers and takes the ASCII path, which reports it).
-template <int PW, int NW>
-int launch_packed_chunks(fqd_context *ctx, const DeviceJob &job, const IngestParams &pp, uint32_t index_base, StageTimes &tt)
+//
+// Packing is the slower of the two legs on the hosts measured (16 threads pack 100 M x 36 nt in 54 ms; the packed
+// rows cross PCIe in 29 ms), so the link would idle half of the time.  Hybrid: whenever the copies queued so far
+// would drain before the next chunk is packed, that chunk is sent as it is (ASCII, straight from the caller's
+// buffer -- no host work at all) and goes through the ASCII partition kernel; the packer threads never wait and the
+// link carries raw rows in what would be its idle time.  FQD_HOST_PACK_HYBRID=0 packs every chunk.
+template <int PW, int NW, typename LaunchAscii>
+int launch_packed_chunks(fqd_context *ctx, const DeviceJob &job, const IngestParams &pp, uint32_t index_base, StageTimes &tt,
+                         LaunchAscii launch_ascii)
 {
     cudaStream_t s = ctx->stream;
     const uint64_t n = job.n;
@@ -230,29 +238,72 @@ int launch_packed_chunks(fqd_context *ctx, const DeviceJob &job, const IngestPar
         FQD_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         ctx->chunk_events.push_back(e);
     }
+    // raw chunks need the caller's buffer to be page-locked (a pageable source makes the copy synchronous and slow)
+    bool hybrid = !(getenv("FQD_HOST_PACK_HYBRID") && atoi(getenv("FQD_HOST_PACK_HYBRID")) == 0) && nchunks > 2;
+    if (hybrid) {
+        cudaPointerAttributes at{};
+        hybrid = cudaPointerGetAttributes(&at, job.host_keys) == cudaSuccess && at.type == cudaMemoryTypeHost;
+        cudaGetLastError();
+    }
     FQD_CUDA(cudaEventRecord(ctx->ev[9], s));
     FQD_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev[9], 0));   // buffers are allocated / idle
     FQD_CUDA(cudaEventRecord(ctx->ev[10], ctx->copy_stream));
-    uint8_t *dev = const_cast<uint8_t *>(job.keys);                   // (the ASCII buffer is large enough for the packed rows)
+    uint8_t *dev = const_cast<uint8_t *>(job.keys);   // every chunk lands inside its own range of the ASCII buffer
+    using clock = std::chrono::steady_clock;
+    auto now = [&] { return std::chrono::duration<double>(clock::now().time_since_epoch()).count(); };
+    double link_free_at = now();                      // estimate of when the copies queued so far are done
+    double link_bps = 50e9, pack_s = 0.0;             // refined below from what this job measures
+    size_t packed_slot = 0, last_copy = (size_t)-1;
+    double first_copy_t0 = 0.0;
+    size_t first_copy_bytes = 0;
+    bool first_copy_timed = false;
     for (size_t i = 0; i < nchunks; i++) {
         const uint64_t c0 = i * chunk, cn = std::min<uint64_t>(chunk, n - c0);
-        const int slot = (int)(i & 1);
-        if (i >= 2) FQD_CUDA(cudaEventSynchronize(ctx->pack_ev[slot]));   // the copy out of this slot is done
-        uint32_t *stage = static_cast<uint32_t *>(ctx->pack_stage[slot]);
-        if (pack_keys_parallel(job.host_keys + c0 * job.key_stride, cn, L, job.key_stride, stage) != cn) {
-            FQD_CUDA(cudaStreamSynchronize(ctx->copy_stream));
-            return RC_PACK_INVALID;
+        double t = now();
+        if (last_copy != (size_t)-1 && cudaEventQuery(ctx->chunk_events[last_copy]) == cudaSuccess) {
+            if (!first_copy_timed && last_copy == 0 && t > first_copy_t0) {   // (an upper bound of its duration: good enough)
+                link_bps = std::max(10e9, std::min(64e9, (double)first_copy_bytes / (t - first_copy_t0)));
+                first_copy_timed = true;
+            }
+            link_free_at = std::min(link_free_at, t);   // the link has drained
         }
-        FQD_CUDA(cudaMemcpyAsync(dev + c0 * rw * 4, stage, cn * rw * 4, cudaMemcpyHostToDevice, ctx->copy_stream));
-        ctx->h2d_bytes += cn * rw * 4;
-        FQD_CUDA(cudaEventRecord(ctx->pack_ev[slot], ctx->copy_stream));
-        FQD_CUDA(cudaEventRecord(ctx->chunk_events[i], ctx->copy_stream));
-        FQD_CUDA(cudaStreamWaitEvent(s, ctx->chunk_events[i], 0));
+        // send raw when the link would run dry while this chunk is being packed (never the last chunk: its copy
+        // is the tail of the job, keep it short)
+        const double est_pack = pack_s > 0.0 ? pack_s * (double)cn / (double)chunk : 0.0;
+        const bool raw = hybrid && i + 1 < nchunks && (i == 0 || link_free_at - t < est_pack);
         IngestParams cp = pp;
         cp.n = cn;
-        cp.keys = dev + c0 * rw * 4;
         cp.index_base = index_base + (uint32_t)c0;
-        partition_packed_kernel<PW, NW><<<cdiv(cn, 256 * LEAN_ROWS), 256, 0, s>>>(cp);
+        size_t bytes;
+        if (raw) {
+            bytes = (size_t)cn * L;
+            FQD_CUDA(cudaMemcpyAsync(dev + c0 * L, job.host_keys + c0 * job.key_stride, bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
+            cp.keys = dev + c0 * L;
+        } else {
+            const int slot = (int)(packed_slot++ & 1);
+            if (packed_slot > 2) FQD_CUDA(cudaEventSynchronize(ctx->pack_ev[slot]));   // the copy out of this slot is done
+            uint32_t *stage = static_cast<uint32_t *>(ctx->pack_stage[slot]);
+            const double p0 = now();
+            if (pack_keys_parallel(job.host_keys + c0 * job.key_stride, cn, L, job.key_stride, stage) != cn) {
+                FQD_CUDA(cudaStreamSynchronize(ctx->copy_stream));
+                return RC_PACK_INVALID;
+            }
+            t = now();
+            const double took = (t - p0) * (double)chunk / (double)cn;
+            pack_s = pack_s > 0.0 ? 0.5 * (pack_s + took) : took;
+            bytes = (size_t)cn * rw * 4;
+            FQD_CUDA(cudaMemcpyAsync(dev + c0 * L, stage, bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
+            FQD_CUDA(cudaEventRecord(ctx->pack_ev[slot], ctx->copy_stream));
+            cp.keys = dev + c0 * L;
+        }
+        if (i == 0) { first_copy_t0 = t; first_copy_bytes = bytes; }
+        link_free_at = std::max(link_free_at, t) + (double)bytes / link_bps;
+        ctx->h2d_bytes += bytes;
+        FQD_CUDA(cudaEventRecord(ctx->chunk_events[i], ctx->copy_stream));
+        FQD_CUDA(cudaStreamWaitEvent(s, ctx->chunk_events[i], 0));
+        last_copy = i;
+        if (raw) launch_ascii(cp);
+        else partition_packed_kernel<PW, NW><<<cdiv(cn, 256 * LEAN_ROWS), 256, 0, s>>>(cp);
         tt.launches++;
     }
     FQD_CUDA(cudaGetLastError());
@@ -292,14 +343,25 @@ int launch_partition(fqd_context *ctx, const DeviceJob &job, const Codec &codec,
             !getenv("FQD_NO_SWAR") && !getenv("FQD_NO_LEAN"))
             lean_nw = (int)(job.key_len >> 2);
     }
+    // the lean ASCII partition kernel over one chunk of rows (cp.keys / cp.n / cp.index_base set by the caller)
+    auto launch_lean = [&](const IngestParams &cp) {
+        if constexpr (K == 3 && slot_words(K * PW) == PART_RW) {
+            if (lean_nw == 3) { partition_dna_kernel<PW, 3><<<cdiv(cp.n, 256 * LEAN_ROWS), 256, 0, s>>>(cp); return; }
+            if (lean_nw == 6) { partition_dna_kernel<PW, 6><<<cdiv(cp.n, 256 * LEAN_ROWS), 256, 0, s>>>(cp); return; }
+            if constexpr (PW >= 2) {
+                if (lean_nw == 9) { partition_dna_kernel<PW, 9><<<cdiv(cp.n, 256 * LEAN_ROWS), 256, 0, s>>>(cp); return; }
+                if (lean_nw == 12) { partition_dna_kernel<PW, 12><<<cdiv(cp.n, 256 * LEAN_ROWS), 256, 0, s>>>(cp); return; }
+            }
+        }
+    };
     if constexpr (K == 3 && slot_words(K * PW) == PART_RW) {
         if (lean_nw && job.host_keys && job.host_pack && job.n) {
             int rc = RC_PACK_INVALID;
-            if (lean_nw == 3) rc = launch_packed_chunks<PW, 3>(ctx, job, pp, index_base, tt);
-            else if (lean_nw == 6) rc = launch_packed_chunks<PW, 6>(ctx, job, pp, index_base, tt);
+            if (lean_nw == 3) rc = launch_packed_chunks<PW, 3>(ctx, job, pp, index_base, tt, launch_lean);
+            else if (lean_nw == 6) rc = launch_packed_chunks<PW, 6>(ctx, job, pp, index_base, tt, launch_lean);
             if constexpr (PW >= 2) {
-                if (lean_nw == 9) rc = launch_packed_chunks<PW, 9>(ctx, job, pp, index_base, tt);
-                else if (lean_nw == 12) rc = launch_packed_chunks<PW, 12>(ctx, job, pp, index_base, tt);
+                if (lean_nw == 9) rc = launch_packed_chunks<PW, 9>(ctx, job, pp, index_base, tt, launch_lean);
+                else if (lean_nw == 12) rc = launch_packed_chunks<PW, 12>(ctx, job, pp, index_base, tt, launch_lean);
             }
             if (rc == FQD_OK) return FQD_OK;
             if (rc != RC_PACK_INVALID) return rc;
@@ -309,14 +371,7 @@ int launch_partition(fqd_context *ctx, const DeviceJob &job, const Codec &codec,
         }
     }
     FQD_TRY(for_each_input_chunk(ctx, job, pp, index_base, nullptr, tt, [&](const IngestParams &cp) {
-        if constexpr (K == 3 && slot_words(K * PW) == PART_RW) {
-            if (lean_nw == 3) { partition_dna_kernel<PW, 3><<<cdiv(cp.n, 256 * LEAN_ROWS), 256, 0, s>>>(cp); return; }
-            if (lean_nw == 6) { partition_dna_kernel<PW, 6><<<cdiv(cp.n, 256 * LEAN_ROWS), 256, 0, s>>>(cp); return; }
-            if constexpr (PW >= 2) {
-                if (lean_nw == 9) { partition_dna_kernel<PW, 9><<<cdiv(cp.n, 256 * LEAN_ROWS), 256, 0, s>>>(cp); return; }
-                if (lean_nw == 12) { partition_dna_kernel<PW, 12><<<cdiv(cp.n, 256 * LEAN_ROWS), 256, 0, s>>>(cp); return; }
-            }
-        }
+        if (lean_nw) { launch_lean(cp); return; }
         ingest_kernel<K, PW><<<cdiv(cp.n, BR), 256, smem, s>>>(cp);
     }));
     FQD_CUDA(cudaGetLastError());
@@ -685,7 +740,15 @@ int stage_passes(fqd_context *ctx, const DeviceJob &job, const Codec &codec, con
         tt.launches += 6;             // sig_count, 3 scan kernels, scatter, compare
         FQD_CUDA(cudaEventRecord(cev[2 * j], s));
         if (fat) compare_fat_kernel<K, PW><<<cdiv(E, 256), 256, 0, s>>>(pp);
-        else compare_kernel<K, PW><<<cdiv(E, 256), 256, 0, s>>>(pp);
+        else {
+            // big buckets (short blocks: many keys per block value) take the dense tiles, small ones the per-entry walk
+            // (measured on config 4, 1.6 M keys of 24 nt: d = 2 / 8-nt blocks 24 vs 32 ms, d = 1 / 12-nt blocks 1.7 vs 1.0 ms)
+            const double block_values = std::pow(4.0, std::min<double>(pp.fix_bl, 20.0));
+            bool dense = (double)E > 8.0 * block_values;
+            if (const char *e = getenv("FQD_COMPARE_DENSE")) dense = atoi(e) != 0;   // measurement switch
+            if (dense) compare_dense_kernel<K, PW><<<cdiv(E, 32u * dense_warps<KW>()), 32 * dense_warps<KW>(), 0, s>>>(pp);
+            else compare_kernel<K, PW><<<cdiv(E, 256), 256, 0, s>>>(pp);
+        }
         FQD_CUDA(cudaEventRecord(cev[2 * j + 1], s));
         FQD_CUDA(cudaGetLastError());
         return FQD_OK;

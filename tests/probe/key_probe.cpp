@@ -94,6 +94,7 @@ int run(int op, const HostCodec &hc, const uint8_t *a, uint32_t la, const uint8_
         return block0_hash<K, PW>(ka, p2, 99) == block0_hash<K, PW>(kb, p2, 99) ? 1 : 0;
     case 11: *out64 = hash_key32<K, PW>(ka); return 0;
     case 12: return shifted_hamming_maybe_within<K, PW>(ka, la, kb, lb, d) ? 1 : 0;
+    case 13: return edit_within<K, PW>(ka, la, kb, lb, d) ? 1 : 0;
     }
     return -1;
 }

@@ -12,7 +12,7 @@ SRC = os.path.join(ROOT, "tests", "probe", "key_probe.cpp")
 OUT = os.path.join(ROOT, "tests", "probe", "build", "key_probe.so")
 
 OPS = dict(hamming=0, myers=1, less=2, equal=3, length=4, blockeq=5, hash=6, symbol=7, swar=8, fixed=9,
-           block0eq=10, hash32=11, shd=12)
+           block0eq=10, hash32=11, shd=12, edit=13)
 
 
 @pytest.fixture(scope="module")
@@ -201,3 +201,38 @@ def test_shifted_hamming_filter_never_rejects_a_neighbour(probe, oracle, K, PW, 
                 rejected += passed == 0
     if total > 50 and len(alphabet) <= 10:
         assert rejected > 0.7 * total, (rejected, total)
+
+
+@pytest.mark.parametrize("K,PW,alphabet,L", CASES)
+def test_edit_within_matches_oracle(probe, oracle, K, PW, alphabet, L):
+    """edit_within (furthest-reaching diagonals for keys of up to 63 symbols and d <= 3, Myers otherwise) is the
+    reference's within_edit_distance: mutated and random pairs, all lengths including empty, PAD in play."""
+    rng = np.random.default_rng(K * 977 + PW * 13 + L)
+    hits = 0
+    for it in range(4000):
+        la = L if it % 3 else int(rng.integers(0, L + 1))
+        a = bytes(rng.choice(list(alphabet), size=la).astype(np.uint8))
+        d = int(rng.integers(0, 5))
+        if it % 5 == 0:
+            b = bytes(rng.choice(list(alphabet), size=int(rng.integers(max(0, la - 3), min(L, la + 3) + 1))).astype(np.uint8))
+        else:
+            b = mutate(rng, a, alphabet, int(rng.integers(0, d + 3)), indel=True)[:L]
+        want = bool(oracle.within_distance(a, b, d, True))
+        hits += want
+        for varlen in ((True, False) if len(a) == len(b) else (True,)):
+            maxlen = L if varlen else len(a)
+            got = probe(K, PW, "edit", alphabet, varlen, a, b, maxlen, d)
+            assert got == int(want), (a, b, d, varlen, got, want)
+            assert probe(K, PW, "edit", alphabet, varlen, b, a, maxlen if varlen else len(b), d) == int(want), (b, a, d)
+    assert 400 < hits < 3600
+
+
+def test_edit_within_short_keys_exhaustive(probe, oracle):
+    """All pairs of strings of length <= 4 over two letters, d = 1..3: every boundary case of the diagonal form."""
+    import itertools
+    words = [bytes(w) for n in range(0, 5) for w in itertools.product(b"AC", repeat=n)]
+    for a in words:
+        for b in words:
+            for d in (1, 2, 3):
+                want = int(bool(oracle.within_distance(a, b, d, True)))
+                assert probe(3, 1, "edit", b"ACGTN", True, a, b, 8, d) == want, (a, b, d)
