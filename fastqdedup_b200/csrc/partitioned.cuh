@@ -72,7 +72,15 @@ struct TileSource {
     uint32_t ntiles;                  // owned tiles
     uint32_t region;                  // records per region of every rank's buffer (PartParams::region)
     int peer_ldg;                     // measurement switch: fetch peer fragments with 16-byte loads instead of bulk copies
+    // Split launches (one GPU): tiles are handled by two instances of a tile kernel, one whose shared-memory tile
+    // holds TILE_R_SMALL records (more resident blocks per SM: the tile kernels are latency-bound) for the tiles
+    // that fit it, one with full-size tiles for the rest.  A launch handles the tiles with cnt_lo < fill <= cnt_hi
+    // (cnt_hi == 0: no window); oversize tiles belong to the launch whose window reaches TILE_R.  `list` (with its
+    // device-side length) names the tiles of a launch explicitly: blocks then loop over it.
+    uint32_t cnt_lo = 0, cnt_hi = 0;
+    const uint32_t *list = nullptr, *n_list = nullptr;
 };
+constexpr int TILE_R_SMALL = 384;    // mean fill 307 +- ~50: nine tiles in ten fit
 
 __device__ __forceinline__ void tile_load_rec(const uint32_t *recs, uint32_t i, uint32_t (&e)[PART_RW])
 {
@@ -134,7 +142,9 @@ __device__ __forceinline__ uint32_t stage_tile(uint32_t *recs, uint32_t *tab, ui
         total += c;
     }
     if (total == 0) return 0;
-    if (over || total > (uint32_t)TILE_R) return TILE_R + 1;
+    const uint32_t hi = S.cnt_hi ? S.cnt_hi : (uint32_t)TILE_R;
+    if (over || total > (uint32_t)TILE_R) return hi >= (uint32_t)TILE_R ? TILE_R + 1 : 0;
+    if (total <= S.cnt_lo || total > hi) return 0;   // another launch's tile
     const uint32_t mbar_a = (uint32_t)__cvta_generic_to_shared(&mbar);
     if (tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar_a), "r"(1) : "memory");
@@ -188,6 +198,7 @@ __device__ __forceinline__ uint32_t stage_tile(uint32_t *recs, uint32_t *tab, ui
         } while (!done);
     }
     __syncthreads();
+    if (tid == 0) asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(mbar_a) : "memory");   // (a block may stage again)
     return total;
 }
 
@@ -485,20 +496,18 @@ struct NextPass {
     int pass_j;
 };
 
-template <int K, int PW, bool FUSED>
-static __global__ void __launch_bounds__(TILE_THREADS) dedupe_tile_kernel(const __grid_constant__ TileSource S,
-                                                                          const __grid_constant__ DedupeOut O,
-                                                                          const __grid_constant__ PassParams P,
-                                                                          const __grid_constant__ EdgeSink E,
-                                                                          const __grid_constant__ NextPass X)
+template <int K, int PW, bool FUSED, int TR>
+__device__ __forceinline__ void dedupe_tile_body(const uint32_t p, const TileSource &S, const DedupeOut &O, const PassParams &P,
+                                                 const EdgeSink &E, const NextPass &X)
 {
     constexpr int KW = K * PW, RW = slot_words(KW);
     static_assert(RW == PART_RW, "partitioned plan: 32-byte records");
-    __shared__ __align__(16) uint32_t recs[TILE_R * PART_RW];
+    static_assert(TR % TILE_THREADS == 0 && TR <= TILE_R, "tile capacity");
+    __shared__ __align__(16) uint32_t recs[TR * PART_RW];
     __shared__ uint32_t tab[TILE_T];
     __shared__ uint32_t warp_sums[32];
     __shared__ uint32_t total, s_base;
-    const uint32_t p = blockIdx.x, tid = threadIdx.x;   // p: owned tile
+    const uint32_t tid = threadIdx.x;   // p: owned tile
     const uint32_t cnt = stage_tile(recs, tab, TILE_T, S, p);
     if (cnt == 0) return;
     if (cnt > (uint32_t)TILE_R) {
@@ -510,7 +519,7 @@ static __global__ void __launch_bounds__(TILE_THREADS) dedupe_tile_kernel(const 
     // meets the representative and adds its weight / lowers the first index there.
     uint32_t rep = 0;   // bit r: my record of round r is a representative
 #pragma unroll
-    for (int r = 0; r < TILE_R / TILE_THREADS; r++) {
+    for (int r = 0; r < TR / TILE_THREADS; r++) {
         const uint32_t i = r * TILE_THREADS + tid;
         if (i >= cnt) break;
         uint32_t e[PART_RW];
@@ -542,10 +551,10 @@ static __global__ void __launch_bounds__(TILE_THREADS) dedupe_tile_kernel(const 
     // representatives -> dense unique arrays (keys whose every record was filtered are dropped).
     // Their tile-local indices are compacted first so that the copy-out (and the fused pass 0)
     // run with full warps and neighbouring threads write neighbouring unique ids.
-    __shared__ uint16_t replist[TILE_R];
+    __shared__ uint16_t replist[TR];
     uint32_t nval = 0;
 #pragma unroll
-    for (int r = 0; r < TILE_R / TILE_THREADS; r++) {
+    for (int r = 0; r < TR / TILE_THREADS; r++) {
         if (!((rep >> r) & 1u)) continue;
         const uint32_t i = r * TILE_THREADS + tid;
         if (recs[(size_t)i * PART_RW + KW] != 0 || O.keep_zero) nval++;
@@ -554,7 +563,7 @@ static __global__ void __launch_bounds__(TILE_THREADS) dedupe_tile_kernel(const 
     uint32_t off = block_exclusive_scan(nval, &total, warp_sums);
     if (tid == 0) s_base = total ? atomicAdd(O.n_unique, total) : 0u;
 #pragma unroll
-    for (int r = 0; r < TILE_R / TILE_THREADS; r++)
+    for (int r = 0; r < TR / TILE_THREADS; r++)
         if ((rep >> r) & 1u) replist[off++] = (uint16_t)(r * TILE_THREADS + tid);
     __syncthreads();
     const uint32_t nrep = total, base = s_base;
@@ -593,7 +602,9 @@ static __global__ void __launch_bounds__(TILE_THREADS) dedupe_tile_kernel(const 
     if constexpr (FUSED) {
         __syncthreads();   // ids are in place, the dedupe probes are over: the table is free for pass 0
         uint32_t merges = 0, cand = 0;
-        // the uniques of a tile need half the table; its other half buffers the edges
+        // the uniques of a tile need half the table; its other half buffers the edges.  (Measured and dropped in round 2:
+        // the unions of pass 0 inside the tile -- 16-bit tile-local forests in that half, every unique leaving with its
+        // parent links -- save init_forest + the pass-0 apply_edges, 0.2 ms, and cost the tile kernel the same 0.2 ms.)
         tile_bucket_pass<K, PW, false>(
             recs, tab, TILE_T / 2, tab + TILE_T / 2, TILE_T / 2, nrep, [&](uint32_t k) { return (uint32_t)replist[k]; },
             [&](const Key<K, PW> &ki) {   // pass 0: the leading block
@@ -603,6 +614,35 @@ static __global__ void __launch_bounds__(TILE_THREADS) dedupe_tile_kernel(const 
             P, E, merges, cand);
         tile_stats(P.ctr, 0, cand);
     }
+}
+
+// TR: records the shared-memory tile holds; MINB: resident blocks per SM the register allocation must allow
+template <int K, int PW, bool FUSED, int TR = TILE_R, int MINB = 10>
+static __global__ void __launch_bounds__(TILE_THREADS, MINB) dedupe_tile_kernel(const __grid_constant__ TileSource S,
+                                                                                const __grid_constant__ DedupeOut O,
+                                                                                const __grid_constant__ PassParams P,
+                                                                                const __grid_constant__ EdgeSink E,
+                                                                                const __grid_constant__ NextPass X)
+{
+    if (S.list) {
+        const uint32_t n = *S.n_list;
+        for (uint32_t t = blockIdx.x; t < n; t += gridDim.x) {
+            dedupe_tile_body<K, PW, FUSED, TR>(S.list[t], S, O, P, E, X);
+            __syncthreads();   // the next tile reuses the shared memory
+        }
+    } else {
+        dedupe_tile_body<K, PW, FUSED, TR>(blockIdx.x, S, O, P, E, X);
+    }
+}
+
+// Tiles whose fill exceeds `small` (they need the full-size launch), as a list; one GPU only (fill = the cursor).
+static __global__ void __launch_bounds__(256) classify_tiles_kernel(const uint32_t *__restrict__ cursor, uint32_t nparts, uint32_t small,
+                                                                    uint32_t *__restrict__ list, uint32_t *n_list)
+{
+    const uint32_t i = blockIdx.x * 256u + threadIdx.x;
+    const bool big = i < nparts && cursor[i] > small;
+    const uint32_t pos = block_reserve(big, n_list);
+    if (big) list[pos] = i;
 }
 
 // Spill path: the records of the oversize partitions (their full regions: TILE_R / 256 consecutive
@@ -676,17 +716,15 @@ static __global__ void __launch_bounds__(256) bucket_partition_kernel(const __gr
         if (go[r] && pos[r] < Q.region) store_rec_stream(Q.buf + ((size_t)part[r] * Q.region + pos[r]) * PART_RW, e[r]);
 }
 
-template <int K, int PW>
-static __global__ void __launch_bounds__(TILE_THREADS) bucket_tile_kernel(const __grid_constant__ TileSource S,
-                                                                          const __grid_constant__ PassParams P,
-                                                                          const __grid_constant__ EdgeSink E)
+template <int K, int PW, int TR>
+__device__ __forceinline__ void bucket_tile_body(const uint32_t p, const TileSource &S, const PassParams &P, const EdgeSink &E)
 {
     constexpr int KW = K * PW, RW = fat_words(KW);
     static_assert(RW == PART_RW, "partitioned plan: 32-byte records");
-    __shared__ __align__(16) uint32_t recs[TILE_R * PART_RW];
+    __shared__ __align__(16) uint32_t recs[TR * PART_RW];
     __shared__ uint32_t tab[TILE_T];
     __shared__ uint32_t s_edges[TILE_E];
-    const uint32_t p = blockIdx.x, tid = threadIdx.x;   // p: owned tile
+    const uint32_t tid = threadIdx.x;   // p: owned tile
     const uint32_t cnt = stage_tile(recs, tab, 0, S, p);   // (the pass clears the table itself)
     if (cnt == 0) return;
     if (cnt > (uint32_t)TILE_R) {
@@ -705,6 +743,22 @@ static __global__ void __launch_bounds__(TILE_THREADS) bucket_tile_kernel(const 
         },
         P, E, merges, cand);
     tile_stats(P.ctr, merges, cand);
+}
+
+template <int K, int PW, int TR = TILE_R, int MINB = 10>
+static __global__ void __launch_bounds__(TILE_THREADS, MINB) bucket_tile_kernel(const __grid_constant__ TileSource S,
+                                                                                const __grid_constant__ PassParams P,
+                                                                                const __grid_constant__ EdgeSink E)
+{
+    if (S.list) {
+        const uint32_t n = *S.n_list;
+        for (uint32_t t = blockIdx.x; t < n; t += gridDim.x) {
+            bucket_tile_body<K, PW, TR>(S.list[t], S, P, E);
+            __syncthreads();   // the next tile reuses the shared memory
+        }
+    } else {
+        bucket_tile_body<K, PW, TR>(blockIdx.x, S, P, E);
+    }
 }
 
 // All pairs among the uniques [lo, hi) (the handful that left the dedupe stage through the spill
@@ -772,8 +826,7 @@ struct EdgeFlags {
     int any_edge;         // highest_count: `linked` for every edge
 };
 
-// APPLY_UNROLL: edges a thread fetches (from a peer's HBM) before it hooks them
-template <int APPLY_UNROLL = 1>
+template <int APPLY_UNROLL = 1>   // (unused: kept so that the launch sites read the same)
 static __global__ void __launch_bounds__(256) apply_edges_kernel(const __grid_constant__ EdgeSource E, uint32_t *parent_full,
                                                                  uint32_t *parent_one, const __grid_constant__ EdgeFlags F,
                                                                  DevCounters *ctr)
@@ -785,15 +838,21 @@ static __global__ void __launch_bounds__(256) apply_edges_kernel(const __grid_co
         const uint32_t n = min(E.n_edges[(size_t)g * E.n_stride], E.cap[g]);
         const uint32_t lo = E.first ? min(E.first[(size_t)g * E.first_stride], n) : 0u;
         const uint2 *edges = E.edges[g];
-        for (uint32_t i0 = lo + blockIdx.x * 256u + threadIdx.x; i0 < n; i0 += APPLY_UNROLL * stride) {
-            uint2 batch[APPLY_UNROLL];
+        // The list may live in a peer's HBM (2-3 us per load over NVLink): a thread keeps the loads of its next
+        // APPLY_AHEAD edges in flight while it hooks the current one, in list order (the edges of a pass-0 tile are
+        // neighbours in the forest; batching the fetches instead broke that locality and was slower).
+        constexpr int APPLY_AHEAD = 2;
+        uint32_t i0 = lo + blockIdx.x * 256u + threadIdx.x;
+        uint2 ahead[APPLY_AHEAD];
 #pragma unroll
-            for (int u = 0; u < APPLY_UNROLL; u++)
-                if (i0 + u * stride < n) batch[u] = __ldcs(edges + i0 + u * stride);
+        for (int a = 0; a < APPLY_AHEAD; a++)
+            if ((uint64_t)i0 + (uint64_t)a * stride < n) ahead[a] = __ldcs(edges + i0 + a * stride);
+        for (; i0 < n; i0 += stride) {
+            const uint2 ed = ahead[0];
 #pragma unroll
-            for (int u = 0; u < APPLY_UNROLL; u++) {
-                if (i0 + u * stride >= n) break;
-                const uint2 ed = batch[u];
+            for (int a = 0; a + 1 < APPLY_AHEAD; a++) ahead[a] = ahead[a + 1];
+            if ((uint64_t)i0 + (uint64_t)APPLY_AHEAD * stride < n) ahead[APPLY_AHEAD - 1] = __ldcs(edges + i0 + APPLY_AHEAD * stride);
+            {
                 const uint32_t st = ed.y & EDGE_STATE, idx = ed.x, idy = ed.y & EDGE_ID;
                 const uint32_t x = slot_of_id(idx, E.G, E.id_stride), y = slot_of_id(idy, E.G, E.id_stride);
                 if (uf_union(parent_full, x, y)) merges++;
@@ -939,10 +998,17 @@ static __global__ void __launch_bounds__(256) best_candidate_kernel(const __grid
     for (uint32_t k = 0; k < P.G; k++) {
         const uint32_t g = (k + blockIdx.x) % P.G;
         const uint32_t n = min(P.n_cand[(size_t)g * P.n_stride], P.cap[g]);
-        for (uint32_t i = blockIdx.x * 256u + threadIdx.x; i < n; i += gridDim.x * 256u) {
+        // (a peer's list: the loads of the next record are in flight while this one is reduced)
+        const uint32_t step = gridDim.x * 256u;
+        uint32_t i = blockIdx.x * 256u + threadIdx.x;
+        uint32_t ne[PART_RW], nr = 0;
+        if (i < n) { load_rec_stream(P.cand[g] + (size_t)i * PART_RW, ne); nr = __ldcs(P.cand_root[g] + i); }
+        for (; i < n; i += step) {
             uint32_t e[PART_RW];
-            load_rec_stream(P.cand[g] + (size_t)i * PART_RW, e);
-            const uint32_t r = __ldcs(P.cand_root[g] + i);
+#pragma unroll
+            for (int w = 0; w < PART_RW; w++) e[w] = ne[w];
+            const uint32_t r = nr;
+            if ((uint64_t)i + step < n) { load_rec_stream(P.cand[g] + (size_t)(i + step) * PART_RW, ne); nr = __ldcs(P.cand_root[g] + i + step); }
             if (e[KW] == 0) { P.deadroot[r] = 1; continue; }   // (only directional jobs send count 0)
             const uint32_t me = (g << 28) | i;
             Key<K, PW> km;

@@ -183,6 +183,36 @@ bool codec_is_dna(const Codec &c)
            c.lut['T'] == 2 && c.lut['G'] == 3 && c.lut['N'] == 7;
 }
 
+// Split launch of a tile kernel (one GPU): tiles of up to TILE_R_SMALL records go through the instance with the small
+// shared-memory tile (12 resident blocks per SM instead of 10 -- the tile kernels wait on barriers and round trips,
+// more tiles in flight is what makes them faster), the rest through the full-size instance, whose blocks loop over
+// the list classify_tiles_kernel wrote.  FQD_TILE_SPLIT=0: one full-size launch for all tiles.
+inline bool tile_split_enabled(uint32_t nparts)
+{
+    const char *e = getenv("FQD_TILE_SPLIT");
+    if (e) return atoi(e) != 0;
+    return nparts >= 4096;   // (small jobs: one launch, the list is not worth a kernel)
+}
+struct TileSplit {
+    uint32_t *list = nullptr, *n_list = nullptr;
+};
+inline int tile_split_prepare(fqd_context *ctx, const PartParams &q, TileSplit &ts, StageTimes &tt)
+{
+    FQD_TRY(arena(ctx, (size_t)q.nparts, &ts.list));
+    FQD_TRY(arena(ctx, 4, &ts.n_list));
+    FQD_CUDA(cudaMemsetAsync(ts.n_list, 0, 4, ctx->stream));
+    classify_tiles_kernel<<<cdiv(q.nparts, 256), 256, 0, ctx->stream>>>(q.cursor, q.nparts, (uint32_t)TILE_R_SMALL, ts.list, ts.n_list);
+    tt.launches++;
+    return FQD_OK;
+}
+inline TileSource small_tiles(TileSource S) { S.cnt_lo = 0; S.cnt_hi = TILE_R_SMALL; return S; }
+inline TileSource large_tiles(TileSource S, const TileSplit &ts)
+{
+    S.cnt_lo = TILE_R_SMALL; S.cnt_hi = TILE_R; S.list = ts.list; S.n_list = ts.n_list;
+    return S;
+}
+constexpr int TILE_SMALL_BLOCKS = 12;   // resident blocks per SM the small-tile instances are compiled for
+
 constexpr uint64_t PARTITION_MIN_RECORDS = 4u << 20;
 constexpr uint64_t PARTITION_MIN_UNIQUES = 1u << 20;
 
@@ -344,15 +374,17 @@ int launch_partition(fqd_context *ctx, const DeviceJob &job, const Codec &codec,
             lean_nw = (int)(job.key_len >> 2);
     }
     // the lean ASCII partition kernel over one chunk of rows (cp.keys / cp.n / cp.index_base set by the caller)
-    auto launch_lean = [&](const IngestParams &cp) {
+    // (false: no instance for this key length -- the general ingest kernel takes the chunk)
+    auto launch_lean = [&](const IngestParams &cp) -> bool {
         if constexpr (K == 3 && slot_words(K * PW) == PART_RW) {
-            if (lean_nw == 3) { partition_dna_kernel<PW, 3><<<cdiv(cp.n, 256 * LEAN_ROWS), 256, 0, s>>>(cp); return; }
-            if (lean_nw == 6) { partition_dna_kernel<PW, 6><<<cdiv(cp.n, 256 * LEAN_ROWS), 256, 0, s>>>(cp); return; }
+            if (lean_nw == 3) { partition_dna_kernel<PW, 3><<<cdiv(cp.n, 256 * LEAN_ROWS), 256, 0, s>>>(cp); return true; }
+            if (lean_nw == 6) { partition_dna_kernel<PW, 6><<<cdiv(cp.n, 256 * LEAN_ROWS), 256, 0, s>>>(cp); return true; }
             if constexpr (PW >= 2) {
-                if (lean_nw == 9) { partition_dna_kernel<PW, 9><<<cdiv(cp.n, 256 * LEAN_ROWS), 256, 0, s>>>(cp); return; }
-                if (lean_nw == 12) { partition_dna_kernel<PW, 12><<<cdiv(cp.n, 256 * LEAN_ROWS), 256, 0, s>>>(cp); return; }
+                if (lean_nw == 9) { partition_dna_kernel<PW, 9><<<cdiv(cp.n, 256 * LEAN_ROWS), 256, 0, s>>>(cp); return true; }
+                if (lean_nw == 12) { partition_dna_kernel<PW, 12><<<cdiv(cp.n, 256 * LEAN_ROWS), 256, 0, s>>>(cp); return true; }
             }
         }
+        return false;
     };
     if constexpr (K == 3 && slot_words(K * PW) == PART_RW) {
         if (lean_nw && job.host_keys && job.host_pack && job.n) {
@@ -371,7 +403,7 @@ int launch_partition(fqd_context *ctx, const DeviceJob &job, const Codec &codec,
         }
     }
     FQD_TRY(for_each_input_chunk(ctx, job, pp, index_base, nullptr, tt, [&](const IngestParams &cp) {
-        if (lean_nw) { launch_lean(cp); return; }
+        if (lean_nw && launch_lean(cp)) return;
         ingest_kernel<K, PW><<<cdiv(cp.n, BR), 256, smem, s>>>(cp);
     }));
     FQD_CUDA(cudaGetLastError());
@@ -482,9 +514,29 @@ int stage_dedupe(fqd_context *ctx, const DeviceJob &job, const Codec &codec, uin
                     nx.st = block_start(job.max_len, 1u, (uint32_t)job.d + 1u);
                     nx.bl = block_start(job.max_len, 2u, (uint32_t)job.d + 1u) - nx.st;
                 }
-                dedupe_tile_kernel<K, PW, true><<<nparts, TILE_THREADS, 0, s>>>(single_source(part), out, p0, sink0, nx);
+                if (tile_split_enabled(nparts)) {
+                    TileSplit ts;
+                    FQD_TRY(tile_split_prepare(ctx, part, ts, tt));
+                    dedupe_tile_kernel<K, PW, true, TILE_R_SMALL, TILE_SMALL_BLOCKS><<<nparts, TILE_THREADS, 0, s>>>(
+                        small_tiles(single_source(part)), out, p0, sink0, nx);
+                    dedupe_tile_kernel<K, PW, true><<<ctx->sm_count * 10, TILE_THREADS, 0, s>>>(
+                        large_tiles(single_source(part), ts), out, p0, sink0, nx);
+                    tt.launches++;
+                } else {
+                    dedupe_tile_kernel<K, PW, true><<<nparts, TILE_THREADS, 0, s>>>(single_source(part), out, p0, sink0, nx);
+                }
             } else {
-                dedupe_tile_kernel<K, PW, false><<<nparts, TILE_THREADS, 0, s>>>(single_source(part), out, p0, sink0, NextPass{});
+                if (tile_split_enabled(nparts)) {
+                    TileSplit ts;
+                    FQD_TRY(tile_split_prepare(ctx, part, ts, tt));
+                    dedupe_tile_kernel<K, PW, false, TILE_R_SMALL, TILE_SMALL_BLOCKS><<<nparts, TILE_THREADS, 0, s>>>(
+                        small_tiles(single_source(part)), out, p0, sink0, NextPass{});
+                    dedupe_tile_kernel<K, PW, false><<<ctx->sm_count * 10, TILE_THREADS, 0, s>>>(
+                        large_tiles(single_source(part), ts), out, p0, sink0, NextPass{});
+                    tt.launches++;
+                } else {
+                    dedupe_tile_kernel<K, PW, false><<<nparts, TILE_THREADS, 0, s>>>(single_source(part), out, p0, sink0, NextPass{});
+                }
             }
             tt.launches++;
             FQD_CUDA(cudaGetLastError());
@@ -777,7 +829,16 @@ int stage_passes(fqd_context *ctx, const DeviceJob &job, const Codec &codec, con
                 tt.launches++;
             }
             FQD_CUDA(cudaEventRecord(cev[2 * j], s));
-            bucket_tile_kernel<K, PW><<<qp.nparts, TILE_THREADS, 0, s>>>(single_source(qp), pp, sink);
+            if (tile_split_enabled(qp.nparts)) {
+                TileSplit ts;
+                FQD_TRY(tile_split_prepare(ctx, qp, ts, tt));
+                bucket_tile_kernel<K, PW, TILE_R_SMALL, TILE_SMALL_BLOCKS><<<qp.nparts, TILE_THREADS, 0, s>>>(
+                    small_tiles(single_source(qp)), pp, sink);
+                bucket_tile_kernel<K, PW><<<ctx->sm_count * 10, TILE_THREADS, 0, s>>>(large_tiles(single_source(qp), ts), pp, sink);
+                tt.launches++;
+            } else {
+                bucket_tile_kernel<K, PW><<<qp.nparts, TILE_THREADS, 0, s>>>(single_source(qp), pp, sink);
+            }
             apply_edges_kernel<1><<<ctx->sm_count * 8, 256, 0, s>>>(single_edges(sink.edges, sink.n_edges, sink.cap), f.parent_full,
                                                                 f.parent_one, EdgeFlags{}, ctx->d_ctr);
             FQD_CUDA(cudaEventRecord(cev[2 * j + 1], s));
