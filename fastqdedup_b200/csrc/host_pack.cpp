@@ -265,6 +265,9 @@ Pool &pool()
 
 uint32_t packed_row_words(uint32_t key_length) { return (3u * key_length + 31u) / 32u; }
 
+// threads a pack_keys_parallel call runs on (the pool's workers + the caller)
+int pack_threads() { return pool().size() + 1; }
+
 // rows [0, n) of `src` (L bytes each, `stride` apart) -> packed rows; returns the index of the first row holding a byte
 // outside ACGTN, or n
 uint64_t pack_keys_parallel(const uint8_t *src, uint64_t n, uint32_t L, uint32_t stride, uint32_t *dst)

@@ -269,7 +269,7 @@ int launch_packed_chunks(fqd_context *ctx, const DeviceJob &job, const IngestPar
         ctx->chunk_events.push_back(e);
     }
     // raw chunks need the caller's buffer to be page-locked (a pageable source makes the copy synchronous and slow)
-    bool hybrid = !(getenv("FQD_HOST_PACK_HYBRID") && atoi(getenv("FQD_HOST_PACK_HYBRID")) == 0) && nchunks > 2;
+    bool hybrid = !(getenv("FQD_HOST_PACK_HYBRID") && atoi(getenv("FQD_HOST_PACK_HYBRID")) == 0) && nchunks > 1;
     if (hybrid) {
         cudaPointerAttributes at{};
         hybrid = cudaPointerGetAttributes(&at, job.host_keys) == cudaSuccess && at.type == cudaMemoryTypeHost;
@@ -282,7 +282,9 @@ int launch_packed_chunks(fqd_context *ctx, const DeviceJob &job, const IngestPar
     using clock = std::chrono::steady_clock;
     auto now = [&] { return std::chrono::duration<double>(clock::now().time_since_epoch()).count(); };
     double link_free_at = now();                      // estimate of when the copies queued so far are done
-    double link_bps = 50e9, pack_s = 0.0;             // refined below from what this job measures
+    // priors, refined below from what this job measures: ~50 GB/s over the link, ~9 ns per row and packer thread
+    // (a rank of a sharded job only has its share of the cores: few threads, and most chunks travel raw)
+    double link_bps = 50e9, pack_s = (double)chunk * 9e-9 * (double)((L + 35u) / 36u) / (double)std::max(1, pack_threads());
     size_t packed_slot = 0, last_copy = (size_t)-1;
     double first_copy_t0 = 0.0;
     size_t first_copy_bytes = 0;
@@ -297,10 +299,9 @@ int launch_packed_chunks(fqd_context *ctx, const DeviceJob &job, const IngestPar
             }
             link_free_at = std::min(link_free_at, t);   // the link has drained
         }
-        // send raw when the link would run dry while this chunk is being packed (never the last chunk: its copy
-        // is the tail of the job, keep it short)
-        const double est_pack = pack_s > 0.0 ? pack_s * (double)cn / (double)chunk : 0.0;
-        const bool raw = hybrid && i + 1 < nchunks && (i == 0 || link_free_at - t < est_pack);
+        // send raw when the link would run dry while this chunk is being packed
+        const double est_pack = pack_s * (double)cn / (double)chunk;
+        const bool raw = hybrid && (i == 0 || link_free_at - t < est_pack);
         IngestParams cp = pp;
         cp.n = cn;
         cp.index_base = index_base + (uint32_t)c0;
@@ -320,7 +321,7 @@ int launch_packed_chunks(fqd_context *ctx, const DeviceJob &job, const IngestPar
             }
             t = now();
             const double took = (t - p0) * (double)chunk / (double)cn;
-            pack_s = pack_s > 0.0 ? 0.5 * (pack_s + took) : took;
+            pack_s = 0.5 * (pack_s + took);
             bytes = (size_t)cn * rw * 4;
             FQD_CUDA(cudaMemcpyAsync(dev + c0 * L, stage, bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
             FQD_CUDA(cudaEventRecord(ctx->pack_ev[slot], ctx->copy_stream));

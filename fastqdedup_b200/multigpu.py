@@ -14,6 +14,7 @@ plus the local index).  Two ways to drive the same native plan (``run_sharded`` 
 Host code here only splits arrays and stitches bitmaps.
 """
 import ctypes
+import os
 from ctypes import POINTER, byref, c_uint64, c_void_p
 
 import numpy as np
@@ -163,6 +164,10 @@ class ShardComm:
 
     def __init__(self, ctx, rank, world, unique_id: bytes):
         self.ctx, self.rank, self.world = ctx, rank, world
+        # the ranks of a box share its cores: the host-side key packer of a rank gets its share of them
+        # (read once, when the library first packs; an explicit FQD_PACK_THREADS wins)
+        local_world = int(os.environ.get("LOCAL_WORLD_SIZE", world) or world)
+        os.environ.setdefault("FQD_PACK_THREADS", str(max(1, (os.cpu_count() or 4) // max(1, local_world))))
         self.lib = _native.load()
         h = c_void_p()
         buf = (ctypes.c_uint8 * 128).from_buffer_copy(unique_id)

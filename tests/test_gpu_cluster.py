@@ -1,6 +1,8 @@
 """Parity of the CUDA clustering path (through the C ABI) with the CPU oracle and with the
 unmodified reference, on seeded inputs at sizes the checkers finish in seconds.
 Bit-exact: this is integer / byte / index work (the filter's doubles included)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -189,3 +191,41 @@ def test_pre_counted_records(gpu_ctx, oracle):
 def test_negative_distance_rejected(gpu_ctx):
     with pytest.raises(ValueError, match="non-negative"):
         cluster_keys([b"AC"], None, -1, False, "directional", context=gpu_ctx)
+
+
+@pytest.fixture
+def env():
+    """Set library switches for one test and restore them afterwards."""
+    saved = {}
+
+    def set_(**kv):
+        for k, v in kv.items():
+            saved.setdefault(k, os.environ.get(k))
+            os.environ[k] = str(v)
+    yield set_
+    for k, v in saved.items():
+        if v is None:
+            os.environ.pop(k, None)
+        else:
+            os.environ[k] = v
+
+
+@pytest.mark.parametrize("dense", [0, 1])
+@pytest.mark.parametrize("method", METHODS)
+def test_levenshtein_compare_kernels_agree_with_oracle(gpu_ctx, oracle, env, dense, method):
+    """Both compare kernels of the Levenshtein passes (per-entry walk, dense tiles) forced onto the same oracle-sized
+    inputs: short blocks with big buckets (24-nt keys, d = 2 and 3), truncated reads (ragged keys, PAD in play), and
+    keys beyond 31 / 63 symbols (64-bit diagonals, Myers fallback)."""
+    from dataclasses import replace
+    env(FQD_COMPARE_DENSE=dense)
+    cfg = replace(synth.CONFIGS["cfg4"].scaled(7000), truncate_frac=0.04, indel_rate=0.003)
+    keys, lens, quals = synth.SynthSource(cfg).reads()
+    for d in (1, 2, 3):
+        run_both(oracle.cluster, keys, None, d, True, method, 1.0, lengths=lens, ctx=gpu_ctx, tag=f"lev/dense{dense}/{method}/d{d}")
+    rng = np.random.default_rng(7 + dense)
+    for L in (40, 70):
+        base = rng.choice(list(b"ACGT"), size=(300, L)).astype(np.uint8)
+        reads = base[rng.integers(0, 300, size=3000)].copy()
+        hit = rng.random(reads.shape) < 0.01
+        reads[hit] = rng.choice(list(b"ACGTN"), size=int(hit.sum())).astype(np.uint8)
+        run_both(oracle.cluster, reads, None, 2, True, method, 1.0, ctx=gpu_ctx, tag=f"lev/dense{dense}/{method}/L{L}")

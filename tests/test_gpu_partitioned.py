@@ -2,6 +2,7 @@
 sized tiles, one thread block per tile -- for the exact dedupe and for the Hamming passes) forced
 onto small inputs with FQD_PARTITION_MIN, so the oracle can check it -- and its spill path /
 fallback to the single-table / counting-sort plan when a partition outgrows its tile."""
+import ctypes
 import os
 from dataclasses import replace
 
@@ -226,3 +227,75 @@ def test_more_oversize_partitions_than_a_launch_grid_has_rows(gpu_ctx):
     assert np.all(got.count == copies) and np.all(got.selected)
     assert np.array_equal(np.nonzero(got.keep_mask())[0], np.arange(n_keys))
     assert got.stats["plan_flags"] & 1
+
+
+@pytest.mark.parametrize("split", [0, 1])
+def test_tile_kernels_split_launches(gpu_ctx, oracle, split):
+    """The tile kernels as one full-size launch and as the small-tile + full-size pair (FQD_TILE_SPLIT), on inputs whose
+    tiles fall on both sides of the 384-record boundary (fill 70 %) and include oversize tiles (a key with 3000
+    copies): dedupe with fused pass 0, the pass-1 tiles it emits, and a d = 2 job with an ordinary third pass."""
+    os.environ["FQD_TILE_SPLIT"] = str(split)
+    os.environ["FQD_TILE_FILL_PCT"] = "70"
+    try:
+        for name, n, d in (("cfg5", 90000, 1), ("cfg3", 40000, 2)):
+            cfg = synth.CONFIGS[name].scaled(n)
+            keys, lens, quals = synth.SynthSource(cfg).reads()
+            keys = np.concatenate([keys, np.tile(keys[:1], (3000, 1))])
+            if quals is not None:
+                quals = np.concatenate([quals, np.tile(quals[:1], (3000, 1))])
+            for method in ("directional", "highest_count"):
+                want = oracle.cluster(keys, quals, d, False, method, cfg.max_average_error_rate)
+                got = cluster_keys(keys, quals, d, False, method, cfg.max_average_error_rate, context=gpu_ctx)
+                assert_same(got, want, f"split{split}/{name}/{method}")
+                assert got.stats["plan_flags"] & 1
+    finally:
+        del os.environ["FQD_TILE_SPLIT"]
+        del os.environ["FQD_TILE_FILL_PCT"]
+
+
+@pytest.mark.parametrize("hybrid", [0, 1])
+def test_host_jobs_packed_and_raw_chunks(gpu_ctx, oracle, hybrid):
+    """HOST jobs with fixed-length ACGTN keys: the keys cross PCIe packed by the host threads, or (hybrid) as a mix of
+    packed and raw ASCII chunks when the caller's buffer is page-locked; several 4 M-record chunks, the result must be
+    the device-resident one.  A foreign byte in a late chunk sends the job down the ASCII path with a grown alphabet."""
+    from fastqdedup_b200 import _native
+    from fastqdedup_b200._native import ClusterJob, METHODS as METHOD_IDS, MEM_HOST
+    from fastqdedup_b200.clustering import cluster_device
+    lib = _native.load()
+    os.environ["FQD_HOST_PACK_HYBRID"] = str(hybrid)
+    try:
+        n, L = 9_000_000, 12
+        cfg = synth.CONFIGS["cfg1"].scaled(n)
+        keys, _, _ = synth.SynthSource(cfg).reads()
+        for foreign in (False, True):
+            if foreign:
+                keys[n - 5, 3] = ord("R")
+            hptr = ctypes.c_void_p()
+            assert lib.fqd_host_alloc(n * L, ctypes.byref(hptr)) == 0
+            host = np.ctypeslib.as_array(ctypes.cast(hptr, ctypes.POINTER(ctypes.c_uint8)), shape=(n, L))
+            host[:] = keys
+            words = (n + 31) // 32
+            bm = np.zeros(words, dtype=np.uint32)
+            job = ClusterJob()
+            job.n_records = n
+            job.keys = hptr.value
+            job.key_stride = job.key_length = L
+            job.max_distance = 1
+            job.method = METHOD_IDS["directional"]
+            job.memory_space = MEM_HOST
+            job.max_average_error_rate = 1.0
+            job.phred_offset = 33
+            st = gpu_ctx.cluster(job, bm.ctypes.data)
+            dkeys = gpu_ctx.upload(keys)
+            dbm = gpu_ctx.device_alloc(words * 4)
+            ref = cluster_device(gpu_ctx, n, dkeys, L, max_distance=1, method="directional", bitmap_ptr=dbm)
+            want = gpu_ctx.download(dbm, words * 4, np.uint32)
+            gpu_ctx.device_free(dkeys)
+            gpu_ctx.device_free(dbm)
+            lib.fqd_host_free(hptr)
+            assert st.number_of_uniques == ref.number_of_uniques and st.number_selected == ref.number_selected
+            assert np.array_equal(bm, want), f"hybrid{hybrid}/foreign{foreign}"
+            if not foreign:
+                assert st.h2d_bytes < n * L          # packed rows (and, hybrid, some raw chunks) crossed PCIe
+    finally:
+        del os.environ["FQD_HOST_PACK_HYBRID"]
