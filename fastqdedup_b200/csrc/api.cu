@@ -322,7 +322,25 @@ struct Resolved {
     uint32_t len_min = 0, len_max = 0;
     uint32_t *host_bitmap = nullptr;   // where to copy the bitmap back to (HOST jobs)
     size_t bitmap_words = 0;
-    cudaEvent_t h0 = nullptr, h1 = nullptr;
+    cudaEvent_t h0 = nullptr, h1 = nullptr;   // owned: destroyed on every exit path of the callers
+    Resolved() = default;
+    Resolved(const Resolved &) = delete;
+    Resolved &operator=(const Resolved &) = delete;
+    ~Resolved() { drop_events(); }
+    void drop_events()
+    {
+        if (h0) cudaEventDestroy(h0);
+        if (h1) cudaEventDestroy(h1);
+        h0 = h1 = nullptr;
+    }
+    void clear()
+    {
+        drop_events();
+        dj = DeviceJob{};
+        len_min = len_max = 0;
+        host_bitmap = nullptr;
+        bitmap_words = 0;
+    }
 };
 
 int validate_job(const fqd_cluster_job *job)
@@ -468,8 +486,7 @@ int finish_job(fqd_context *ctx, Resolved &r, fqd_cluster_stats *stats)
         float t = 0.f;
         cudaEventElapsedTime(&t, r.h0, r.h1);
         stats->ms_h2d += t;
-        cudaEventDestroy(r.h0); cudaEventDestroy(r.h1);
-        r.h0 = r.h1 = nullptr;
+        r.drop_events();
     }
     return FQD_OK;
 }
@@ -634,8 +651,7 @@ static int cluster_sharded_common(fqd_context **ctxs, int n_local, Exchange *ex,
             }
             if (rc_local != FQD_OK) break;
             ctxs[i]->res = fqd_result{};
-            if (R[i].h0) { cudaEventDestroy(R[i].h0); cudaEventDestroy(R[i].h1); }
-            R[i] = Resolved{};
+            R[i].clear();
             rc_local = arena_reset(ctxs[i]);
             if (rc_local == FQD_OK) rc_local = resolve_job(ctxs[i], &jobs[i], keep_bitmaps ? keep_bitmaps[i] : nullptr, R[i]);
             if (rc_local == FQD_OK && jobs[i].n_records) { lmin = std::min(lmin, R[i].len_min); lmax = std::max(lmax, R[i].len_max); }

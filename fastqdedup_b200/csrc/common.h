@@ -195,6 +195,29 @@ inline uint32_t tile_partitions(uint64_t n)
 }
 
 // host_pack.cpp
+// A set of CUDA events that is destroyed on every exit path (the launch plans return early through FQD_TRY).
+struct EventSet {
+    std::vector<cudaEvent_t> ev;
+    EventSet() = default;
+    EventSet(const EventSet &) = delete;
+    EventSet &operator=(const EventSet &) = delete;
+    ~EventSet()
+    {
+        for (cudaEvent_t e : ev)
+            if (e) cudaEventDestroy(e);
+    }
+    cudaError_t create(size_t n)
+    {
+        ev.assign(n, nullptr);
+        for (auto &e : ev) {
+            const cudaError_t rc = cudaEventCreate(&e);
+            if (rc != cudaSuccess) return rc;
+        }
+        return cudaSuccess;
+    }
+    cudaEvent_t &operator[](size_t i) { return ev[i]; }
+};
+
 uint32_t packed_row_words(uint32_t key_length);
 uint64_t pack_keys_parallel(const uint8_t *src, uint64_t n, uint32_t L, uint32_t stride, uint32_t *dst);
 int pack_threads();

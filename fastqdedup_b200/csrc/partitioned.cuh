@@ -826,7 +826,6 @@ struct EdgeFlags {
     int any_edge;         // highest_count: `linked` for every edge
 };
 
-template <int APPLY_UNROLL = 1>   // (unused: kept so that the launch sites read the same)
 static __global__ void __launch_bounds__(256) apply_edges_kernel(const __grid_constant__ EdgeSource E, uint32_t *parent_full,
                                                                  uint32_t *parent_one, const __grid_constant__ EdgeFlags F,
                                                                  DevCounters *ctr)

@@ -742,8 +742,8 @@ int stage_passes(fqd_context *ctx, const DeviceJob &job, const Codec &codec, con
     pp.dominated = f.dominated; pp.dead = f.dead;
     pp.edges = f.edges; pp.edge_cap = f.edge_cap; pp.ctr = ctx->d_ctr;
     for (int i = 0; i < 256; i++) pp.rank_of_code[i] = codec.rank[i];
-    std::vector<cudaEvent_t> cev(2 * npass);
-    for (auto &e : cev) FQD_CUDA(cudaEventCreate(&e));
+    EventSet cev;   // per pass: before / after the compare
+    FQD_CUDA(cev.create((size_t)2 * npass));
 
     // Hamming passes of large jobs: partition by the block hash, multimap in L2 (partitioned.cuh)
     bool use_part = false;
@@ -840,7 +840,7 @@ int stage_passes(fqd_context *ctx, const DeviceJob &job, const Codec &codec, con
             } else {
                 bucket_tile_kernel<K, PW><<<qp.nparts, TILE_THREADS, 0, s>>>(single_source(qp), pp, sink);
             }
-            apply_edges_kernel<1><<<ctx->sm_count * 8, 256, 0, s>>>(single_edges(sink.edges, sink.n_edges, sink.cap), f.parent_full,
+            apply_edges_kernel<<<ctx->sm_count * 8, 256, 0, s>>>(single_edges(sink.edges, sink.n_edges, sink.cap), f.parent_full,
                                                                 f.parent_one, EdgeFlags{}, ctx->d_ctr);
             FQD_CUDA(cudaEventRecord(cev[2 * j + 1], s));
             FQD_CUDA(cudaGetLastError());
@@ -903,7 +903,6 @@ int stage_passes(fqd_context *ctx, const DeviceJob &job, const Codec &codec, con
         cudaEventElapsedTime(&t, cev[2 * j], cev[2 * j + 1]);
         tt.compare += t;
     }
-    for (auto &e : cev) cudaEventDestroy(e);
     return FQD_OK;
 }
 
@@ -1024,7 +1023,7 @@ int run_typed(fqd_context *ctx, const DeviceJob &job, const Codec &codec, fqd_cl
     FQD_CUDA(cudaEventRecord(ev[6], s));
     int first_pass = 0;
     if (fp.done && U > 1) {
-        apply_edges_kernel<1><<<ctx->sm_count * 8, 256, 0, s>>>(single_edges(fp.edges, fp.aux, fp.edge_cap), f.parent_full, f.parent_one,
+        apply_edges_kernel<<<ctx->sm_count * 8, 256, 0, s>>>(single_edges(fp.edges, fp.aux, fp.edge_cap), f.parent_full, f.parent_one,
                                                             EdgeFlags{}, ctx->d_ctr);
         tt.launches++;
         tt.pass0_fused = true;
@@ -1155,7 +1154,9 @@ int run_sharded_typed(std::vector<Shard> &S, Exchange *ex, int world, const Code
     constexpr int KW = K * PW, RW = slot_words(KW);
     const int L = (int)S.size();               // shards driven by this process
     auto rank_of = [&](int i) { return ex ? ex->rank : i; };
-    std::vector<cudaEvent_t> e0(L), e1(L);
+    EventSet e0, e1;   // per local rank: start / end of the job on its stream
+    e0.ev.assign(L, nullptr);
+    e1.ev.assign(L, nullptr);
     // FQD_TRACE=1: host wall-clock per phase (every phase ends synchronised)
     const bool trace = getenv("FQD_TRACE") && rank_of(0) == 0;
     auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
@@ -1169,6 +1170,7 @@ int run_sharded_typed(std::vector<Shard> &S, Exchange *ex, int world, const Code
     };
 
     // ---- phase 1: local dedupe ----
+    int rc_local = FQD_OK;
     for (int i = 0; i < L; i++) {
         Shard &sh = S[i];
         FQD_CUDA(cudaSetDevice(sh.ctx->device));
@@ -1177,26 +1179,38 @@ int run_sharded_typed(std::vector<Shard> &S, Exchange *ex, int world, const Code
         FQD_CUDA(cudaEventCreate(&e0[i])); FQD_CUDA(cudaEventCreate(&e1[i]));
         FQD_CUDA(cudaEventRecord(e0[i], sh.ctx->stream));
         uint32_t unk[8] = {};
-        FQD_TRY(stage_dedupe<K, PW>(sh.ctx, sh.job, codec, sh.index_base, true, sh.st, unk, sh.local, sh.tt));
+        // a failure of the local stage (arena, spill overflow, unsupported key) must not return before the exchange
+        // below: the other ranks would wait in it forever.  It travels in the agreement vector instead.
+        const int rc = stage_dedupe<K, PW>(sh.ctx, sh.job, codec, sh.index_base, true, sh.st, unk, sh.local, sh.tt);
+        if (rc != FQD_OK && rc_local == FQD_OK) rc_local = rc;
         for (int k = 0; k < 8; k++) unknown_out[k] |= unk[k];
     }
-    // error / alphabet agreement across ranks: [bad_record, bad_char, unknown x8]
+    // error / alphabet agreement across ranks: [bad_record, bad_char, unknown x8, status of the local stage]
     {
-        std::vector<std::vector<uint64_t>> mine(L, std::vector<uint64_t>(10));
+        constexpr int AW = 11;
+        std::vector<std::vector<uint64_t>> mine(L, std::vector<uint64_t>(AW));
         for (int i = 0; i < L; i++) {
             mine[i][0] = S[i].st->bad_record;
             mine[i][1] = S[i].st->bad_char;
             for (int k = 0; k < 8; k++) mine[i][2 + k] = unknown_out[k];
+            mine[i][10] = (uint64_t)(int64_t)rc_local;
         }
         std::vector<uint64_t> all;
-        FQD_TRY(gather_host_u64(S, ex, world, 10, mine, all));
+        FQD_TRY(gather_host_u64(S, ex, world, AW, mine, all));
         uint64_t bad = ~0ull, bad_char = 0;
         bool any_unknown = false;
         for (int g = 0; g < world; g++) {
-            if (all[(size_t)g * 10] < bad) { bad = all[(size_t)g * 10]; bad_char = all[(size_t)g * 10 + 1]; }
+            const int rc_g = (int)(int64_t)all[(size_t)g * AW + 10];
+            if (rc_g != FQD_OK) {   // every rank leaves here, with the same status
+                if (rc_local == FQD_OK) set_error("rank %d failed in its local dedupe stage (status %d)", g, rc_g);
+                return rc_local != FQD_OK ? rc_local : rc_g;
+            }
+        }
+        for (int g = 0; g < world; g++) {
+            if (all[(size_t)g * AW] < bad) { bad = all[(size_t)g * AW]; bad_char = all[(size_t)g * AW + 1]; }
             for (int k = 0; k < 8; k++) {
-                unknown_out[k] |= (uint32_t)all[(size_t)g * 10 + 2 + k];
-                any_unknown |= all[(size_t)g * 10 + 2 + k] != 0;
+                unknown_out[k] |= (uint32_t)all[(size_t)g * AW + 2 + k];
+                any_unknown |= all[(size_t)g * AW + 2 + k] != 0;
             }
         }
         if (bad != ~0ull) {
@@ -1511,7 +1525,6 @@ int run_sharded_typed(std::vector<Shard> &S, Exchange *ex, int world, const Code
         st->plan_flags = (sh.tt.partitioned ? FQD_PLAN_DEDUPE_PARTITIONED : 0u) | (sh.tt.passes_partitioned ? FQD_PLAN_PASSES_PARTITIONED : 0u);
         st->ms_partition_kernel = sh.tt.partitioned ? sh.tt.ingest_kernel : 0.f;
         st->ms_dedupe_kernel = sh.tt.dedupe_kernel;
-        cudaEventDestroy(e0[i]); cudaEventDestroy(e1[i]);
     }
     {
         std::vector<std::vector<uint64_t>> mine(L, std::vector<uint64_t>(1));

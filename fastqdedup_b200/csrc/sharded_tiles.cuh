@@ -600,7 +600,7 @@ int run_sharded_tiles(std::vector<Shard> &S, Exchange *ex, const ShardWorld &W, 
                     for (int g = 0; g < G; g++) { es.edges[g] = reinterpret_cast<const uint2 *>(peer_ptr(sh, g, t.edges)); es.cap[g] = cap_e; }
                     es.n_edges = t.gath_in + 4; es.n_stride = 1; es.G = (uint32_t)G; es.self = (uint32_t)r; es.id_stride = U_max;
                     EdgeFlags ef{sh.f.dominated, sh.f.dead, t.linked, method == METHOD_HIGHEST ? 1 : 0};
-                    apply_edges_kernel<1><<<sh.ctx->sm_count * 4, 256, 0, sh.ctx->copy_stream>>>(es, sh.f.parent_full, sh.f.parent_one, ef,
+                    apply_edges_kernel<<<sh.ctx->sm_count * 4, 256, 0, sh.ctx->copy_stream>>>(es, sh.f.parent_full, sh.f.parent_one, ef,
                                                                                            sh.ctx->d_ctr);
                     FQD_CUDA(cudaGetLastError());
                     FQD_CUDA(cudaEventRecord(t.ev_join, sh.ctx->copy_stream));
@@ -652,11 +652,8 @@ int run_sharded_tiles(std::vector<Shard> &S, Exchange *ex, const ShardWorld &W, 
             es.n_edges = t.gath; es.n_stride = 4; es.G = (uint32_t)G; es.self = (uint32_t)rank_of(i); es.id_stride = U_max;
             es.first = early_first[i]; es.first_stride = early_stride;   // (what the overlapped launch has taken care of)
             EdgeFlags ef{sh.f.dominated, sh.f.dead, t.linked, method == METHOD_HIGHEST ? 1 : 0};
-            if (getenv("FQD_X_NOFLAGS")) ef = EdgeFlags{};   // (measurement only: wrong results)
-            if (npass_all && getenv("FQD_X_UNROLL4"))
-                apply_edges_kernel<4><<<sh.ctx->sm_count * 8, 256, 0, sh.ctx->stream>>>(es, sh.f.parent_full, sh.f.parent_one, ef, sh.ctx->d_ctr);
-            else if (npass_all)
-                apply_edges_kernel<1><<<sh.ctx->sm_count * 8, 256, 0, sh.ctx->stream>>>(es, sh.f.parent_full, sh.f.parent_one, ef, sh.ctx->d_ctr);
+            if (npass_all)
+                apply_edges_kernel<<<sh.ctx->sm_count * 8, 256, 0, sh.ctx->stream>>>(es, sh.f.parent_full, sh.f.parent_one, ef, sh.ctx->d_ctr);
             if (early_first[i]) FQD_CUDA(cudaStreamWaitEvent(sh.ctx->stream, t.ev_join, 0));
             sh.tt.launches++;
             FQD_CUDA(cudaGetLastError());
