@@ -696,6 +696,7 @@ struct PassParams {
     const uint32_t *U_dev = nullptr;   // when set: the unique count on the device (U is then an upper bound)
     uint32_t nb_mask;
     uint32_t *cnt;          // NB+1 counters -> exclusive offsets after the scan
+    uint32_t *fill;         // thin entries: 2 * NB cursors -- builds fill a bucket from the front, probes from the back
     uint32_t *rank;         // U*V
     uint2 *entries;         // thin {tag, uid|flags} entries (Levenshtein passes)
     uint32_t *fat;          // fat {key, count, uid|flags} entries (Hamming passes)
@@ -784,7 +785,10 @@ static __global__ void __launch_bounds__(256) scatter_kernel(const __grid_consta
         pass_variant<K, PW>(key, len, P, v, sig, build);
         const uint32_t b = (uint32_t)sig & P.nb_mask;
         const uint32_t lo = P.cnt[b], hi = P.cnt[b + 1];
-        const uint32_t pos = lo + r;
+        // builds first: a pair needs at least one build entry, so behind a probe entry nothing of its bucket pairs
+        // with it -- the compare kernels drop probe rows at once and the lanes of a warp that work are (nearly) all
+        // build rows with every column behind them live (ncu before: 11 of 32 lanes per instruction)
+        const uint32_t pos = build ? lo + atomicAdd(P.fill + 2u * b, 1u) : hi - 1u - atomicAdd(P.fill + 2u * b + 1u, 1u);
         uint32_t meta = u | (build ? ENT_BUILD : 0u) | (pos + 1 == hi ? ENT_LAST : 0u);
         P.entries[pos] = make_uint2((uint32_t)(sig >> 32), meta);
     }
@@ -831,7 +835,7 @@ static __global__ void __launch_bounds__(256) compare_kernel(const __grid_consta
     uint32_t merges = 0, cand = 0;
     if (i < P.cnt[P.nb_mask + 1]) {   // cnt[NB] = number of entries after the scan
         const uint2 e = P.entries[i];
-        if (!(e.y & ENT_LAST)) {
+        if (!(e.y & ENT_LAST) && (e.y & ENT_BUILD)) {   // (builds come first in a bucket: behind a probe entry only probes)
             const uint32_t ui = e.y & ENT_UID;
             bool loaded = false;
             Key<K, PW> ki;
@@ -899,7 +903,8 @@ static __global__ void __launch_bounds__(dense_warps<K * PW>() * 32) compare_den
         const uint32_t i = row0 + lane;
         const uint2 e = i < E ? P.entries[i] : make_uint2(0u, ENT_LAST);
         const uint32_t ui = e.y & ENT_UID;
-        bool ended = (e.y & ENT_LAST) != 0;    // nothing follows the last entry of a bucket
+        // nothing follows the last entry of a bucket, and (builds first) nothing behind a probe entry pairs with it
+        bool ended = (e.y & ENT_LAST) != 0 || !(e.y & ENT_BUILD);
         Key<K, PW> ki;
 #pragma unroll
         for (int w = 0; w < KW; w++) ki.w[w] = 0;

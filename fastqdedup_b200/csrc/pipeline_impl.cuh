@@ -767,16 +767,17 @@ int stage_passes(fqd_context *ctx, const DeviceJob &job, const Codec &codec, con
     // legacy plan (small jobs, Levenshtein, skewed buckets): counting sort by block hash + compare
     uint32_t NB = 1024;
     while (NB < (1u << 24) && NB < E / 2) NB <<= 1;
-    uint32_t *cnt = nullptr, *rank_arr = nullptr, *entries = nullptr, *block_sums = nullptr, *grand = nullptr;
+    uint32_t *cnt = nullptr, *fill = nullptr, *rank_arr = nullptr, *entries = nullptr, *block_sums = nullptr, *grand = nullptr;
     auto legacy_alloc = [&]() -> int {
         if (cnt) return FQD_OK;
         FQD_TRY(arena(ctx, (size_t)NB + 1, &cnt));
         FQD_TRY(arena(ctx, E, &rank_arr));
+        if (!fat) FQD_TRY(arena(ctx, (size_t)2 * NB, &fill));
         FQD_TRY(arena(ctx, fat ? E * FW : E * 2, &entries));
         FQD_TRY(arena(ctx, (size_t)cdiv(NB, SCAN_TILE) + 16, &block_sums));
         FQD_TRY(arena(ctx, 4, &grand));
         pp.nb_mask = NB - 1;
-        pp.cnt = cnt; pp.rank = rank_arr; pp.entries = reinterpret_cast<uint2 *>(entries); pp.fat = entries;
+        pp.cnt = cnt; pp.fill = fill; pp.rank = rank_arr; pp.entries = reinterpret_cast<uint2 *>(entries); pp.fat = entries;
         return FQD_OK;
     };
     auto legacy_pass = [&](int j) -> int {
@@ -788,16 +789,20 @@ int stage_passes(fqd_context *ctx, const DeviceJob &job, const Codec &codec, con
         sig_count_kernel<K, PW><<<cdiv(U, 256), 256, 0, s>>>(pp);
         FQD_TRY(exclusive_scan_inplace(ctx, cnt, NB, block_sums, grand));
         if (fat) scatter_fat_kernel<K, PW><<<cdiv(U, 256), 256, 0, s>>>(pp);
-        else scatter_kernel<K, PW><<<cdiv(U, 256), 256, 0, s>>>(pp);
+        else {
+            FQD_CUDA(cudaMemsetAsync(fill, 0, (size_t)2 * NB * 4, s));
+            scatter_kernel<K, PW><<<cdiv(U, 256), 256, 0, s>>>(pp);
+        }
         pp.n_entries = (uint32_t)E;   // upper bound; the kernel stops at cnt[NB]
         tt.launches += 6;             // sig_count, 3 scan kernels, scatter, compare
         FQD_CUDA(cudaEventRecord(cev[2 * j], s));
         if (fat) compare_fat_kernel<K, PW><<<cdiv(E, 256), 256, 0, s>>>(pp);
         else {
-            // big buckets (short blocks: many keys per block value) take the dense tiles, small ones the per-entry walk
-            // (measured on config 4, 1.6 M keys of 24 nt: d = 2 / 8-nt blocks 24 vs 32 ms, d = 1 / 12-nt blocks 1.7 vs 1.0 ms)
+            // very big buckets (short blocks: hundreds of keys per block value) take the dense tiles, the rest the
+            // per-entry walk.  Measured on config 4 (1.6 M keys of 24 nt), builds first in every bucket: d = 2 / 8-nt
+            // blocks, ~73 entries per bucket: walk 6.3 ms, dense 6.6 ms of compare; d = 1 / 12-nt blocks: 0.27 vs 0.46 ms
             const double block_values = std::pow(4.0, std::min<double>(pp.fix_bl, 20.0));
-            bool dense = (double)E > 8.0 * block_values;
+            bool dense = (double)E > 256.0 * block_values;
             if (const char *e = getenv("FQD_COMPARE_DENSE")) dense = atoi(e) != 0;   // measurement switch
             if (dense) compare_dense_kernel<K, PW><<<cdiv(E, 32u * dense_warps<KW>()), 32 * dense_warps<KW>(), 0, s>>>(pp);
             else compare_kernel<K, PW><<<cdiv(E, 256), 256, 0, s>>>(pp);
