@@ -488,7 +488,8 @@ def run_ours(args, rank, world, local_rank):
     dom = max(kernels, key=lambda k: k["ms"])
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tpath):
+    from fastqdedup_b200 import synth as _synth
+    if os.path.exists(tpath) and cfg.n_reads == _synth.CONFIGS[cfg.name].n_reads:   # (captured at the config's full size)
         try:
             for name, val in json.load(open(tpath)).get(cfg.name, {}).items():
                 if dom["kernel"].startswith(name):
