@@ -548,7 +548,7 @@ def run_ours(args, rank, world, local_rank):
         "e2e": {"value": U / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * e2e_s,
                 "steps": e2e_steps, "h2d_ms": est.ms_h2d, "host_input_bytes_per_step": int(host_in),
-                "host_packing": "keys packed to 3 bits/symbol by the library's host threads inside the timed region"
+                "host_packing": "keys packed to 3 bits/symbol (plane streams per chunk) by the library's host threads inside the timed region, some chunks sent raw when the link would idle"
                                 if h2d < host_in else "none"},
         "gpu_launches": int(sum(s.launches for s in stats)),
         "clocks": clocks,

@@ -221,6 +221,8 @@ struct EventSet {
 uint32_t packed_row_words(uint32_t key_length);
 uint64_t pack_keys_parallel(const uint8_t *src, uint64_t n, uint32_t L, uint32_t stride, uint32_t *dst);
 int pack_threads();
+uint64_t plane_stream_words(uint64_t n, uint32_t L);
+uint64_t pack_planes_parallel(const uint8_t *src, uint64_t n, uint32_t L, uint64_t *dst);
 
 // largest key (in symbols) this build can pack for a given number of code bits
 uint32_t max_supported_length(int bits);

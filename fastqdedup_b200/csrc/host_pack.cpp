@@ -101,9 +101,10 @@ template <uint32_t L>
 FQD_AVX512 size_t pack_rows_avx512_fixed(const uint8_t *src, size_t n, uint32_t stride, uint32_t *dst)
 {
     constexpr uint32_t RW = (3u * L + 31u) / 32u;
-    // table: index = byte & 63; the five letters map to themselves, everything else to 0xFF (never equal to the byte)
+    // table: index = byte & 63; the five letters map to themselves, every other entry to a value with other low bits
+    // than its index (so it never equals a byte that looks it up -- 0xFF as the filler would accept the byte 0xFF)
     alignas(64) uint8_t lut[64];
-    memset(lut, 0xFF, sizeof lut);
+    for (int i = 0; i < 64; i++) lut[i] = (uint8_t)(i ^ 1);   // never equal to a byte that indexes it (its low 6 bits are i)
     lut['A' & 63] = 'A'; lut['C' & 63] = 'C'; lut['G' & 63] = 'G'; lut['T' & 63] = 'T'; lut['N' & 63] = 'N';
     const __m512i table = _mm512_load_si512(lut);
     const __m512i b1 = _mm512_set1_epi8(0x02), b2 = _mm512_set1_epi8(0x04), b3 = _mm512_set1_epi8(0x08);
@@ -144,7 +145,7 @@ FQD_AVX512 size_t pack_rows_avx512(const uint8_t *src, size_t n, uint32_t L, uin
     default: break;
     }
     alignas(64) uint8_t lut[64];
-    memset(lut, 0xFF, sizeof lut);
+    for (int i = 0; i < 64; i++) lut[i] = (uint8_t)(i ^ 1);   // never equal to a byte that indexes it (its low 6 bits are i)
     lut['A' & 63] = 'A'; lut['C' & 63] = 'C'; lut['G' & 63] = 'G'; lut['T' & 63] = 'T'; lut['N' & 63] = 'N';
     const __m512i table = _mm512_load_si512(lut);
     const __m512i b1 = _mm512_set1_epi8(0x02), b2 = _mm512_set1_epi8(0x04), b3 = _mm512_set1_epi8(0x08);
@@ -262,6 +263,117 @@ Pool &pool()
 }
 
 }  // namespace
+
+// ---- plane streams of a whole chunk (what fqd_cluster sends over PCIe for HOST jobs) -------------------------------
+//
+// The row format above costs ~6 ns per 36-byte row and thread, most of it the per-row bit shuffling; 16 threads pack
+// 100 M keys in 54 ms, which made the PACKER the slower leg of a HOST job (the packed rows cross PCIe in 29 ms).  For
+// the library's own use the rows of a chunk are therefore treated as one stream of bytes (fixed-length rows back to
+// back): bit t of plane p = bit p+1 of byte t of the chunk.  One 64-byte load, three VPTESTMB and three 8-byte stores
+// per 64 symbols, validity by one VPERMB look-up -- no per-row work at all on the host, and 3 bits per symbol
+// exactly (13.5 bytes per 36-nt key instead of 16).  The GPU cuts a row's L bits out of each stream with a funnel
+// shift (partition_planes_kernel).
+
+namespace {
+
+constexpr size_t NO_BAD = ~(size_t)0;
+
+// vectors [v0, v1) of the stream of nbytes bytes; returns the index of the first byte outside ACGTN in them, or NO_BAD
+size_t planes_range_scalar(const uint8_t *src, size_t nbytes, size_t v0, size_t v1, uint64_t *p0, uint64_t *p1, uint64_t *p2)
+{
+    for (size_t v = v0; v < v1; v++) {
+        uint64_t m0 = 0, m1 = 0, m2 = 0;
+        const size_t lo = v * 64, hi = lo + 64 < nbytes ? lo + 64 : nbytes;
+        for (size_t t = lo; t < hi; t++) {
+            const uint8_t c = src[t];
+            if (c != 'A' && c != 'C' && c != 'G' && c != 'T' && c != 'N') return t;
+            m0 |= (uint64_t)((c >> 1) & 1u) << (t - lo);
+            m1 |= (uint64_t)((c >> 2) & 1u) << (t - lo);
+            m2 |= (uint64_t)((c >> 3) & 1u) << (t - lo);
+        }
+        p0[v] = m0; p1[v] = m1; p2[v] = m2;
+    }
+    return NO_BAD;
+}
+
+#if defined(__x86_64__)
+FQD_AVX512 size_t planes_range_avx512(const uint8_t *src, size_t nbytes, size_t v0, size_t v1, uint64_t *p0, uint64_t *p1, uint64_t *p2)
+{
+    alignas(64) uint8_t lut[64];
+    for (int i = 0; i < 64; i++) lut[i] = (uint8_t)(i ^ 1);   // never equal to a byte that indexes it (its low 6 bits are i)
+    lut['A' & 63] = 'A'; lut['C' & 63] = 'C'; lut['G' & 63] = 'G'; lut['T' & 63] = 'T'; lut['N' & 63] = 'N';
+    const __m512i table = _mm512_load_si512(lut);
+    const __m512i b1 = _mm512_set1_epi8(0x02), b2 = _mm512_set1_epi8(0x04), b3 = _mm512_set1_epi8(0x08);
+    const size_t full = nbytes / 64;   // vectors below this index are complete
+    size_t v = v0;
+    const size_t vfull = v1 < full ? v1 : full;
+    for (; v + 4 <= vfull; v += 4) {   // four independent vectors per step
+        __m512i x[4];
+        __mmask64 bad = 0;
+#pragma GCC unroll 4
+        for (int k = 0; k < 4; k++) x[k] = _mm512_loadu_si512(src + (v + k) * 64);
+#pragma GCC unroll 4
+        for (int k = 0; k < 4; k++) {
+            p0[v + k] = _mm512_test_epi8_mask(x[k], b1);
+            p1[v + k] = _mm512_test_epi8_mask(x[k], b2);
+            p2[v + k] = _mm512_test_epi8_mask(x[k], b3);
+            bad |= _mm512_cmpneq_epi8_mask(_mm512_permutexvar_epi8(x[k], table), x[k]);
+        }
+        if (bad) return planes_range_scalar(src, nbytes, v, v + 4, p0, p1, p2);   // (names the byte)
+    }
+    for (; v < v1; v++) {
+        const size_t off = v * 64;
+        const __mmask64 lanes = off + 64 <= nbytes ? ~0ull : ((1ull << (nbytes - off)) - 1ull);
+        const __m512i xv = _mm512_maskz_loadu_epi8(lanes, src + off);
+        p0[v] = _mm512_test_epi8_mask(xv, b1);
+        p1[v] = _mm512_test_epi8_mask(xv, b2);
+        p2[v] = _mm512_test_epi8_mask(xv, b3);
+        if (_mm512_mask_cmpneq_epi8_mask(lanes, _mm512_permutexvar_epi8(xv, table), xv))
+            return planes_range_scalar(src, nbytes, v, v + 1, p0, p1, p2);
+    }
+    return NO_BAD;
+}
+#endif
+
+size_t planes_range(const uint8_t *src, size_t nbytes, size_t v0, size_t v1, uint64_t *p0, uint64_t *p1, uint64_t *p2)
+{
+#if defined(__x86_64__)
+    static const bool fast = __builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512bw") &&
+                             __builtin_cpu_supports("avx512vbmi");
+    if (fast) return planes_range_avx512(src, nbytes, v0, v1, p0, p1, p2);
+#endif
+    return planes_range_scalar(src, nbytes, v0, v1, p0, p1, p2);
+}
+
+}  // namespace
+
+// 64-bit words one plane stream of n rows of L symbols takes, including the zero word behind it that lets the GPU
+// read "this word and the next" for the last row
+uint64_t plane_stream_words(uint64_t n, uint32_t L) { return (n * L + 63u) / 64u + 1u; }
+
+// rows [0, n) of `src` (L bytes each, back to back) -> three plane streams of plane_stream_words(n, L) words at dst,
+// dst + words, dst + 2 * words; returns the index of the first row holding a byte outside ACGTN, or n
+uint64_t pack_planes_parallel(const uint8_t *src, uint64_t n, uint32_t L, uint64_t *dst)
+{
+    const uint64_t words = plane_stream_words(n, L);
+    const size_t nbytes = (size_t)(n * L), nv = (nbytes + 63) / 64;
+    uint64_t *p0 = dst, *p1 = dst + words, *p2 = dst + 2 * words;
+    for (uint64_t w = nv; w < words; w++) p0[w] = p1[w] = p2[w] = 0;
+    Pool &p = pool();
+    const int parts = (int)std::min<uint64_t>((uint64_t)(p.size() + 1) * 4, std::max<uint64_t>(1, nv / 1024));
+    std::atomic<uint64_t> bad{(uint64_t)nbytes};
+    const std::function<void(int)> fn = [&](int part) {
+        const size_t v0 = nv * (size_t)part / parts, v1 = nv * (size_t)(part + 1) / parts;
+        const size_t b = planes_range(src, nbytes, v0, v1, p0, p1, p2);
+        if (b != NO_BAD) {
+            uint64_t cur = bad.load();
+            while (b < cur && !bad.compare_exchange_weak(cur, b)) {}
+        }
+    };
+    p.run(parts, fn);
+    const uint64_t b = bad.load();
+    return b == nbytes ? n : b / L;
+}
 
 uint32_t packed_row_words(uint32_t key_length) { return (3u * key_length + 31u) / 32u; }
 

@@ -271,59 +271,49 @@ static __global__ void __launch_bounds__(256) partition_dna_kernel(const __grid_
         if (go[r]) part_place(P.part, part[r], pos[r], e[r]);
 }
 
-// The same pass over keys the HOST has already packed (host_pack.cpp): a row is the three code-bit planes of the key
-// back to back, plane p in bits [p*L, (p+1)*L), in ceil(3L/32) words -- 16 bytes instead of 36 for the 36-nt
-// configs, which is what crosses PCIe.  The bytes were validated by the packer.
+// The same pass over keys the HOST has already packed (host_pack.cpp, pack_planes_parallel): the rows of a chunk back
+// to back form one stream of symbols, and the chunk arrives as three bit streams -- bit t of plane p is code bit p of
+// symbol t.  Row r owns bits [r * L, (r + 1) * L) of each stream: two 64-bit loads and one funnel shift per plane give
+// the plane-major key, 13.5 bytes instead of 36 for the 36-nt configs is what crossed PCIe, and the host did no
+// per-row work at all.  The bytes were validated by the packer.
 template <int PW, int NW>
-static __global__ void __launch_bounds__(256) partition_packed_kernel(const __grid_constant__ IngestParams P)
+static __global__ void __launch_bounds__(256) partition_planes_kernel(const __grid_constant__ IngestParams P)
 {
     constexpr int K = 3, KW = K * PW, ROWS = LEAN_ROWS;
-    constexpr uint32_t L = 4u * NW, RWP = (3u * L + 31u) / 32u;
+    constexpr uint32_t L = 4u * NW;
+    static_assert(L <= 64u && L <= 32u * PW, "a row's plane bits fit one 64-bit word and the key");
     static_assert(slot_words(KW) == PART_RW, "partitioned plan: 32-byte records");
-    __shared__ __align__(16) uint32_t stage[256 * ROWS * RWP];
     const uint32_t tid = threadIdx.x;
     const uint64_t t0 = (uint64_t)blockIdx.x * (256u * ROWS);
-    const uint32_t nblk = (uint32_t)min((uint64_t)(256u * ROWS), P.n - t0);
-    const uint32_t nwords = nblk * RWP;
-    const uint32_t *src = reinterpret_cast<const uint32_t *>(P.keys) + t0 * RWP;
-    if ((reinterpret_cast<uintptr_t>(src) & 15u) == 0 && (nwords & 3u) == 0) {
-        bulk_load_to_shared(stage, src, nwords * 4u);
-    } else {
-        for (uint32_t i = tid; i < nwords; i += 256) stage[i] = __ldcs(src + i);
-        __syncthreads();
-    }
+    const uint64_t *planes = reinterpret_cast<const uint64_t *>(P.keys);
+    constexpr uint64_t row_mask = L >= 64u ? ~0ull : ((1ull << L) - 1ull);
     uint32_t e[ROWS][PART_RW], part[ROWS], pos[ROWS];
     bool go[ROWS];
 #pragma unroll
     for (int r = 0; r < ROWS; r++) {
-        const uint32_t row = r * 256u + tid;
-        go[r] = row < nblk;
+        const uint64_t row = t0 + r * 256u + tid;
+        go[r] = row < P.n;
         if (!go[r]) continue;
-        uint32_t w[RWP + 1];
-#pragma unroll
-        for (uint32_t i = 0; i < RWP; i++) w[i] = stage[row * RWP + i];
-        w[RWP] = 0;
+        const uint64_t bit = row * L, w = bit >> 6;
+        const uint32_t sh = (uint32_t)(bit & 63u);
         Key<K, PW> key;
 #pragma unroll
-        for (int p = 0; p < K; p++)
+        for (int p = 0; p < K; p++) {
+            const uint64_t *pl = planes + (size_t)p * P.plane_words + w;
+            const uint64_t lo = __ldg(pl), hi = __ldg(pl + 1);   // (a zero word follows the stream)
+            const uint64_t bits = (sh ? (lo >> sh) | (hi << (64u - sh)) : lo) & row_mask;
+            key.w[p * PW] = (uint32_t)bits;
+            if constexpr (PW >= 2) key.w[p * PW + 1] = (uint32_t)(bits >> 32);
 #pragma unroll
-            for (int i = 0; i < PW; i++) {
-                const uint32_t at = (uint32_t)p * L + 32u * i;               // first bit of this plane word in the row
-                const uint32_t nb = L > 32u * i ? (L - 32u * i >= 32u ? 32u : L - 32u * i) : 0u;
-                uint32_t v = 0;
-                if (nb) {
-                    v = __funnelshift_r(w[at >> 5], w[(at >> 5) + 1 <= RWP ? (at >> 5) + 1 : RWP], at & 31u);
-                    if (nb < 32u) v &= (1u << nb) - 1u;
-                }
-                key.w[p * PW + i] = v;
-            }
+            for (int i = 2; i < PW; i++) key.w[p * PW + i] = 0u;
+        }
         const uint64_t h = P.part_blocks ? block0_hash(key, block_start(L, 1, P.part_blocks), PART_SALT | L) : hash_key(key);
 #pragma unroll
         for (int i = 0; i < PART_RW; i++) e[r][i] = 0;
 #pragma unroll
         for (int i = 0; i < KW; i++) e[r][i] = key.w[i];
         e[r][KW] = 1u;
-        e[r][KW + 1] = P.index_base + (uint32_t)(t0 + row);
+        e[r][KW + 1] = P.index_base + (uint32_t)row;
         part[r] = part_of(h, P.part.nparts);
         pos[r] = atomicAdd(P.part.cursor + part[r], 1u);
     }

@@ -265,6 +265,7 @@ struct IngestParams {
                                //    index must reach the key's owner rank), no fix-up phase
     DevCounters *ctr;
     Codec codec;
+    uint64_t plane_words = 0;  // partition_planes_kernel: 64-bit words per plane stream (`keys` points at plane 0)
 };
 
 // One probe reads a whole table record.  A 32-byte record is exactly one L2 sector and is

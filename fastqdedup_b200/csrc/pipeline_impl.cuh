@@ -233,12 +233,13 @@ inline EdgeSource single_edges(const uint2 *edges, const uint32_t *n_edges, uint
     return E;
 }
 
-// HOST jobs with fixed-length ACGTN rows: the host packs chunk i+1 (threads, AVX-512) while chunk i crosses PCIe at
-// 3 bits per symbol and the partition kernel unpacks the chunk before that.  RC_PACK_INVALID: a byte outside ACGTN
+// HOST jobs with fixed-length ACGTN rows: the host packs chunk i+1 (threads, AVX-512: three plane streams per chunk,
+// host_pack.cpp) while chunk i crosses PCIe at 3 bits per symbol and partition_planes_kernel unpacks the chunk before that.  RC_PACK_INVALID: a byte outside ACGTN
 // (the caller clears the partition buffers and takes the ASCII path, which reports it).
 //
-// Packing is the slower of the two legs on the hosts measured (16 threads pack 100 M x 36 nt in 54 ms; the packed
-// rows cross PCIe in 29 ms), so the link would idle half of the time.  Hybrid: whenever the copies queued so far
+// Packing is the slower of the two legs on the hosts measured (16 threads packed 100 M x 36 nt rows in 54 ms in the
+// per-row format of round 2's first version, ~40 ms as plane streams; the packed chunk crosses PCIe in 25 ms), so the
+// link would idle a good part of the time.  Hybrid: whenever the copies queued so far
 // would drain before the next chunk is packed, that chunk is sent as it is (ASCII, straight from the caller's
 // buffer -- no host work at all) and goes through the ASCII partition kernel; the packer threads never wait and the
 // link carries raw rows in what would be its idle time.  FQD_HOST_PACK_HYBRID=0 packs every chunk.
@@ -248,18 +249,20 @@ int launch_packed_chunks(fqd_context *ctx, const DeviceJob &job, const IngestPar
 {
     cudaStream_t s = ctx->stream;
     const uint64_t n = job.n;
-    const uint32_t L = job.key_len, rw = packed_row_words(L);
+    const uint32_t L = job.key_len;
     const uint64_t chunk = 4u << 20;   // records; a multiple of every block tile
     const size_t nchunks = (size_t)((n + chunk - 1) / chunk);
-    const size_t stage_bytes = (size_t)std::min<uint64_t>(chunk, n) * rw * 4;
+    // a chunk crosses PCIe as three plane streams (host_pack.cpp): 3 bits per symbol
+    const size_t full_stage = (size_t)3 * plane_stream_words(chunk, L) * 8;
+    const size_t stage_bytes = (size_t)3 * plane_stream_words(std::min<uint64_t>(chunk, n), L) * 8;
     if (ctx->pack_stage_bytes < stage_bytes) {
         for (int k = 0; k < 2; k++) {
             if (ctx->pack_stage[k]) FQD_CUDA(cudaFreeHost(ctx->pack_stage[k]));
             ctx->pack_stage[k] = nullptr;
         }
         ctx->pack_stage_bytes = 0;
-        for (int k = 0; k < 2; k++) FQD_CUDA(cudaHostAlloc(&ctx->pack_stage[k], (size_t)chunk * rw * 4, cudaHostAllocDefault));
-        ctx->pack_stage_bytes = (size_t)chunk * rw * 4;
+        for (int k = 0; k < 2; k++) FQD_CUDA(cudaHostAlloc(&ctx->pack_stage[k], full_stage, cudaHostAllocDefault));
+        ctx->pack_stage_bytes = full_stage;
     }
     for (int k = 0; k < 2; k++)
         if (!ctx->pack_ev[k]) FQD_CUDA(cudaEventCreateWithFlags(&ctx->pack_ev[k], cudaEventDisableTiming));
@@ -282,9 +285,9 @@ int launch_packed_chunks(fqd_context *ctx, const DeviceJob &job, const IngestPar
     using clock = std::chrono::steady_clock;
     auto now = [&] { return std::chrono::duration<double>(clock::now().time_since_epoch()).count(); };
     double link_free_at = now();                      // estimate of when the copies queued so far are done
-    // priors, refined below from what this job measures: ~50 GB/s over the link, ~9 ns per row and packer thread
+    // priors, refined below from what this job measures: ~50 GB/s over the link, ~6 ns per 36-nt row and packer thread
     // (a rank of a sharded job only has its share of the cores: few threads, and most chunks travel raw)
-    double link_bps = 50e9, pack_s = (double)chunk * 9e-9 * (double)((L + 35u) / 36u) / (double)std::max(1, pack_threads());
+    double link_bps = 50e9, pack_s = (double)chunk * 6e-9 * ((double)L / 36.0) / (double)std::max(1, pack_threads());
     size_t packed_slot = 0, last_copy = (size_t)-1;
     double first_copy_t0 = 0.0;
     size_t first_copy_bytes = 0;
@@ -301,7 +304,9 @@ int launch_packed_chunks(fqd_context *ctx, const DeviceJob &job, const IngestPar
         }
         // send raw when the link would run dry while this chunk is being packed
         const double est_pack = pack_s * (double)cn / (double)chunk;
-        const bool raw = hybrid && (i == 0 || link_free_at - t < est_pack);
+        const uint64_t words = plane_stream_words(cn, L);   // per plane
+        const bool tiny = (size_t)3 * words * 8 > (size_t)cn * L;   // (a handful of rows: the streams would not fit the chunk's range)
+        const bool raw = tiny || (hybrid && (i == 0 || link_free_at - t < est_pack));
         IngestParams cp = pp;
         cp.n = cn;
         cp.index_base = index_base + (uint32_t)c0;
@@ -313,19 +318,20 @@ int launch_packed_chunks(fqd_context *ctx, const DeviceJob &job, const IngestPar
         } else {
             const int slot = (int)(packed_slot++ & 1);
             if (packed_slot > 2) FQD_CUDA(cudaEventSynchronize(ctx->pack_ev[slot]));   // the copy out of this slot is done
-            uint32_t *stage = static_cast<uint32_t *>(ctx->pack_stage[slot]);
+            uint64_t *stage = static_cast<uint64_t *>(ctx->pack_stage[slot]);
             const double p0 = now();
-            if (pack_keys_parallel(job.host_keys + c0 * job.key_stride, cn, L, job.key_stride, stage) != cn) {
+            if (pack_planes_parallel(job.host_keys + c0 * job.key_stride, cn, L, stage) != cn) {   // (key_stride == L here)
                 FQD_CUDA(cudaStreamSynchronize(ctx->copy_stream));
                 return RC_PACK_INVALID;
             }
             t = now();
             const double took = (t - p0) * (double)chunk / (double)cn;
             pack_s = 0.5 * (pack_s + took);
-            bytes = (size_t)cn * rw * 4;
+            bytes = (size_t)3 * words * 8;
             FQD_CUDA(cudaMemcpyAsync(dev + c0 * L, stage, bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
             FQD_CUDA(cudaEventRecord(ctx->pack_ev[slot], ctx->copy_stream));
             cp.keys = dev + c0 * L;
+            cp.plane_words = words;
         }
         if (i == 0) { first_copy_t0 = t; first_copy_bytes = bytes; }
         link_free_at = std::max(link_free_at, t) + (double)bytes / link_bps;
@@ -334,7 +340,7 @@ int launch_packed_chunks(fqd_context *ctx, const DeviceJob &job, const IngestPar
         FQD_CUDA(cudaStreamWaitEvent(s, ctx->chunk_events[i], 0));
         last_copy = i;
         if (raw) launch_ascii(cp);
-        else partition_packed_kernel<PW, NW><<<cdiv(cn, 256 * LEAN_ROWS), 256, 0, s>>>(cp);
+        else partition_planes_kernel<PW, NW><<<cdiv(cn, 256 * LEAN_ROWS), 256, 0, s>>>(cp);
         tt.launches++;
     }
     FQD_CUDA(cudaGetLastError());

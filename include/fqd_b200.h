@@ -256,8 +256,9 @@ int fqd_fastq_emit(const char *const *in_paths, const char *const *out_paths, in
  * rows of key_length (<= 64) bytes over ACGTN, key_stride apart -> rows of ceil(3 * key_length / 32) uint32 words,
  * the three code-bit planes of the key back to back (plane p = bit p+1 of every ASCII byte, in bits
  * [p * key_length, (p+1) * key_length)).  Multithreaded (FQD_PACK_THREADS, default: all cores), AVX-512 when the CPU
- * has it.  fqd_cluster uses the same packer internally for HOST jobs with fixed-length keys, chunk by chunk ahead of
- * the PCIe copy.  FQD_ERR_UNSUPPORTED + *bad_record when a byte is outside ACGTN. */
+ * has it.  (fqd_cluster packs HOST jobs with fixed-length keys itself, chunk by chunk ahead of the PCIe copy, in a
+ * cheaper internal form: the rows of a chunk as three plane streams.)  FQD_ERR_UNSUPPORTED + *bad_record when a byte
+ * is outside ACGTN. */
 int fqd_pack_keys(const uint8_t *keys, uint64_t n_records, uint32_t key_length, uint32_t key_stride, uint32_t *packed,
                   uint64_t *bad_record);
 
