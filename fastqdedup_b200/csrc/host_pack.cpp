@@ -2,14 +2,16 @@
 // symbol instead of 8 ("pack keys in C straight from the parser's buffers").
 //
 // With the clustering at a few milliseconds, a job that starts from host buffers is bound by the PCIe copy of its
-// keys (100 M x 36 bytes: 65 of 71 ms).  A packed row is the key's three code-bit planes back to back -- plane p
-// (bit p+1 of every ASCII byte: A 0, C 1, T 2, G 3, N 7, the code of key.cuh) in bits [p*L, (p+1)*L) -- in
-// ceil(3L / 32) 32-bit words: 16 bytes for 36 symbols.  partition_packed_kernel (partitioned.cuh) unpacks it into
-// the plane-major key with a handful of funnel shifts.
+// keys (100 M x 36 bytes: 65 of 71 ms).  Two forms, both with the code of key.cuh (bit p+1 of every ASCII byte is
+// code bit p: A 0, C 1, T 2, G 3, N 7):
+//   * rows (fqd_pack_keys, the public utility): per key its three code-bit planes back to back -- plane p in bits
+//     [p*L, (p+1)*L) -- in ceil(3L / 32) 32-bit words, 16 bytes for 36 symbols;
+//   * plane streams (pack_planes_parallel, what fqd_cluster sends for HOST jobs): the rows of a chunk as one stream of
+//     symbols, three bit streams per chunk; partition_planes_kernel (partitioned.cuh) cuts a row out with funnel shifts.
 //
-// The packer is one AVX-512 step per row (masked 64-byte load, one VPTESTMB per plane gives the plane as a mask
-// register, one VPERMB table look-up validates all bytes at once) with a scalar fallback, run by a small pool of
-// threads over the rows of a chunk.  No CUDA here.
+// The row packer is one AVX-512 step per row (masked 64-byte load, one VPTESTMB per plane gives the plane as a mask
+// register, one VPERMB table look-up validates all bytes at once), the stream packer the same per 64 symbols with no
+// per-row work; scalar fallbacks; a small pool of threads over a chunk.  No CUDA here.
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
