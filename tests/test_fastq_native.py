@@ -150,3 +150,31 @@ def test_emit_matches_python_writer(tmp_path, n, frac):
     frontend.filter_fastq_files_on_bitmap([str(p1), str(p2)], [str(w1), str(w2)], keep)
     assert o1.read_bytes() == w1.read_bytes()
     assert gzip.decompress(o2.read_bytes()) == w2.read_bytes()       # gzip members differ, the bytes inside do not
+
+
+def test_records_across_chunk_boundaries_and_a_giant_record(tmp_path):
+    """The parser works in place on the reader's 8 MB chunks: a record cut by a chunk boundary is completed in the
+    next chunk's headroom, a record longer than the headroom (64 KB) takes the copying path.  ~40 MB of long records
+    (every chunk boundary cuts one) with a 300 kB record in the middle, scanned and emitted."""
+    rng = np.random.default_rng(77)
+    recs = random_records(rng, 24000, 800, 2400)
+    giant = "".join(rng.choice(list("ACGT"), 300_000))
+    recs.insert(12000, ("giant read", giant, "I" * len(giant)))
+    n = len(recs)
+    src = tmp_path / "long.fastq"
+    write_fastq(src, recs, final_newline=False)
+    with _native.FastqScan([str(src)], [slice(5, 905, 3)], want_quals=True) as scan:
+        assert scan.n_records == n
+        keys, quals = rows_of(scan.keys, n), rows_of(scan.quals, n)
+    for t in list(range(0, n, 97)) + [11999, 12000, 12001, n - 1]:
+        assert keys[t].decode() == recs[t][1][5:905:3], t
+        assert quals[t].decode() == recs[t][2][5:905:3], t
+    keep = rng.random(n) < 0.3
+    keep[12000] = True
+    words = np.packbits(keep, bitorder="little")
+    words = np.concatenate([words, np.zeros((-len(words)) % 4, dtype=np.uint8)]).view(np.uint32)
+    for out in (tmp_path / "out.fastq", tmp_path / "out.fastq.gz"):
+        _native.fastq_emit([str(src)], [str(out)], words, n)
+        data = gzip.open(out, "rb").read() if str(out).endswith(".gz") else open(out, "rb").read()
+        want = "".join(f"@{nm}\n{s}\n+\n{q}\n" for (nm, s, q), k in zip(recs, keep) if k).encode("latin-1")
+        assert data == want
